@@ -1,0 +1,147 @@
+/* libzkp_b200 -- C ABI of the B200-native prover hot path for interactive-zkp-study.
+ *
+ * The reference (tokamak-network/interactive-zkp-study) is pure Python and has no FFI; the seam
+ * is the set of Python callables listed in SURVEY.md section 8(a).  Each entry point below names
+ * the reference code it replaces (file:line under /root/reference).  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - Field elements cross the boundary as 32 bytes little-endian, canonical (in [0, modulus)),
+ *     NOT in Montgomery form.  Scalars (Fr) may be any 256-bit value; they are reduced mod r on
+ *     the device (zkp/plonk/field.py:88 does `scalar % CURVE_ORDER`).
+ *   - G1 affine point = x || y (64 B).  G2 affine point = x.c0 || x.c1 || y.c0 || y.c1 (128 B),
+ *     c0 + c1*u as in py_ecc FQ2.coeffs (plonk_serializers.py:56-57).
+ *   - The point at infinity (py_ecc `None`) is encoded as all-zero coordinates on input and
+ *     reported through `*out_is_inf = 1` (coordinates zeroed) on output.
+ *   - Every function returns 0 on success, a negative value on error; zkp_last_error() gives the
+ *     message of the last failure on the calling thread's process.  The caller owns all host
+ *     buffers; nothing is retained after return except through explicit handles.
+ *   - There is no CPU fallback: without an sm_100 device zkp_init fails and every other call
+ *     returns ZKP_ERR_NOT_INITIALISED.
+ *   - Entry points are serialised by an internal mutex (Flask's dev server is multi-threaded and
+ *     ctypes releases the GIL; app.py:1444).
+ */
+#ifndef ZKP_B200_H
+#define ZKP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKP_OK 0
+#define ZKP_ERR_CUDA (-1)
+#define ZKP_ERR_NOT_INITIALISED (-2)
+#define ZKP_ERR_INVALID_ARGUMENT (-3)
+#define ZKP_ERR_BAD_HANDLE (-4)
+#define ZKP_ERR_NOT_DIVISIBLE (-5)
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+/* device < 0: use $LOCAL_RANK if set, else 0.  Fails unless the device is compute capability 10.x. */
+int zkp_init(int device);
+int zkp_shutdown(void);
+const char* zkp_last_error(void);
+int zkp_device_info(char* name, int name_cap, int* sm_count, int* cc_major, int* cc_minor, int* sm_clock_khz);
+/* number of kernels this library has launched since zkp_init (bench.py "gpu_launches") */
+uint64_t zkp_launch_count(void);
+/* CUDA-event timer on the library's stream (the stream every kernel is launched on) */
+int zkp_timer_start(void);
+int zkp_timer_stop(float* elapsed_ms);
+int zkp_sync(void);
+
+/* ---- multi-scalar multiplication ------------------------------------------------------------
+ * sum_i scalars[i] * pts[i].  Replaces the scalar-mul loops of
+ *   kzg.commit            zkp/plonk/kzg.py:59-67            (G1)
+ *   proof_a / proof_c     zkp/groth16/proving.py:27-31,56-60,66-73   (G1)
+ *   proof_b               zkp/groth16/proving.py:39-43      (G2)
+ * i.e. py_ecc bn128.multiply + bn128.add per term.  Zero scalars and infinity points contribute
+ * nothing (kzg.py:62-63).  n == 0 yields infinity. */
+int zkp_g1_msm(const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t out_xy[64], int* out_is_inf);
+int zkp_g2_msm(const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t out_xy[128], int* out_is_inf);
+
+/* Device-resident static tables (srs.g1_powers, sigma1_2, sigma1_5, sigma2_2 are re-passed on every
+ * reference call; the host wrapper caches them by identity) and device-resident scalar vectors. */
+int zkp_g1_table_load(const uint8_t* pts, uint64_t n, uint64_t* handle);
+int zkp_g2_table_load(const uint8_t* pts, uint64_t n, uint64_t* handle);
+int zkp_scalars_load(const uint8_t* scalars, uint64_t n, uint64_t* handle);
+int zkp_free(uint64_t handle);
+/* points [offset, offset+n) of the table, scalars from the host (H2D inside the call) */
+int zkp_g1_msm_table(uint64_t table, uint64_t offset, const uint8_t* scalars, uint64_t n, uint8_t out_xy[64],
+                     int* out_is_inf);
+int zkp_g2_msm_table(uint64_t table, uint64_t offset, const uint8_t* scalars, uint64_t n, uint8_t out_xy[128],
+                     int* out_is_inf);
+/* everything resident: scalars [sc_offset, sc_offset+n) of a scalar handle */
+int zkp_g1_msm_dev(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n,
+                   uint8_t out_xy[64], int* out_is_inf);
+int zkp_g2_msm_dev(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n,
+                   uint8_t out_xy[128], int* out_is_inf);
+/* Shard form for the multi-GPU path: the un-normalised XYZZ partial sum of this rank's
+ * point range, 4 coordinates x 32 B Montgomery for G1 (128 B); combine folds `count` partials
+ * (gathered from all ranks) into the affine result. */
+int zkp_g1_msm_dev_partial(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n,
+                           uint8_t out_xyzz[128]);
+int zkp_g1_combine_partials(const uint8_t* partials, uint32_t count, uint8_t out_xy[64], int* out_is_inf);
+/* Window-width override for experiments (0 = automatic). */
+int zkp_msm_set_window_bits(int c);
+
+/* ---- fixed-base batch scalar multiplication (CRS generation) -------------------
+ * out[i] = scalars[i] * base.  Replaces SRS.generate (zkp/plonk/srs.py:78-82) and
+ * sigma12/sigma15/sigma22 (zkp/groth16/setup.py:18-23,56-60,64-69).  Result stays on the device
+ * as a table handle; zkp_table_download copies canonical affine points back. */
+int zkp_g1_fixed_base_mul(const uint8_t base_xy[64], const uint8_t* scalars, uint64_t n, uint64_t* out_table);
+int zkp_g2_fixed_base_mul(const uint8_t base_xy[128], const uint8_t* scalars, uint64_t n, uint64_t* out_table);
+int zkp_g1_fixed_base_mul_dev(const uint8_t base_xy[64], uint64_t scalars, uint64_t n, uint64_t* out_table);
+int zkp_table_download(uint64_t table, uint64_t offset, uint64_t n, uint8_t* out_pts);
+int zkp_scalars_download(uint64_t scalars, uint64_t offset, uint64_t n, uint8_t* out);
+
+/* ---- synthetic inputs (bench / large parity tests) --------------------------------
+ * Element i of stream `seed` is the first of 16 draws  v_t = mix(seed, 64*i + 4*t + j), j < 4 limbs
+ * (SplitMix64 finaliser), masked to 254 bits, that is < r; if none is, draw 15 minus r.
+ * oracle/synthetic.py restates it. */
+int zkp_scalars_generate(uint64_t seed, uint64_t n, uint64_t* handle);
+
+/* ---- Fr vectors: NTT and pointwise ops --------------------------------------------------------
+ * zkp_fr_ntt: in-place on a host buffer of n = 2^log_n elements, natural order in and out.
+ *   out[k] = sum_j in[j] * omega^(jk)                  replaces fft   zkp/plonk/polynomial.py:292-341
+ *   inverse != 0: uses omega^-1 and scales by n^-1      replaces ifft  zkp/plonk/polynomial.py:344-378
+ *   coset_shift != NULL: forward pre-scales in[j] *= k^j (coset_fft, zkp/plonk/utils.py:145-176);
+ *                        inverse post-scales out[j] *= k^-j (coset_ifft, zkp/plonk/utils.py:179-205).
+ * omega must be an element of order n (the reference passes get_root_of_unity(n) or its inverse). */
+int zkp_fr_ntt(uint8_t* data, uint32_t log_n, const uint8_t omega[32], int inverse, const uint8_t* coset_shift);
+int zkp_fr_ntt_dev(uint64_t scalars, uint64_t offset, uint32_t log_n, const uint8_t omega[32], int inverse,
+                   const uint8_t* coset_shift);
+
+/* op: 0 add, 1 sub, 2 mul (pointwise), out may alias a or b.  Polynomial.__add__/__sub__
+ * (polynomial.py:108-136) and the evaluation-form products behind the quotients. */
+int zkp_fr_vec_op(int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
+/* out[i] = a[i]^-1, inv(0) = 0 (py_ecc prime_field_inv) */
+int zkp_fr_batch_inverse(const uint8_t* a, uint64_t n, uint8_t* out);
+/* Horner evaluation p(x), Polynomial.evaluate zkp/plonk/polynomial.py:85-106 */
+int zkp_fr_poly_eval(const uint8_t* coeffs, uint64_t n, const uint8_t x[32], uint8_t out[32]);
+
+/* ---- quotients ----------------------------------------------------------------------------- */
+/* Groth16 hxr (zkp/groth16/poly_utils.py:116-125): P = a*b - c (len(a)=len(b)=len(c)=len),
+ * (H, rem) = P divmod Z with Z of z_len coefficients.  h_out: 2*len-1 - z_len + 1 elements,
+ * rem_out: z_len - 1 elements. */
+int zkp_groth16_quotient(const uint8_t* a, const uint8_t* b, const uint8_t* c, uint64_t len, const uint8_t* z,
+                         uint64_t z_len, uint8_t* h_out, uint8_t* rem_out);
+/* General product and exact/long division over Fr in coefficient form
+ * (Polynomial.__mul__ polynomial.py:144-159; poly_div polynomial.py:385-435). */
+int zkp_fr_poly_mul(const uint8_t* a, uint64_t a_len, const uint8_t* b, uint64_t b_len, uint8_t* out);
+int zkp_fr_poly_divmod(const uint8_t* a, uint64_t a_len, const uint8_t* b, uint64_t b_len, uint8_t* q_out,
+                       uint8_t* r_out);
+
+/* ---- diagnostics --------------------------------------------------------------------------- */
+/* Dependent-free integer-MAD microbenchmark: variant 0 = IMAD.WIDE.U32 (the roofline unit),
+ * 1 = IMAD (32-bit lo), 2 = IMAD.HI.  Returns G(limb-MAC)/s over the whole chip. */
+int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effective);
+/* Field-op self-test hooks used by tests/ (field: 0 = Fp, 1 = Fr; op: 0 add,1 sub,2 mul,3 inv,4 sqr) */
+int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
+/* out[i] = a[i] + b[i] on G1 (group: 0 = G1, 1 = G2) via XYZZ, result affine; exercises all edge cases */
+int zkp_dbg_point_add(int group, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKP_B200_H */

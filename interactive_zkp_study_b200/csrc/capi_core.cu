@@ -1,0 +1,388 @@
+// libzkp_b200: lifecycle, handles, timers, diagnostics.  See include/zkp_b200.h.
+#include <cstdlib>
+#include <cstring>
+#include "ec.cuh"
+#include "registry.cuh"
+
+namespace zkp {
+
+static Context g_ctx;
+static bool g_ready = false;
+static Registry g_registry;
+static std::mutex g_err_mu;
+static std::string g_last_error;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+
+Context& ctx() {
+  if (!g_ready) throw std::runtime_error("zkp_init has not been called successfully");
+  return g_ctx;
+}
+bool ctx_ready() { return g_ready; }
+Registry& registry() { return g_registry; }
+void set_last_error(const std::string& s) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_last_error = s;
+}
+
+// ------------------------------------------------------------------ integer-MAD microbenchmark
+// 8 independent dependent-chains per thread (the multiplicand of each MAD is the previous result,
+// so nothing can be hoisted), 256 threads x 8 blocks/SM: the FMA-pipe issue rate is the only limit.
+// VARIANT 0: mad.wide.u32 (IMAD.WIDE.U32, 32x32+64 -> 64: the roofline unit "limb-MAC")
+//         1: mad.lo.u32   (IMAD)
+//         2: mad.hi.u32   (IMAD.HI)
+//         3: Fp Montgomery multiplication chains (136 limb-MACs each): the practical ceiling
+static constexpr int PEAK_UNROLL = 16;
+template <int VARIANT>
+__global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters, uint32_t m0) {
+  uint32_t seed = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+  uint32_t b = m0 | 1u;
+  if (VARIANT == 3) {
+    Fp x, y;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      x.v[k] = seed + k * 0x9e3779b9u;
+      y.v[k] = (seed ^ 0x5bd1e995u) + k * 0x85ebca6bu;
+    }
+    x.v[7] &= 0x0fffffffu;
+    y.v[7] &= 0x0fffffffu;
+    for (int it = 0; it < iters; it++) {
+      x = x * y;
+      y = y * x;
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= x.v[k] ^ y.v[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    return;
+  }
+  unsigned long long acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = ((unsigned long long)(seed + k) << 32) | (seed * (k + 3));
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < PEAK_UNROLL; u++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (VARIANT == 0) {
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"((uint32_t)acc[k]), "r"(b));
+        } else if (VARIANT == 1) {
+          uint32_t x = (uint32_t)acc[k];
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(b), "r"(seed));
+          acc[k] = x;
+        } else {
+          uint32_t x = (uint32_t)acc[k];
+          asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(b), "r"(seed));
+          acc[k] = x;
+        }
+      }
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s ^= (uint32_t)acc[k] ^ (uint32_t)(acc[k] >> 32);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ------------------------------------------------------------------ debug kernels (tests only)
+template <class FE>
+__global__ void dbg_field_op_kernel(int op, const FE* a, const FE* b, uint64_t n, FE* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  FE x = a[i].to_mont(), y = b ? b[i].to_mont() : FE::zero(), r;
+  switch (op) {
+    case 0: r = x + y; break;
+    case 1: r = x - y; break;
+    case 2: r = x * y; break;
+    case 3: r = x.inv(); break;
+    default: r = x.sqr(); break;
+  }
+  out[i] = r.from_mont();
+}
+
+template <class F>
+__global__ void dbg_point_add_kernel(const Affine<F>* a, const Affine<F>* b, uint64_t n, Affine<F>* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> p = {a[i].x.to_mont(), a[i].y.to_mont()};
+  Affine<F> q = {b[i].x.to_mont(), b[i].y.to_mont()};
+  // exercise both the mixed and the full addition: (p as XYZZ) + q, then + infinity via add()
+  XYZZ<F> acc = XYZZ<F>::from_affine(p);
+  acc.madd(q);
+  XYZZ<F> z = XYZZ<F>::inf();
+  z.add(acc);
+  Affine<F> r = z.to_affine();
+  out[i] = {r.x.from_mont(), r.y.from_mont()};
+}
+
+// ------------------------------------------------------------------ synthetic scalars
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void scalars_generate_kernel(uint64_t seed, uint64_t n, uint32_t* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t v[8];
+  bool ok = false;
+  for (int t = 0; t < 16 && !ok; t++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint64_t w = mix64(seed + 64 * i + 4 * t + j);
+      v[2 * j] = (uint32_t)w;
+      v[2 * j + 1] = (uint32_t)(w >> 32);
+    }
+    v[7] &= 0x3fffffffu;  // 254 bits
+    // v < r ?
+    uint32_t borrow = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint64_t d = (uint64_t)v[k] - FrParams::MOD_(k) - borrow;
+      borrow = (uint32_t)(d >> 63);
+    }
+    ok = borrow != 0;
+  }
+  if (!ok) {  // 2^254 < 2r: one subtraction suffices
+    uint32_t borrow = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint64_t d = (uint64_t)v[k] - FrParams::MOD_(k) - borrow;
+      v[k] = (uint32_t)d;
+      borrow = (uint32_t)(d >> 63);
+    }
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + 8 * i);
+  o[0] = make_uint4(v[0], v[1], v[2], v[3]);
+  o[1] = make_uint4(v[4], v[5], v[6], v[7]);
+}
+
+}  // namespace zkp
+
+using namespace zkp;
+
+extern "C" {
+
+int zkp_init(int device) {
+  try {
+    if (g_ready) return ZKP_OK;
+    int count = 0;
+    CUDA_CHECK(cudaGetDeviceCount(&count));
+    if (count == 0) throw std::runtime_error("no CUDA device visible; libzkp_b200 has no CPU fallback");
+    if (device < 0) {
+      const char* lr = getenv("LOCAL_RANK");
+      device = lr ? atoi(lr) : 0;
+    }
+    if (device >= count) throw std::runtime_error("device index out of range");
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      throw std::runtime_error(std::string("libzkp_b200 is built for sm_100a only; device is ") + prop.name);
+    CUDA_CHECK(cudaSetDevice(device));
+    g_ctx.device = device;
+    g_ctx.sm_count = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreate(&g_ev0));
+    CUDA_CHECK(cudaEventCreate(&g_ev1));
+    g_ready = true;
+    return ZKP_OK;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return ZKP_ERR_CUDA;
+  }
+}
+
+int zkp_shutdown(void) {
+  if (!g_ready) return ZKP_OK;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  cudaSetDevice(g_ctx.device);
+  cudaStreamSynchronize(g_ctx.stream);
+  for (auto& kv : g_registry.items) kv.second->buf.release();
+  g_registry.items.clear();
+  return ZKP_OK;  // the context (stream, engines' workspaces) stays usable; nothing else to tear down
+}
+
+const char* zkp_last_error(void) {
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  copy = g_last_error;
+  return copy.c_str();
+}
+
+int zkp_device_info(char* name, int name_cap, int* sm_count, int* cc_major, int* cc_minor, int* sm_clock_khz) {
+  return guarded([&](Context& c) {
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, c.device));
+    if (name && name_cap > 0) {
+      strncpy(name, prop.name, name_cap - 1);
+      name[name_cap - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (sm_clock_khz) {
+      int khz = 0;
+      CUDA_CHECK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c.device));
+      *sm_clock_khz = khz;
+    }
+  });
+}
+
+uint64_t zkp_launch_count(void) { return g_ready ? g_ctx.launches : 0; }
+
+int zkp_timer_start(void) {
+  return guarded([&](Context& c) { CUDA_CHECK(cudaEventRecord(g_ev0, c.stream)); });
+}
+int zkp_timer_stop(float* elapsed_ms) {
+  return guarded([&](Context& c) {
+    CUDA_CHECK(cudaEventRecord(g_ev1, c.stream));
+    CUDA_CHECK(cudaEventSynchronize(g_ev1));
+    CUDA_CHECK(cudaEventElapsedTime(elapsed_ms, g_ev0, g_ev1));
+  });
+}
+int zkp_sync(void) {
+  return guarded([&](Context& c) { CUDA_CHECK(cudaStreamSynchronize(c.stream)); });
+}
+
+int zkp_free(uint64_t handle) {
+  return guarded([&](Context& c) {
+    auto it = registry().items.find(handle);
+    if (it == registry().items.end()) throw BadHandle("zkp_free: unknown handle");
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    it->second->buf.release();
+    registry().items.erase(it);
+  });
+}
+
+int zkp_scalars_load(const uint8_t* scalars, uint64_t n, uint64_t* handle) {
+  return guarded([&](Context& c) {
+    if (!handle || (n && !scalars)) throw InvalidArgument("zkp_scalars_load: null argument");
+    auto r = std::make_unique<Resource>();
+    r->kind = HandleKind::Scalars;
+    r->n = n;
+    r->buf.reserve(n ? n * 32 : 32);
+    if (n) CUDA_CHECK(cudaMemcpyAsync(r->buf.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    *handle = registry().put(std::move(r));
+  });
+}
+
+int zkp_scalars_generate(uint64_t seed, uint64_t n, uint64_t* handle) {
+  return guarded([&](Context& c) {
+    if (!handle) throw InvalidArgument("zkp_scalars_generate: null handle");
+    auto r = std::make_unique<Resource>();
+    r->kind = HandleKind::Scalars;
+    r->n = n;
+    r->buf.reserve(n ? n * 32 : 32);
+    if (n) {
+      scalars_generate_kernel<<<ceil_div(n, 256), 256, 0, c.stream>>>(seed, n, r->buf.as<uint32_t>());
+      CUDA_CHECK_LAUNCH();
+      c.launches++;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    *handle = registry().put(std::move(r));
+  });
+}
+
+int zkp_scalars_download(uint64_t scalars, uint64_t offset, uint64_t n, uint8_t* out) {
+  return guarded([&](Context& c) {
+    Resource* r = need(scalars, HandleKind::Scalars, "zkp_scalars_download");
+    if (offset + n > r->n) throw InvalidArgument("zkp_scalars_download: range out of bounds");
+    CUDA_CHECK(cudaMemcpyAsync(out, r->buf.as<uint8_t>() + offset * 32, n * 32, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effective) {
+  return guarded([&](Context& c) {
+    if (variant < 0 || variant > 3 || !gmacs_per_s) throw InvalidArgument("zkp_imad_peak: bad variant");
+    const int blocks = c.sm_count * 8, threads = 256;
+    const int iters = variant == 3 ? 2000 : 4000;
+    DevBuf out;
+    out.reserve((size_t)blocks * threads * 4);
+    auto launch = [&](int it) {
+      switch (variant) {
+        case 0: imad_peak_kernel<0><<<blocks, threads, 0, c.stream>>>(out.as<uint32_t>(), it, 0x12345677u); break;
+        case 1: imad_peak_kernel<1><<<blocks, threads, 0, c.stream>>>(out.as<uint32_t>(), it, 0x12345677u); break;
+        case 2: imad_peak_kernel<2><<<blocks, threads, 0, c.stream>>>(out.as<uint32_t>(), it, 0x12345677u); break;
+        default: imad_peak_kernel<3><<<blocks, threads, 0, c.stream>>>(out.as<uint32_t>(), it, 0x12345677u); break;
+      }
+      CUDA_CHECK_LAUNCH();
+      c.launches++;
+    };
+    launch(iters / 10);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+      CUDA_CHECK(cudaEventRecord(g_ev0, c.stream));
+      launch(iters);
+      CUDA_CHECK(cudaEventRecord(g_ev1, c.stream));
+      CUDA_CHECK(cudaEventSynchronize(g_ev1));
+      float ms;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, g_ev0, g_ev1));
+      if (ms < best) best = ms;
+    }
+    double per_thread = variant == 3 ? (double)iters * 2 * 136 : (double)iters * PEAK_UNROLL * 8;
+    double macs = per_thread * blocks * threads;
+    *gmacs_per_s = macs / (best * 1e-3) / 1e9;
+    if (sm_clock_mhz_effective) *sm_clock_mhz_effective = 0.0;  // clocks are sampled by bench.py via nvidia-smi
+    out.release();
+  });
+}
+
+int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out) {
+  return guarded([&](Context& c) {
+    if (!a || !out || op < 0 || op > 4) throw InvalidArgument("zkp_dbg_field_op: bad argument");
+    if (n == 0) return;
+    DevBuf da, db, dout;
+    da.reserve(n * 32);
+    dout.reserve(n * 32);
+    CUDA_CHECK(cudaMemcpyAsync(da.p, a, n * 32, cudaMemcpyHostToDevice, c.stream));
+    if (b) {
+      db.reserve(n * 32);
+      CUDA_CHECK(cudaMemcpyAsync(db.p, b, n * 32, cudaMemcpyHostToDevice, c.stream));
+    }
+    if (field == 0)
+      dbg_field_op_kernel<Fp><<<ceil_div(n, 128), 128, 0, c.stream>>>(op, da.as<Fp>(), b ? db.as<Fp>() : nullptr, n,
+                                                                     dout.as<Fp>());
+    else
+      dbg_field_op_kernel<Fr><<<ceil_div(n, 128), 128, 0, c.stream>>>(op, da.as<Fr>(), b ? db.as<Fr>() : nullptr, n,
+                                                                     dout.as<Fr>());
+    CUDA_CHECK_LAUNCH();
+    c.launches++;
+    CUDA_CHECK(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    da.release();
+    db.release();
+    dout.release();
+  });
+}
+
+int zkp_dbg_point_add(int group, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out) {
+  return guarded([&](Context& c) {
+    if (!a || !b || !out) throw InvalidArgument("zkp_dbg_point_add: null argument");
+    if (n == 0) return;
+    size_t sz = group == 0 ? 64 : 128;
+    DevBuf da, db, dout;
+    da.reserve(n * sz);
+    db.reserve(n * sz);
+    dout.reserve(n * sz);
+    CUDA_CHECK(cudaMemcpyAsync(da.p, a, n * sz, cudaMemcpyHostToDevice, c.stream));
+    CUDA_CHECK(cudaMemcpyAsync(db.p, b, n * sz, cudaMemcpyHostToDevice, c.stream));
+    if (group == 0)
+      dbg_point_add_kernel<Fp><<<ceil_div(n, 64), 64, 0, c.stream>>>(da.as<G1Affine>(), db.as<G1Affine>(), n,
+                                                                    dout.as<G1Affine>());
+    else
+      dbg_point_add_kernel<Fp2><<<ceil_div(n, 64), 64, 0, c.stream>>>(da.as<G2Affine>(), db.as<G2Affine>(), n,
+                                                                     dout.as<G2Affine>());
+    CUDA_CHECK_LAUNCH();
+    c.launches++;
+    CUDA_CHECK(cudaMemcpyAsync(out, dout.p, n * sz, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    da.release();
+    db.release();
+    dout.release();
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// Shared host-side plumbing for libzkp_b200: error reporting, the per-process device context
+// (one device per process, as bench.py / torchrun launch it), a grow-only workspace arena.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+namespace zkp {
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+  if (e != cudaSuccess) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s failed at %s:%d: %s", what, file, line, cudaGetErrorString(e));
+    throw CudaError(buf);
+  }
+}
+#define CUDA_CHECK(x) ::zkp::cuda_check((x), #x, __FILE__, __LINE__)
+#define CUDA_CHECK_LAUNCH() ::zkp::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
+
+// A device buffer that only ever grows; reused across calls so steady-state calls allocate nothing.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) CUDA_CHECK(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    CUDA_CHECK(cudaMalloc(&p, bytes));
+    cap = bytes;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Context {
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;  // serialises entry points (Flask's dev server is threaded, ctypes drops the GIL)
+  unsigned long long launches = 0;  // kernels launched by this library (bench.py "gpu_launches")
+};
+
+Context& ctx();             // throws if zkp_init has not succeeded
+bool ctx_ready();
+
+inline unsigned int ceil_div(uint64_t a, uint64_t b) { return (unsigned int)((a + b - 1) / b); }
+
+}  // namespace zkp

@@ -1,0 +1,308 @@
+// Montgomery arithmetic for the two 254-bit BN254 prime fields (Fp, Fr) on sm_100a.
+//
+// Replaces, on the device, the per-element Python arithmetic of py_ecc's FQ as the
+// reference uses it (/root/reference/zkp/plonk/field.py:36-51 `FR(FQ)`,
+// /root/reference/zkp/groth16/poly_utils.py:12-13, and every FQ op inside
+// bn128.add/double/multiply, call sites /root/reference/zkp/groth16/proving.py:12-15).
+//
+// Representation: 8 x 32-bit little-endian limbs, Montgomery radix 2^256, always fully
+// reduced to [0, MOD) so equality is limb equality.  The multiplier is a row-wise CIOS
+// built from 32x32+64 wide MADs (PTX mad.lo.cc/madc.hi.cc pairs, which ptxas fuses into
+// IMAD.WIDE.U32[.X] with a predicate carry).  Products of even and odd limbs are kept in
+// two accumulators whose 64-bit lanes never overlap, so each half-row is one 4-deep carry
+// chain and the two half-rows are independent (ILP 2):
+//
+//     T = X + Y * 2^32,  X lanes at limb pairs (0,1)(2,3)(4,5)(6,7), Y at (1,2)...(7,8)
+//
+// Per row: X += a_even*b_i, Y += a_odd*b_i, q = X[0]*N0INV, X += n_even*q, Y += n_odd*q;
+// then X[0] == 0, the roles of X and Y swap (a one-limb shift of T) and the surviving
+// limb X[1] is carried into the next row's first add.  128 IMAD.WIDE + 8 IMAD per
+// multiplication, no 32-bit carry propagation across the whole accumulator inside the loop.
+#pragma once
+#include <cstdint>
+#include "bn254_params.cuh"
+
+namespace zkp {
+
+#define ZKP_DEVINL __device__ __forceinline__
+
+namespace detail {
+
+// acc (8 limbs, four 64-bit lanes) += {m0,m1,m2,m3} * b, lane k gets m_k*b; returns the carry out.
+ZKP_DEVINL uint32_t mad_lanes(uint32_t (&acc)[8], uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3,
+                              uint32_t b) {
+  uint32_t c;
+  asm("mad.lo.cc.u32   %0, %9,  %13, %0;\n\t"
+      "madc.hi.cc.u32  %1, %9,  %13, %1;\n\t"
+      "madc.lo.cc.u32  %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32  %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32  %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
+      "addc.u32        %8, 0, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+        "+r"(acc[6]), "+r"(acc[7]), "=r"(c)
+      : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
+  return c;
+}
+
+// x0 += left (one limb below the first lane of acc); the carry of that add enters acc's
+// first lane, then acc += {m0..m3} * b.  The top lane cannot carry out (see ff.cuh header:
+// Y * 2^32 <= T < 2^288).
+ZKP_DEVINL void mad_lanes_cin(uint32_t& x0, uint32_t left, uint32_t (&acc)[8], uint32_t m0, uint32_t m1,
+                              uint32_t m2, uint32_t m3, uint32_t b) {
+  asm("add.cc.u32      %8, %8, %9;\n\t"
+      "madc.lo.cc.u32  %0, %10, %14, %0;\n\t"
+      "madc.hi.cc.u32  %1, %10, %14, %1;\n\t"
+      "madc.lo.cc.u32  %2, %11, %14, %2;\n\t"
+      "madc.hi.cc.u32  %3, %11, %14, %3;\n\t"
+      "madc.lo.cc.u32  %4, %12, %14, %4;\n\t"
+      "madc.hi.cc.u32  %5, %12, %14, %5;\n\t"
+      "madc.lo.cc.u32  %6, %13, %14, %6;\n\t"
+      "madc.hi.u32     %7, %13, %14, %7;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+        "+r"(acc[6]), "+r"(acc[7]), "+r"(x0)
+      : "r"(left), "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
+}
+
+// One CIOS row.  X: lanes aligned with the current limb 0; Y: lanes one limb higher.
+template <class P>
+ZKP_DEVINL void mont_row(uint32_t (&X)[8], uint32_t (&Y)[8], uint32_t left, const uint32_t (&a)[8],
+                         uint32_t bi) {
+  mad_lanes_cin(X[0], left, Y, a[1], a[3], a[5], a[7], bi);
+  uint32_t cx = mad_lanes(X, a[0], a[2], a[4], a[6], bi);
+  Y[7] += cx;
+  uint32_t q = X[0] * P::N0INV;
+  cx = mad_lanes(X, P::MOD_(0), P::MOD_(2), P::MOD_(4), P::MOD_(6), q);
+  uint32_t cy = mad_lanes(Y, P::MOD_(1), P::MOD_(3), P::MOD_(5), P::MOD_(7), q);
+  (void)cy;  // provably 0
+  Y[7] += cx;
+}
+
+}  // namespace detail
+
+template <class P, bool COMPACT>
+struct Mont256;
+
+// Out-of-line multiplication (arguments and result travel in registers): used by the COMPACT
+// flavour of the field type.  The serial phases of the MSM (bucket reduction, Horner, inversion) run
+// a handful of warps; with every product inlined their code is >100 KB and each lone warp stalls on
+// instruction fetch, while with one shared 4 KB body the loop stays in the instruction cache.
+template <class P>
+__device__ __noinline__ Mont256<P, false> mont_mul_outlined(Mont256<P, false> a, Mont256<P, false> b);
+
+template <class P, bool COMPACT = false>
+struct __align__(16) Mont256 {
+  uint32_t v[8];
+  using Params = P;
+  using Plain = Mont256<P, false>;
+
+  static ZKP_DEVINL Mont256 zero() {
+    Mont256 r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+    return r;
+  }
+  static ZKP_DEVINL Mont256 one() {
+    Mont256 r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::R1_(i);
+    return r;
+  }
+  static ZKP_DEVINL Mont256 r2() {
+    Mont256 r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::R2_(i);
+    return r;
+  }
+  ZKP_DEVINL bool is_zero() const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= v[i];
+    return o == 0;
+  }
+  ZKP_DEVINL bool operator==(const Mont256& b) const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= v[i] ^ b.v[i];
+    return o == 0;
+  }
+  ZKP_DEVINL bool operator!=(const Mont256& b) const { return !(*this == b); }
+
+  // r = (t >= MOD) ? t - MOD : t        (t < 2*MOD < 2^256)
+  static ZKP_DEVINL void final_sub(uint32_t (&t)[8]) {
+    uint32_t s[8], borrow;
+    asm("sub.cc.u32  %0, %9,  %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32    %8, 0, 0;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]),
+          "=r"(borrow)
+        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]),
+          "r"(P::MOD_(0)), "r"(P::MOD_(1)), "r"(P::MOD_(2)), "r"(P::MOD_(3)), "r"(P::MOD_(4)),
+          "r"(P::MOD_(5)), "r"(P::MOD_(6)), "r"(P::MOD_(7)));
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = borrow ? t[i] : s[i];
+  }
+
+  friend ZKP_DEVINL Mont256 operator+(const Mont256& a, const Mont256& b) {
+    Mont256 r;
+    asm("add.cc.u32  %0, %8,  %16;\n\t"
+        "addc.cc.u32 %1, %9,  %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32    %7, %15, %23;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+          "=r"(r.v[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+          "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]),
+          "r"(b.v[6]), "r"(b.v[7]));
+    final_sub(r.v);  // a + b < 2*MOD < 2^255: no carry out of limb 7
+    return r;
+  }
+
+  friend ZKP_DEVINL Mont256 operator-(const Mont256& a, const Mont256& b) {
+    Mont256 r;
+    uint32_t borrow;
+    asm("sub.cc.u32  %0, %9,  %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32    %8, 0, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+          "=r"(r.v[7]), "=r"(borrow)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+          "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]),
+          "r"(b.v[6]), "r"(b.v[7]));
+    // borrow is 0 or 0xffffffff: add back MOD & borrow
+    asm("add.cc.u32  %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32    %7, %7, %15;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]),
+          "+r"(r.v[7])
+        : "r"(P::MOD_(0) & borrow), "r"(P::MOD_(1) & borrow), "r"(P::MOD_(2) & borrow),
+          "r"(P::MOD_(3) & borrow), "r"(P::MOD_(4) & borrow), "r"(P::MOD_(5) & borrow),
+          "r"(P::MOD_(6) & borrow), "r"(P::MOD_(7) & borrow));
+    return r;
+  }
+
+  ZKP_DEVINL Mont256 neg() const { return is_zero() ? *this : (zero() - *this); }
+  ZKP_DEVINL Mont256 dbl() const { return *this + *this; }
+
+  friend ZKP_DEVINL Mont256 operator*(const Mont256& a, const Mont256& b) {
+    if constexpr (COMPACT) {
+      Plain pa, pb;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        pa.v[i] = a.v[i];
+        pb.v[i] = b.v[i];
+      }
+      Plain pr = mont_mul_outlined<P>(pa, pb);
+      Mont256 r;
+#pragma unroll
+      for (int i = 0; i < 8; i++) r.v[i] = pr.v[i];
+      return r;
+    } else {
+      return mul_inline(a, b);
+    }
+  }
+
+  static ZKP_DEVINL Mont256 mul_inline(const Mont256& a, const Mont256& b) {
+    uint32_t E[8], O[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) E[i] = O[i] = 0;
+    uint32_t left = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      detail::mont_row<P>(E, O, left, a.v, b.v[i]);
+      // E[0] == 0 now; T >>= 32: O becomes the aligned accumulator, E shifts down two limbs.
+      left = E[1];
+#pragma unroll
+      for (int k = 0; k < 6; k++) E[k] = E[k + 2];
+      E[6] = E[7] = 0;
+      detail::mont_row<P>(O, E, left, a.v, b.v[i + 1]);
+      left = O[1];
+#pragma unroll
+      for (int k = 0; k < 6; k++) O[k] = O[k + 2];
+      O[6] = O[7] = 0;
+    }
+    // T = E + left + (O << 32), O[6] = O[7] = 0, T < 2*MOD
+    Mont256 r;
+    asm("add.cc.u32  %0, %8,  %16;\n\t"
+        "addc.cc.u32 %1, %9,  %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32    %7, %15, %23;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+          "=r"(r.v[7])
+        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(left),
+          "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
+    final_sub(r.v);
+    return r;
+  }
+
+  ZKP_DEVINL Mont256 sqr() const { return (*this) * (*this); }
+
+  // canonical integer (non-Montgomery) <-> Montgomery
+  ZKP_DEVINL Mont256 to_mont() const { return (*this) * r2(); }
+  ZKP_DEVINL Mont256 from_mont() const {
+    Mont256 o;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o.v[i] = i == 0 ? 1u : 0u;
+    return (*this) * o;
+  }
+
+  // a^e for a canonical (non-Montgomery) little-endian exponent held in 8 limbs
+  ZKP_DEVINL Mont256 pow(const uint32_t (&e)[8]) const {
+    Mont256 acc = one();
+    for (int i = 7; i >= 0; i--) {
+      for (int b = 31; b >= 0; b--) {
+        acc = acc.sqr();
+        if ((e[i] >> b) & 1) acc = acc * (*this);
+      }
+    }
+    return acc;
+  }
+
+  // Fermat inverse a^(MOD-2); inv(0) = 0 as in py_ecc's prime_field_inv.
+  __device__ __noinline__ Mont256 inv() const {
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = P::MOD_(i);
+    e[0] -= 2;  // MOD is odd and its low limb is >= 2 for both fields
+    return pow(e);
+  }
+};
+
+template <class P>
+__device__ __noinline__ Mont256<P, false> mont_mul_outlined(Mont256<P, false> a, Mont256<P, false> b) {
+  return Mont256<P, false>::mul_inline(a, b);
+}
+
+using Fp = Mont256<FpParams>;
+using Fr = Mont256<FrParams>;
+using FpC = Mont256<FpParams, true>;  // same layout as Fp, out-of-line products
+using FrC = Mont256<FrParams, true>;
+
+}  // namespace zkp

@@ -1,0 +1,543 @@
+// Pippenger multi-scalar multiplication, templated on the coordinate field (Fp -> G1, Fp2 -> G2).
+//
+// Replaces the reference's MSM-shaped Python loops: kzg.commit
+// (/root/reference/zkp/plonk/kzg.py:59-67) and the inner loops of proof_a/proof_b/proof_c
+// (/root/reference/zkp/groth16/proving.py:27-31,39-43,56-60,66-73), each of which is
+// "sum_i scalar_i * point_i" done as one affine double-and-add per term.
+//
+// Stages (all on the device, one stream):
+//   1. digits     : reduce each scalar mod r, cut it into W signed c-bit digits d in
+//                   [-2^(c-1), 2^(c-1)], histogram the (window, |d|) buckets.
+//   2. sort       : counting sort of (bucket, point index | sign) pairs: exclusive scan of the
+//                   histogram + atomic-cursor scatter.  Order inside a bucket is irrelevant
+//                   (the group is commutative and the final affine point is unique).
+//   3. accumulate : one thread per bucket walks its run of point indices and sums the points
+//                   with XYZZ mixed additions (negating y for negative digits).
+//   4. reduce     : per window sum_b (b+1)*B_b by a radix-L weighted-sum recursion
+//                   (V = sum_i i*A_i + sum_i E_i is preserved level to level), then Horner over
+//                   the windows, one inversion, out of Montgomery form.
+//
+// HBM layout: points AoS affine Montgomery (64 B G1 / 128 B G2, 16-byte aligned -> LDG.128),
+// scalars canonical 8xu32, codes/sorted W*n u32, buckets W*2^(c-1) XYZZ.
+#pragma once
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace zkp {
+
+static constexpr uint32_t MSM_INVALID = 0xffffffffu;
+static constexpr int MSM_SCALAR_BITS = 255;  // 254-bit scalars + 1 for the signed-digit carry
+
+struct MsmPlan {
+  int c;              // window bits
+  int W;              // number of windows
+  uint32_t B;         // buckets per window = 2^(c-1)
+  uint32_t nbuckets;  // W * B
+};
+
+inline MsmPlan msm_plan(uint64_t n, int force_c = 0) {
+  int c;
+  if (force_c) c = force_c;
+  else {
+    int lg = 0;
+    while ((1ull << (lg + 1)) <= n) lg++;
+    c = lg - 4;
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+  }
+  MsmPlan p;
+  p.c = c;
+  p.W = (MSM_SCALAR_BITS + c - 1) / c;
+  p.B = 1u << (c - 1);
+  p.nbuckets = (uint32_t)p.W * p.B;
+  return p;
+}
+
+// ---------------------------------------------------------------- stage 1: digits + histogram
+static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, int c, int W, uint32_t B,
+                                  uint32_t* __restrict__ codes, uint32_t* __restrict__ hist) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[9];
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * i);
+  uint4 lo = sp[0], hi = sp[1];
+  s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
+  s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+  s[8] = 0;
+  // reduce mod r (2^256 / r < 6): the group has order r, so k*P == (k mod r)*P (field.py:88).
+  for (int it = 0; it < 6; it++) {
+    uint32_t t[8];
+    uint32_t borrow = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint64_t d = (uint64_t)s[k] - FrParams::MOD_(k) - borrow;
+      t[k] = (uint32_t)d;
+      borrow = (uint32_t)(d >> 63);
+    }
+    if (borrow) break;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = t[k];
+  }
+  uint32_t carry = 0;
+  const uint32_t mask = (1u << c) - 1;
+  for (int w = 0; w < W; w++) {
+    int pos = w * c;
+    int word = pos >> 5, sh = pos & 31;
+    uint32_t v = 0;
+    if (word < 8) {
+      uint64_t two = (uint64_t)s[word] | ((uint64_t)s[word + 1] << 32);
+      v = (uint32_t)(two >> sh) & mask;
+    }
+    v += carry;
+    uint32_t code = MSM_INVALID;
+    if (v > B) {  // digit = v - 2^c  (negative), |digit| = 2^c - v in [1, B-1]
+      uint32_t mag = (1u << c) - v;
+      carry = 1;
+      if (mag != 0) code = (((uint32_t)w * B + (mag - 1)) << 1) | 1u;
+    } else {
+      carry = 0;
+      if (v != 0) code = (((uint32_t)w * B + (v - 1)) << 1);
+    }
+    codes[(uint64_t)w * n + i] = code;
+    if (code != MSM_INVALID) atomicAdd(&hist[code >> 1], 1u);
+  }
+}
+
+// ---------------------------------------------------------------- exclusive scan (u32), 3 kernels
+static constexpr int SCAN_BLOCK = 1024;
+static constexpr int SCAN_ITEMS = 4;
+static constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t val, uint32_t* total) {
+  __shared__ uint32_t warp_sums[32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = val;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t ws = warp_sums[lane];
+    uint32_t winc = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    warp_sums[lane] = winc - ws;  // exclusive warp offsets
+    if (lane == 31) *total = winc;
+  }
+  __syncthreads();
+  uint32_t r = inc - val + warp_sums[wid];
+  __syncthreads();
+  return r;
+}
+
+static __global__ void scan_tile_sums_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ tile_sums) {
+  __shared__ uint32_t total;
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++)
+    if (base + k < n) s += in[base + k];
+  block_exclusive_scan(s, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of up to SCAN_TILE*? tile sums, sequential over chunks of 1024
+static __global__ void scan_tile_offsets_kernel(uint32_t* __restrict__ tile_sums, uint32_t ntiles) {
+  __shared__ uint32_t total;
+  uint32_t running = 0;
+  for (uint32_t base = 0; base < ntiles; base += SCAN_BLOCK) {
+    uint32_t idx = base + threadIdx.x;
+    uint32_t v = idx < ntiles ? tile_sums[idx] : 0;
+    uint32_t ex = block_exclusive_scan(v, &total);
+    if (idx < ntiles) tile_sums[idx] = ex + running;
+    running += total;
+    __syncthreads();
+  }
+}
+
+// out[i] = exclusive prefix; out[n] = grand total
+static __global__ void scan_apply_kernel(const uint32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ tile_offsets,
+                                  uint32_t* __restrict__ out) {
+  __shared__ uint32_t total;
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    s += v[k];
+  }
+  uint32_t ex = block_exclusive_scan(s, &total) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_BLOCK - 1) out[n] = ex;
+}
+
+// ---------------------------------------------------------------- stage 2: scatter
+static __global__ void msm_scatter_kernel(const uint32_t* __restrict__ codes, uint64_t total, uint64_t n,
+                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+  uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  uint32_t code = codes[idx];
+  if (code == MSM_INVALID) return;
+  uint32_t i = (uint32_t)(idx % n);
+  uint32_t pos = atomicAdd(&cursor[code >> 1], 1u);
+  sorted[pos] = i | ((code & 1u) << 31);
+}
+
+// ---------------------------------------------------------------- stage 3: bucket accumulation
+// Load balance: a bucket's run of entries is cut into tasks of at most MSM_TASK_LEN entries; tasks
+// are counting-sorted by length (longest first) so the 32 lanes of a warp walk runs of equal length
+// whatever the scalar distribution (uniform scalars: Poisson(32) runs; the top window and
+// structured inputs: a few huge buckets).  One thread per task; buckets with several tasks are
+// folded afterwards.
+static constexpr uint32_t MSM_TASK_LEN = 64;
+
+static __global__ void msm_task_count_kernel(const uint32_t* __restrict__ offsets, uint32_t nbuckets,
+                                             uint32_t* __restrict__ ntasks) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbuckets) return;
+  uint32_t cnt = offsets[b + 1] - offsets[b];
+  ntasks[b] = (cnt + MSM_TASK_LEN - 1) / MSM_TASK_LEN;
+}
+
+// len_hist[MSM_TASK_LEN - len] counts tasks of each length (descending order of length)
+static __global__ void msm_task_hist_kernel(const uint32_t* __restrict__ offsets, uint32_t nbuckets,
+                                            uint32_t* __restrict__ len_hist) {
+  __shared__ uint32_t h[MSM_TASK_LEN + 1];
+  for (uint32_t k = threadIdx.x; k <= MSM_TASK_LEN; k += blockDim.x) h[k] = 0;
+  __syncthreads();
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nbuckets) {
+    uint32_t cnt = offsets[b + 1] - offsets[b];
+    uint32_t full = cnt / MSM_TASK_LEN, rem = cnt % MSM_TASK_LEN;
+    if (full) atomicAdd(&h[0], full);
+    if (rem) atomicAdd(&h[MSM_TASK_LEN - rem], 1u);
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k <= MSM_TASK_LEN; k += blockDim.x)
+    if (h[k]) atomicAdd(&len_hist[k], h[k]);
+}
+
+// single warp: exclusive scan of the MSM_TASK_LEN+1 length bins -> cursors
+static __global__ void msm_task_bins_kernel(uint32_t* __restrict__ len_hist) {
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (uint32_t k = 0; k <= MSM_TASK_LEN; k++) {
+      uint32_t v = len_hist[k];
+      len_hist[k] = run;
+      run += v;
+    }
+  }
+}
+
+// task record: x = bucket, y = first entry, z = length, w = slot in the partial-sum array
+static __global__ void msm_task_emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_base,
+                                            uint32_t nbuckets, uint32_t* __restrict__ len_cursor,
+                                            uint4* __restrict__ tasks) {
+  __shared__ uint32_t h[MSM_TASK_LEN + 1];     // block-local count per bin
+  __shared__ uint32_t base[MSM_TASK_LEN + 1];  // block's reserved start per bin
+  for (uint32_t k = threadIdx.x; k <= MSM_TASK_LEN; k += blockDim.x) h[k] = 0;
+  __syncthreads();
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t beg = 0, cnt = 0, full = 0, rem = 0, r_full = 0, r_rem = 0;
+  if (b < nbuckets) {
+    beg = offsets[b];
+    cnt = offsets[b + 1] - beg;
+    full = cnt / MSM_TASK_LEN;
+    rem = cnt % MSM_TASK_LEN;
+    if (full) r_full = atomicAdd(&h[0], full);
+    if (rem) r_rem = atomicAdd(&h[MSM_TASK_LEN - rem], 1u);
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k <= MSM_TASK_LEN; k += blockDim.x)
+    base[k] = h[k] ? atomicAdd(&len_cursor[k], h[k]) : 0;
+  __syncthreads();
+  if (b < nbuckets) {
+    uint32_t tb = task_base[b];
+    for (uint32_t k = 0; k < full; k++)
+      tasks[base[0] + r_full + k] = make_uint4(b, beg + k * MSM_TASK_LEN, MSM_TASK_LEN, tb + k);
+    if (rem) tasks[base[MSM_TASK_LEN - rem] + r_rem] = make_uint4(b, beg + full * MSM_TASK_LEN, rem, tb + full);
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<F>* __restrict__ pts,
+                                                              const uint32_t* __restrict__ sorted,
+                                                              const uint4* __restrict__ tasks,
+                                                              const uint32_t* __restrict__ ntasks_ptr,
+                                                              XYZZ<F>* __restrict__ partials) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *ntasks_ptr) return;  // the task count is data dependent and stays on the device
+  uint4 task = tasks[t];
+  uint32_t beg = task.y, end = task.y + task.z;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t k = beg; k < end; k++) {
+    uint32_t e = sorted[k];
+    Affine<F> p = pts[e & 0x7fffffffu];
+    if (e >> 31) p.y = p.y.neg();
+    acc.madd(p);
+  }
+  partials[task.w] = acc;
+}
+
+// buckets[b] = sum of its tasks' partial sums (usually exactly one)
+template <class F>
+__global__ void __launch_bounds__(128) msm_bucket_fold_kernel(const XYZZ<F>* __restrict__ partials,
+                                                               const uint32_t* __restrict__ task_base, uint32_t nbuckets,
+                                                               XYZZ<F>* __restrict__ buckets) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbuckets) return;
+  uint32_t t0 = task_base[b], t1 = task_base[b + 1];
+  XYZZ<F> acc = XYZZ<F>::inf();
+  if (t1 > t0) acc = partials[t0];
+  for (uint32_t t = t0 + 1; t < t1; t++) acc.add(partials[t]);
+  buckets[b] = acc;
+}
+
+// ---------------------------------------------------------------- stage 4: weighted-sum recursion
+// Per window: items (A_i, E_i), i < n_in, value V = sum_i i*A_i + sum_i E_i.  One thread per chunk
+// of L items j: A'_j = L * sum A_i, E'_j = sum E_i + sum_i (i mod L) * A_i; V is unchanged with
+// n_in/L items.  E == nullptr means E_i = A_i (first level: bucket b has weight b+1).
+template <class F>
+__global__ void __launch_bounds__(128) msm_ws_level_kernel(const XYZZ<F>* __restrict__ A, const XYZZ<F>* __restrict__ E,
+                                                            uint32_t n_in, uint32_t L, int logL, uint32_t n_windows,
+                                                            XYZZ<F>* __restrict__ A_out, XYZZ<F>* __restrict__ E_out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t T = n_in / L;
+  if (t >= T * n_windows) return;
+  uint32_t w = t / T, j = t % T;
+  const XYZZ<F>* a = A + (uint64_t)w * n_in + (uint64_t)j * L;
+  XYZZ<F> acc = XYZZ<F>::inf(), run = XYZZ<F>::inf();
+  for (uint32_t i = L - 1; i >= 1; i--) {
+    acc.add(a[i]);
+    run.add(acc);
+  }
+  acc.add(a[0]);
+  if (E) {
+    const XYZZ<F>* e = E + (uint64_t)w * n_in + (uint64_t)j * L;
+    for (uint32_t i = 0; i < L; i++) run.add(e[i]);
+  } else {
+    run.add(acc);
+  }
+  for (int k = 0; k < logL; k++) acc = acc.dbl();
+  A_out[t] = acc;
+  E_out[t] = run;
+}
+
+// Radix-2 level of the same recursion with the two outputs on two threads, so a level is two
+// group operations deep: role 0: A' = 2*(A0+A1); role 1: E' = E0 + E1 + A1 (first level: A0 + 2*A1).
+// Used once the item count is too small to fill the machine and latency is all that matters.
+template <class F>
+__global__ void __launch_bounds__(64) msm_ws2_kernel(const XYZZ<F>* __restrict__ A, const XYZZ<F>* __restrict__ E,
+                                                      uint32_t n_in, uint32_t n_windows, XYZZ<F>* __restrict__ A_out,
+                                                      XYZZ<F>* __restrict__ E_out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t T = n_in / 2;
+  uint32_t chunk = t >> 1, role = t & 1;
+  if (chunk >= T * n_windows) return;
+  uint32_t w = chunk / T, j = chunk % T;
+  const XYZZ<F>* a = A + (uint64_t)w * n_in + 2 * (uint64_t)j;
+  if (role == 0) {
+    XYZZ<F> acc = a[0];
+    acc.add(a[1]);
+    A_out[chunk] = acc.dbl();
+  } else {
+    XYZZ<F> r;
+    if (E) {
+      const XYZZ<F>* e = E + (uint64_t)w * n_in + 2 * (uint64_t)j;
+      r = e[0];
+      r.add(e[1]);
+      r.add(a[1]);
+    } else {
+      r = a[1].dbl();
+      r.add(a[0]);
+    }
+    E_out[chunk] = r;
+  }
+}
+
+// Horner over the window sums (one thread), to affine, out of Montgomery form.
+// out: canonical little-endian coordinates; flag = 1 when the result is the point at infinity.
+template <class F>
+__global__ void msm_final_kernel(const XYZZ<F>* __restrict__ window_sums, int W, int c, const XYZZ<F>* extra,
+                                 int n_extra, Affine<F>* __restrict__ out, int* __restrict__ inf_flag,
+                                 XYZZ<F>* __restrict__ out_xyzz) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  XYZZ<F> r = XYZZ<F>::inf();
+  for (int w = W - 1; w >= 0; w--) {
+    if (!r.is_inf())
+      for (int k = 0; k < c; k++) r = r.dbl();
+    r.add(window_sums[w]);
+  }
+  for (int k = 0; k < n_extra; k++) r.add(extra[k]);
+  if (out_xyzz) *out_xyzz = r;
+  if (out) {
+    Affine<F> a = r.to_affine();
+    *inf_flag = r.is_inf() ? 1 : 0;
+    a.x = a.x.from_mont();
+    a.y = a.y.from_mont();
+    *out = a;
+  }
+}
+
+// canonical <-> Montgomery conversion of coordinate arrays (n_fe field elements of the base field)
+template <class FE>
+__global__ void fe_to_mont_kernel(FE* __restrict__ v, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = v[i].to_mont();
+}
+template <class FE>
+__global__ void fe_from_mont_kernel(FE* __restrict__ v, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = v[i].from_mont();
+}
+
+// ---------------------------------------------------------------- host driver
+template <class F>
+struct MsmEngine {
+  using FC = typename CompactOf<F>::type;  // same layout, out-of-line products (small code)
+  DevBuf codes, sorted, hist, offsets, cursor, tile_sums, buckets, lvlA[2], lvlE[2], result, flag;
+  DevBuf ntask, task_base, len_bins, tasks, partials;
+  int reduce_L = 8;
+  uint32_t wide_threshold = 1u << 17;  // items (all windows) above which a level is throughput bound
+  bool compact_accumulate = false;
+
+  // pts: device, affine Montgomery; scalars: device, canonical.  Leaves the affine canonical result
+  // in `result` (and the infinity flag in `flag`), or the XYZZ Montgomery partial sum when
+  // want_xyzz (multi-GPU shards).  Returns the number of kernels launched.
+  int run(const Affine<F>* pts, const uint32_t* scalars, uint64_t n, cudaStream_t st, bool want_xyzz = false,
+          int force_c = 0) {
+    int launches = 0;
+    result.reserve(sizeof(XYZZ<F>) + sizeof(Affine<F>));
+    flag.reserve(sizeof(int));
+    Affine<F>* out_aff = result.as<Affine<F>>();
+    XYZZ<F>* out_xyzz = reinterpret_cast<XYZZ<F>*>(result.as<char>() + sizeof(Affine<F>));
+    if (n == 0) {
+      CUDA_CHECK(cudaMemsetAsync(result.p, 0, sizeof(XYZZ<F>) + sizeof(Affine<F>), st));
+      int one = 1;
+      CUDA_CHECK(cudaMemcpyAsync(flag.p, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      return 0;
+    }
+    if (n >= (1ull << 31)) throw std::runtime_error("msm: n must be < 2^31");
+    MsmPlan pl = msm_plan(n, force_c);
+    uint64_t total = (uint64_t)pl.W * n;
+    if (total >= (1ull << 32)) throw std::runtime_error("msm: W*n must be < 2^32");
+    codes.reserve(total * 4);
+    sorted.reserve(total * 4);
+    hist.reserve((size_t)pl.nbuckets * 4);
+    offsets.reserve(((size_t)pl.nbuckets + 1) * 4);
+    cursor.reserve(((size_t)pl.nbuckets + 1) * 4);
+    uint32_t ntiles = ceil_div(pl.nbuckets, SCAN_TILE);
+    tile_sums.reserve((size_t)ntiles * 4);
+    buckets.reserve((size_t)pl.nbuckets * sizeof(XYZZ<F>));
+
+    CUDA_CHECK(cudaMemsetAsync(hist.p, 0, (size_t)pl.nbuckets * 4, st));
+    msm_digits_kernel<<<ceil_div(n, 256), 256, 0, st>>>(scalars, n, pl.c, pl.W, pl.B, codes.as<uint32_t>(),
+                                                       hist.as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    scan_tile_sums_kernel<<<ntiles, SCAN_BLOCK, 0, st>>>(hist.as<uint32_t>(), pl.nbuckets, tile_sums.as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    scan_tile_offsets_kernel<<<1, SCAN_BLOCK, 0, st>>>(tile_sums.as<uint32_t>(), ntiles);
+    CUDA_CHECK_LAUNCH();
+    scan_apply_kernel<<<ntiles, SCAN_BLOCK, 0, st>>>(hist.as<uint32_t>(), pl.nbuckets, tile_sums.as<uint32_t>(),
+                                                    offsets.as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    CUDA_CHECK(cudaMemcpyAsync(cursor.p, offsets.p, ((size_t)pl.nbuckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    msm_scatter_kernel<<<ceil_div(total, 256), 256, 0, st>>>(codes.as<uint32_t>(), total, n, cursor.as<uint32_t>(),
+                                                            sorted.as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    // tasks: count per bucket -> scan -> length histogram -> emit sorted by length
+    ntask.reserve(((size_t)pl.nbuckets + 1) * 4);
+    task_base.reserve(((size_t)pl.nbuckets + 1) * 4);
+    len_bins.reserve((MSM_TASK_LEN + 1) * 4);
+    uint32_t max_tasks = (uint32_t)(total / MSM_TASK_LEN) + pl.nbuckets + 1;
+    tasks.reserve((size_t)max_tasks * sizeof(uint4));
+    partials.reserve((size_t)max_tasks * sizeof(XYZZ<F>));
+    msm_task_count_kernel<<<ceil_div(pl.nbuckets, 256), 256, 0, st>>>(offsets.as<uint32_t>(), pl.nbuckets,
+                                                                     ntask.as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    scan_tile_sums_kernel<<<ntiles, SCAN_BLOCK, 0, st>>>(ntask.as<uint32_t>(), pl.nbuckets, tile_sums.as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    scan_tile_offsets_kernel<<<1, SCAN_BLOCK, 0, st>>>(tile_sums.as<uint32_t>(), ntiles);
+    CUDA_CHECK_LAUNCH();
+    scan_apply_kernel<<<ntiles, SCAN_BLOCK, 0, st>>>(ntask.as<uint32_t>(), pl.nbuckets, tile_sums.as<uint32_t>(),
+                                                    task_base.as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    CUDA_CHECK(cudaMemsetAsync(len_bins.p, 0, (MSM_TASK_LEN + 1) * 4, st));
+    msm_task_hist_kernel<<<ceil_div(pl.nbuckets, 256), 256, 0, st>>>(offsets.as<uint32_t>(), pl.nbuckets,
+                                                                    len_bins.as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    msm_task_bins_kernel<<<1, 32, 0, st>>>(len_bins.as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    msm_task_emit_kernel<<<ceil_div(pl.nbuckets, 256), 256, 0, st>>>(offsets.as<uint32_t>(), task_base.as<uint32_t>(),
+                                                                    pl.nbuckets, len_bins.as<uint32_t>(),
+                                                                    tasks.as<uint4>());
+    CUDA_CHECK_LAUNCH();
+    // the task count is data dependent: launch for the upper bound, threads past
+    // task_base[nbuckets] exit at once (no host round trip in the middle of the pipeline)
+    const uint32_t* d_ntasks = task_base.as<uint32_t>() + pl.nbuckets;
+    if (compact_accumulate)
+      msm_accumulate_kernel<FC><<<ceil_div(max_tasks, 128), 128, 0, st>>>(
+          reinterpret_cast<const Affine<FC>*>(pts), sorted.as<uint32_t>(), tasks.as<uint4>(), d_ntasks,
+          partials.as<XYZZ<FC>>());
+    else
+      msm_accumulate_kernel<F><<<ceil_div(max_tasks, 128), 128, 0, st>>>(pts, sorted.as<uint32_t>(), tasks.as<uint4>(),
+                                                                        d_ntasks, partials.as<XYZZ<F>>());
+    CUDA_CHECK_LAUNCH();
+    msm_bucket_fold_kernel<FC><<<ceil_div(pl.nbuckets, 128), 128, 0, st>>>(
+        partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(), pl.nbuckets, buckets.as<XYZZ<FC>>());
+    CUDA_CHECK_LAUNCH();
+    launches += 15;
+
+    // weighted-sum recursion down to one item per window
+    uint32_t n_in = pl.B;
+    const XYZZ<FC>* A = buckets.as<XYZZ<FC>>();
+    const XYZZ<FC>* E = nullptr;
+    int pp = 0;
+    while (n_in > 1) {
+      // wide levels (many items): radix reduce_L running sums, fewest group operations per bucket;
+      // narrow levels: radix 2 on two threads, shortest dependency chain.
+      bool wide = (uint64_t)n_in * pl.W >= (uint64_t)wide_threshold && n_in >= (uint32_t)reduce_L;
+      uint32_t L = wide ? (uint32_t)reduce_L : 2u;
+      int logL = 0;
+      while ((1u << logL) < L) logL++;
+      uint32_t T = n_in / L;
+      size_t bytes = (size_t)T * pl.W * sizeof(XYZZ<F>);
+      lvlA[pp].reserve(bytes);
+      lvlE[pp].reserve(bytes);
+      if (wide)
+        msm_ws_level_kernel<FC><<<ceil_div((uint64_t)T * pl.W, 64), 64, 0, st>>>(
+            A, E, n_in, L, logL, pl.W, lvlA[pp].template as<XYZZ<FC>>(), lvlE[pp].template as<XYZZ<FC>>());
+      else
+        msm_ws2_kernel<FC><<<ceil_div((uint64_t)T * pl.W * 2, 64), 64, 0, st>>>(
+            A, E, n_in, pl.W, lvlA[pp].template as<XYZZ<FC>>(), lvlE[pp].template as<XYZZ<FC>>());
+      CUDA_CHECK_LAUNCH();
+      launches++;
+      A = lvlA[pp].template as<XYZZ<FC>>();
+      E = lvlE[pp].template as<XYZZ<FC>>();
+      n_in = T;
+      pp ^= 1;
+    }
+    // n_in == 1: V_w = E_w (c == 1 never happens; for B == 1 the single bucket has weight 1 = itself)
+    const XYZZ<FC>* wsum = E ? E : A;
+    msm_final_kernel<FC><<<1, 32, 0, st>>>(wsum, pl.W, pl.c, nullptr, 0,
+                                          want_xyzz ? nullptr : reinterpret_cast<Affine<FC>*>(out_aff), flag.as<int>(),
+                                          want_xyzz ? reinterpret_cast<XYZZ<FC>*>(out_xyzz) : nullptr);
+    CUDA_CHECK_LAUNCH();
+    launches++;
+    return launches;
+  }
+};
+
+}  // namespace zkp

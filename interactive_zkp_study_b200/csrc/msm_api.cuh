@@ -1,0 +1,237 @@
+// Group-generic implementation of the MSM / table entry points; instantiated for G1 (msm_g1.cu)
+// and G2 (msm_g2.cu).  See include/zkp_b200.h for the contract of each function.
+#pragma once
+#include "msm.cuh"
+#include "registry.cuh"
+
+namespace zkp {
+
+extern int g_force_window_bits;     // defined in msm_g1.cu
+extern int g_compact_accumulate;    // experiment switch: out-of-line products in the accumulate kernel
+
+// out[i] = scalars[i] * base: MSB-first double-and-add in XYZZ with mixed additions, one thread per
+// scalar, then one inversion per point.  Replaces the n sequential Python scalar-muls of
+// SRS.generate (/root/reference/zkp/plonk/srs.py:78-82) and sigma12/15/22 (setup.py:18-23,56-69).
+template <class F>
+__global__ void __launch_bounds__(128) fixed_base_mul_kernel(Affine<F> base_canon, const uint32_t* __restrict__ scalars,
+                                                              uint64_t n, Affine<F>* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> base = {base_canon.x.to_mont(), base_canon.y.to_mont()};
+  uint32_t s[8];
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * i);
+  uint4 lo = sp[0], hi = sp[1];
+  s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
+  s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+  for (int it = 0; it < 6; it++) {
+    uint32_t t[8], borrow = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint64_t d = (uint64_t)s[k] - FrParams::MOD_(k) - borrow;
+      t[k] = (uint32_t)d;
+      borrow = (uint32_t)(d >> 63);
+    }
+    if (borrow) break;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = t[k];
+  }
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int w = 7; w >= 0; w--) {
+    uint32_t word = s[w];
+    for (int b = 31; b >= 0; b--) {
+      acc = acc.dbl();
+      if ((word >> b) & 1) acc.madd(base);
+    }
+  }
+  out[i] = acc.to_affine();  // Montgomery affine, (0,0) for infinity
+}
+
+template <class F>
+__global__ void combine_partials_kernel(const XYZZ<F>* __restrict__ parts, uint32_t count, Affine<F>* __restrict__ out,
+                                        int* __restrict__ inf_flag) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  XYZZ<F> r = XYZZ<F>::inf();
+  for (uint32_t k = 0; k < count; k++) r.add(parts[k]);
+  Affine<F> a = r.to_affine();
+  *inf_flag = r.is_inf() ? 1 : 0;
+  a.x = a.x.from_mont();
+  a.y = a.y.from_mont();
+  *out = a;
+}
+
+template <class F>
+struct GroupApi {
+  static constexpr size_t PT = sizeof(Affine<F>);  // 64 (G1) / 128 (G2)
+  static constexpr uint64_t FE_PER_PT = PT / 32;
+  static constexpr HandleKind KIND = sizeof(F) == 32 ? HandleKind::G1Table : HandleKind::G2Table;
+
+  static MsmEngine<F>& engine() {
+    static MsmEngine<F> e;
+    static const int env_compact = getenv("ZKP_B200_COMPACT_ACC") ? atoi(getenv("ZKP_B200_COMPACT_ACC")) : 0;
+    e.compact_accumulate = (g_compact_accumulate | env_compact) != 0;
+    return e;
+  }
+  static DevBuf& scratch_pts() {
+    static DevBuf b;
+    return b;
+  }
+  static DevBuf& scratch_scalars() {
+    static DevBuf b;
+    return b;
+  }
+
+  static void upload_points(Context& c, const uint8_t* pts, uint64_t n, void* dst) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, pts, n * PT, cudaMemcpyHostToDevice, c.stream));
+    fe_to_mont_kernel<Fp><<<ceil_div(n * FE_PER_PT, 256), 256, 0, c.stream>>>(reinterpret_cast<Fp*>(dst), n * FE_PER_PT);
+    CUDA_CHECK_LAUNCH();
+    c.launches++;
+  }
+
+  static void fetch_result(Context& c, uint8_t* out_xy, int* out_is_inf) {
+    MsmEngine<F>& e = engine();
+    int flag = 0;
+    CUDA_CHECK(cudaMemcpyAsync(out_xy, e.result.p, PT, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaMemcpyAsync(&flag, e.flag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    if (flag) memset(out_xy, 0, PT);
+    if (out_is_inf) *out_is_inf = flag;
+  }
+
+  static int table_load(const uint8_t* pts, uint64_t n, uint64_t* handle) {
+    return guarded([&](Context& c) {
+      if (!handle || (n && !pts)) throw InvalidArgument("table_load: null argument");
+      auto r = std::make_unique<Resource>();
+      r->kind = KIND;
+      r->n = n;
+      r->buf.reserve(n ? n * PT : PT);
+      if (n) upload_points(c, pts, n, r->buf.p);
+      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      *handle = registry().put(std::move(r));
+    });
+  }
+
+  static int msm_host(const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t* out_xy, int* out_is_inf) {
+    return guarded([&](Context& c) {
+      if (!out_xy || (n && (!pts || !scalars))) throw InvalidArgument("msm: null argument");
+      DevBuf& dp = scratch_pts();
+      DevBuf& ds = scratch_scalars();
+      if (n) {
+        dp.reserve(n * PT);
+        ds.reserve(n * 32);
+        upload_points(c, pts, n, dp.p);
+        CUDA_CHECK(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
+      }
+      c.launches += engine().run(dp.as<Affine<F>>(), ds.as<uint32_t>(), n, c.stream, false, g_force_window_bits);
+      fetch_result(c, out_xy, out_is_inf);
+    });
+  }
+
+  static int msm_table(uint64_t table, uint64_t offset, const uint8_t* scalars, uint64_t n, uint8_t* out_xy,
+                       int* out_is_inf) {
+    return guarded([&](Context& c) {
+      Resource* t = need(table, KIND, "msm_table");
+      if (!out_xy || (n && !scalars)) throw InvalidArgument("msm_table: null argument");
+      if (offset + n > t->n) throw InvalidArgument("msm_table: point range exceeds the table");
+      DevBuf& ds = scratch_scalars();
+      if (n) {
+        ds.reserve(n * 32);
+        CUDA_CHECK(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
+      }
+      c.launches += engine().run(t->buf.as<Affine<F>>() + offset, ds.as<uint32_t>(), n, c.stream, false,
+                                 g_force_window_bits);
+      fetch_result(c, out_xy, out_is_inf);
+    });
+  }
+
+  static int msm_dev(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n, uint8_t* out,
+                     int* out_is_inf, bool partial) {
+    return guarded([&](Context& c) {
+      Resource* t = need(table, KIND, "msm_dev");
+      Resource* s = need(scalars, HandleKind::Scalars, "msm_dev");
+      if (!out) throw InvalidArgument("msm_dev: null output");
+      if (offset + n > t->n || sc_offset + n > s->n) throw InvalidArgument("msm_dev: range out of bounds");
+      MsmEngine<F>& e = engine();
+      c.launches += e.run(t->buf.as<Affine<F>>() + offset, s->buf.as<uint32_t>() + 8 * sc_offset, n, c.stream, partial,
+                          g_force_window_bits);
+      if (partial) {
+        CUDA_CHECK(cudaMemcpyAsync(out, e.result.template as<char>() + PT, sizeof(XYZZ<F>), cudaMemcpyDeviceToHost,
+                                   c.stream));
+        CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      } else {
+        fetch_result(c, out, out_is_inf);
+      }
+    });
+  }
+
+  static int combine(const uint8_t* partials, uint32_t count, uint8_t* out_xy, int* out_is_inf) {
+    return guarded([&](Context& c) {
+      if (!out_xy || (count && !partials)) throw InvalidArgument("combine_partials: null argument");
+      MsmEngine<F>& e = engine();
+      e.result.reserve(sizeof(XYZZ<F>) + sizeof(Affine<F>));
+      e.flag.reserve(sizeof(int));
+      DevBuf& dp = scratch_pts();
+      dp.reserve((size_t)(count ? count : 1) * sizeof(XYZZ<F>));
+      if (count)
+        CUDA_CHECK(cudaMemcpyAsync(dp.p, partials, (size_t)count * sizeof(XYZZ<F>), cudaMemcpyHostToDevice, c.stream));
+      using FC = typename CompactOf<F>::type;
+      combine_partials_kernel<FC><<<1, 32, 0, c.stream>>>(dp.as<XYZZ<FC>>(), count, e.result.template as<Affine<FC>>(),
+                                                        e.flag.template as<int>());
+      CUDA_CHECK_LAUNCH();
+      c.launches++;
+      fetch_result(c, out_xy, out_is_inf);
+    });
+  }
+
+  static void fixed_base_run(Context& c, const uint8_t* base_xy, const uint32_t* dscalars, uint64_t n,
+                             uint64_t* out_table) {
+    Affine<F> base;
+    memcpy(&base, base_xy, PT);
+    auto r = std::make_unique<Resource>();
+    r->kind = KIND;
+    r->n = n;
+    r->buf.reserve(n ? n * PT : PT);
+    if (n) {
+      fixed_base_mul_kernel<F><<<ceil_div(n, 128), 128, 0, c.stream>>>(base, dscalars, n, r->buf.as<Affine<F>>());
+      CUDA_CHECK_LAUNCH();
+      c.launches++;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    *out_table = registry().put(std::move(r));
+  }
+
+  static int fixed_base_host(const uint8_t* base_xy, const uint8_t* scalars, uint64_t n, uint64_t* out_table) {
+    return guarded([&](Context& c) {
+      if (!base_xy || !out_table || (n && !scalars)) throw InvalidArgument("fixed_base_mul: null argument");
+      DevBuf& ds = scratch_scalars();
+      if (n) {
+        ds.reserve(n * 32);
+        CUDA_CHECK(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
+      }
+      fixed_base_run(c, base_xy, ds.as<uint32_t>(), n, out_table);
+    });
+  }
+
+  static int fixed_base_dev(const uint8_t* base_xy, uint64_t scalars, uint64_t n, uint64_t* out_table) {
+    return guarded([&](Context& c) {
+      Resource* s = need(scalars, HandleKind::Scalars, "fixed_base_mul_dev");
+      if (!base_xy || !out_table) throw InvalidArgument("fixed_base_mul_dev: null argument");
+      if (n > s->n) throw InvalidArgument("fixed_base_mul_dev: n exceeds the scalar vector");
+      fixed_base_run(c, base_xy, s->buf.as<uint32_t>(), n, out_table);
+    });
+  }
+
+  static void download(Context& c, Resource* t, uint64_t offset, uint64_t n, uint8_t* out_pts) {
+    if (offset + n > t->n) throw InvalidArgument("table_download: range out of bounds");
+    if (!n) return;
+    DevBuf& dp = scratch_pts();
+    dp.reserve(n * PT);
+    CUDA_CHECK(cudaMemcpyAsync(dp.p, t->buf.as<uint8_t>() + offset * PT, n * PT, cudaMemcpyDeviceToDevice, c.stream));
+    fe_from_mont_kernel<Fp><<<ceil_div(n * FE_PER_PT, 256), 256, 0, c.stream>>>(dp.as<Fp>(), n * FE_PER_PT);
+    CUDA_CHECK_LAUNCH();
+    c.launches++;
+    CUDA_CHECK(cudaMemcpyAsync(out_pts, dp.p, n * PT, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  }
+};
+
+}  // namespace zkp

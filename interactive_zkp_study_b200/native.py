@@ -1,0 +1,298 @@
+"""Thin Python layer over the C ABI: plain ints / tuples in, plain ints / tuples out.
+
+Encoding at the boundary (include/zkp_b200.h): field elements are 32-byte little-endian canonical
+integers; a G1 point is x||y; a G2 point is x.c0||x.c1||y.c0||y.c1; infinity (py_ecc ``None``) is
+all zeros on input and an ``is_inf`` flag on output.
+"""
+import ctypes
+
+from . import _lib
+from ._lib import ZkpB200Error, NotDivisibleError, buf, check  # noqa: F401
+
+R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+P_MOD = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+
+_ZERO32 = bytes(32)
+
+
+# ------------------------------------------------------------------ encoders / decoders
+def fe_bytes(x):
+    return int(x).to_bytes(32, "little")
+
+
+def fr_vec_bytes(xs):
+    """list of int / FR (anything with __int__, already reduced) -> bytes."""
+    return b"".join([int(x).to_bytes(32, "little") for x in xs])
+
+
+def fr_vec_from_bytes(b, n=None):
+    n = len(b) // 32 if n is None else n
+    fb = int.from_bytes
+    return [fb(b[32 * i:32 * i + 32], "little") for i in range(n)]
+
+
+def g1_bytes(pt):
+    if pt is None:
+        return bytes(64)
+    return int(pt[0]).to_bytes(32, "little") + int(pt[1]).to_bytes(32, "little")
+
+
+def g1_vec_bytes(pts):
+    return b"".join([g1_bytes(p) for p in pts])
+
+
+def g2_bytes(pt):
+    if pt is None:
+        return bytes(128)
+    (x, y) = pt
+    xc = x.coeffs if hasattr(x, "coeffs") else x
+    yc = y.coeffs if hasattr(y, "coeffs") else y
+    return b"".join(int(v).to_bytes(32, "little") for v in (xc[0], xc[1], yc[0], yc[1]))
+
+
+def g2_vec_bytes(pts):
+    return b"".join([g2_bytes(p) for p in pts])
+
+
+def g1_from_bytes(b, is_inf=False):
+    if is_inf or b == bytes(64):
+        return None
+    return (int.from_bytes(b[:32], "little"), int.from_bytes(b[32:64], "little"))
+
+
+def g2_from_bytes(b, is_inf=False):
+    if is_inf or b == bytes(128):
+        return None
+    v = [int.from_bytes(b[32 * i:32 * i + 32], "little") for i in range(4)]
+    return ((v[0], v[1]), (v[2], v[3]))
+
+
+# ------------------------------------------------------------------ device info / timing
+def device_info():
+    l = _lib.lib()
+    name = ctypes.create_string_buffer(128)
+    sm, maj, mnr, khz = (ctypes.c_int() for _ in range(4))
+    check(l.zkp_device_info(name, 128, ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr), ctypes.byref(khz)))
+    return {"name": name.value.decode(), "sm_count": sm.value, "cc": (maj.value, mnr.value),
+            "sm_clock_khz": khz.value}
+
+
+def launch_count():
+    return int(_lib.lib().zkp_launch_count())
+
+
+def timer_start():
+    check(_lib.lib().zkp_timer_start())
+
+
+def timer_stop():
+    ms = ctypes.c_float()
+    check(_lib.lib().zkp_timer_stop(ctypes.byref(ms)))
+    return ms.value
+
+
+def sync():
+    check(_lib.lib().zkp_sync())
+
+
+def imad_peak(variant=0):
+    g = ctypes.c_double()
+    clk = ctypes.c_double()
+    check(_lib.lib().zkp_imad_peak(variant, ctypes.byref(g), ctypes.byref(clk)))
+    return g.value
+
+
+def set_window_bits(c):
+    check(_lib.lib().zkp_msm_set_window_bits(int(c)))
+
+
+# ------------------------------------------------------------------ handles
+class DeviceHandle:
+    """Owns a device-resident table or scalar vector; freed on garbage collection."""
+
+    def __init__(self, handle, n, kind):
+        self.handle = handle
+        self.n = n
+        self.kind = kind
+
+    def free(self):
+        if self.handle:
+            try:
+                _lib.lib().zkp_free(self.handle)
+            finally:
+                self.handle = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _load(fn_name, data, n, kind):
+    h = ctypes.c_uint64()
+    check(getattr(_lib.lib(), fn_name)(buf(data), n, ctypes.byref(h)))
+    return DeviceHandle(h.value, n, kind)
+
+
+def g1_table_load(pts_bytes, n):
+    return _load("zkp_g1_table_load", pts_bytes, n, "g1")
+
+
+def g2_table_load(pts_bytes, n):
+    return _load("zkp_g2_table_load", pts_bytes, n, "g2")
+
+
+def scalars_load(sc_bytes, n):
+    return _load("zkp_scalars_load", sc_bytes, n, "fr")
+
+
+def scalars_generate(seed, n):
+    h = ctypes.c_uint64()
+    check(_lib.lib().zkp_scalars_generate(seed, n, ctypes.byref(h)))
+    return DeviceHandle(h.value, n, "fr")
+
+
+def scalars_download(handle, offset, n):
+    out = bytearray(32 * n)
+    check(_lib.lib().zkp_scalars_download(handle.handle, offset, n, buf(out)))
+    return bytes(out)
+
+
+def table_download(handle, offset, n):
+    sz = 64 if handle.kind == "g1" else 128
+    out = bytearray(sz * n)
+    check(_lib.lib().zkp_table_download(handle.handle, offset, n, buf(out)))
+    return bytes(out)
+
+
+def g1_fixed_base_mul(base_bytes, sc_bytes, n):
+    h = ctypes.c_uint64()
+    check(_lib.lib().zkp_g1_fixed_base_mul(buf(base_bytes), buf(sc_bytes), n, ctypes.byref(h)))
+    return DeviceHandle(h.value, n, "g1")
+
+
+def g2_fixed_base_mul(base_bytes, sc_bytes, n):
+    h = ctypes.c_uint64()
+    check(_lib.lib().zkp_g2_fixed_base_mul(buf(base_bytes), buf(sc_bytes), n, ctypes.byref(h)))
+    return DeviceHandle(h.value, n, "g2")
+
+
+def g1_fixed_base_mul_dev(base_bytes, scalars, n):
+    h = ctypes.c_uint64()
+    check(_lib.lib().zkp_g1_fixed_base_mul_dev(buf(base_bytes), scalars.handle, n, ctypes.byref(h)))
+    return DeviceHandle(h.value, n, "g1")
+
+
+# ------------------------------------------------------------------ MSM
+def _msm_out(group):
+    return bytearray(64 if group == 1 else 128), ctypes.c_int()
+
+
+def g1_msm(pts_bytes, sc_bytes, n):
+    out, inf = _msm_out(1)
+    check(_lib.lib().zkp_g1_msm(buf(pts_bytes), buf(sc_bytes), n, buf(out), ctypes.byref(inf)))
+    return g1_from_bytes(bytes(out), bool(inf.value))
+
+
+def g2_msm(pts_bytes, sc_bytes, n):
+    out, inf = _msm_out(2)
+    check(_lib.lib().zkp_g2_msm(buf(pts_bytes), buf(sc_bytes), n, buf(out), ctypes.byref(inf)))
+    return g2_from_bytes(bytes(out), bool(inf.value))
+
+
+def g1_msm_table(table, offset, sc_bytes, n):
+    out, inf = _msm_out(1)
+    check(_lib.lib().zkp_g1_msm_table(table.handle, offset, buf(sc_bytes), n, buf(out), ctypes.byref(inf)))
+    return g1_from_bytes(bytes(out), bool(inf.value))
+
+
+def g2_msm_table(table, offset, sc_bytes, n):
+    out, inf = _msm_out(2)
+    check(_lib.lib().zkp_g2_msm_table(table.handle, offset, buf(sc_bytes), n, buf(out), ctypes.byref(inf)))
+    return g2_from_bytes(bytes(out), bool(inf.value))
+
+
+def g1_msm_dev(table, offset, scalars, sc_offset, n):
+    out, inf = _msm_out(1)
+    check(_lib.lib().zkp_g1_msm_dev(table.handle, offset, scalars.handle, sc_offset, n, buf(out), ctypes.byref(inf)))
+    return g1_from_bytes(bytes(out), bool(inf.value))
+
+
+def g2_msm_dev(table, offset, scalars, sc_offset, n):
+    out, inf = _msm_out(2)
+    check(_lib.lib().zkp_g2_msm_dev(table.handle, offset, scalars.handle, sc_offset, n, buf(out), ctypes.byref(inf)))
+    return g2_from_bytes(bytes(out), bool(inf.value))
+
+
+def g1_msm_dev_partial(table, offset, scalars, sc_offset, n):
+    out = bytearray(128)
+    check(_lib.lib().zkp_g1_msm_dev_partial(table.handle, offset, scalars.handle, sc_offset, n, buf(out)))
+    return bytes(out)
+
+
+def g1_combine_partials(partials_bytes, count):
+    out, inf = _msm_out(1)
+    check(_lib.lib().zkp_g1_combine_partials(buf(partials_bytes), count, buf(out), ctypes.byref(inf)))
+    return g1_from_bytes(bytes(out), bool(inf.value))
+
+
+# ------------------------------------------------------------------ Fr vectors
+def fr_ntt(data_bytes, log_n, omega, inverse=False, coset_shift=None):
+    data = bytearray(data_bytes)
+    cs = fe_bytes(coset_shift) if coset_shift is not None else None
+    check(_lib.lib().zkp_fr_ntt(buf(data), log_n, buf(fe_bytes(omega)), 1 if inverse else 0, buf(cs)))
+    return bytes(data)
+
+
+def fr_vec_op(op, a_bytes, b_bytes, n):
+    out = bytearray(32 * n)
+    check(_lib.lib().zkp_fr_vec_op(op, buf(a_bytes), buf(b_bytes), n, buf(out)))
+    return bytes(out)
+
+
+def fr_batch_inverse(a_bytes, n):
+    out = bytearray(32 * n)
+    check(_lib.lib().zkp_fr_batch_inverse(buf(a_bytes), n, buf(out)))
+    return bytes(out)
+
+
+def fr_poly_eval(coeff_bytes, n, x):
+    out = bytearray(32)
+    check(_lib.lib().zkp_fr_poly_eval(buf(coeff_bytes), n, buf(fe_bytes(x)), buf(out)))
+    return int.from_bytes(out, "little")
+
+
+def fr_poly_mul(a_bytes, a_len, b_bytes, b_len):
+    out = bytearray(32 * (a_len + b_len - 1))
+    check(_lib.lib().zkp_fr_poly_mul(buf(a_bytes), a_len, buf(b_bytes), b_len, buf(out)))
+    return bytes(out)
+
+
+def fr_poly_divmod(a_bytes, a_len, b_bytes, b_len):
+    q = bytearray(32 * (a_len - b_len + 1))
+    r = bytearray(32 * max(b_len - 1, 1))
+    check(_lib.lib().zkp_fr_poly_divmod(buf(a_bytes), a_len, buf(b_bytes), b_len, buf(q), buf(r)))
+    return bytes(q), bytes(r[:32 * (b_len - 1)])
+
+
+def groth16_quotient(a_bytes, b_bytes, c_bytes, length, z_bytes, z_len):
+    h = bytearray(32 * (2 * length - 1 - z_len + 1))
+    r = bytearray(32 * max(z_len - 1, 1))
+    check(_lib.lib().zkp_groth16_quotient(buf(a_bytes), buf(b_bytes), buf(c_bytes), length, buf(z_bytes), z_len,
+                                          buf(h), buf(r)))
+    return bytes(h), bytes(r[:32 * (z_len - 1)])
+
+
+# ------------------------------------------------------------------ diagnostics (tests)
+def dbg_field_op(field, op, a_bytes, b_bytes, n):
+    out = bytearray(32 * n)
+    check(_lib.lib().zkp_dbg_field_op(field, op, buf(a_bytes), buf(b_bytes), n, buf(out)))
+    return bytes(out)
+
+
+def dbg_point_add(group, a_bytes, b_bytes, n):
+    sz = 64 if group == 0 else 128
+    out = bytearray(sz * n)
+    check(_lib.lib().zkp_dbg_point_add(group, buf(a_bytes), buf(b_bytes), n, buf(out)))
+    return bytes(out)

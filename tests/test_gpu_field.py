@@ -1,0 +1,63 @@
+"""-m gpu: the Montgomery field core and the XYZZ group law of libzkp_b200 against Python ints
+(field ops) and the plain-int oracle (group law, incl. every edge case py_ecc defines:
+infinity operands, P+P, P+(-P))."""
+import random
+
+import pytest
+
+from oracle import bn254
+
+pytestmark = pytest.mark.gpu
+
+P, R = bn254.P, bn254.R
+
+
+def _vec(vals):
+    return b"".join(int(v).to_bytes(32, "little") for v in vals)
+
+
+def _unvec(b):
+    return [int.from_bytes(b[i:i + 32], "little") for i in range(0, len(b), 32)]
+
+
+@pytest.mark.parametrize("field,mod", [(0, P), (1, R)])
+def test_field_ops_bit_exact(native, field, mod):
+    rng = random.Random(1234 + field)
+    edge = [0, 1, 2, mod - 1, mod - 2, (1 << 253), (1 << 32) - 1, 1 << 32, (mod - 1) // 2, (mod + 1) // 2]
+    a = edge + [rng.randrange(mod) for _ in range(4000)]
+    b = list(reversed(edge)) + [rng.randrange(mod) for _ in range(4000)]
+    n = len(a)
+    ab, bb = _vec(a), _vec(b)
+    assert _unvec(native.dbg_field_op(field, 0, ab, bb, n)) == [(x + y) % mod for x, y in zip(a, b)]
+    assert _unvec(native.dbg_field_op(field, 1, ab, bb, n)) == [(x - y) % mod for x, y in zip(a, b)]
+    assert _unvec(native.dbg_field_op(field, 2, ab, bb, n)) == [(x * y) % mod for x, y in zip(a, b)]
+    assert _unvec(native.dbg_field_op(field, 4, ab, None, n)) == [(x * x) % mod for x in a]
+    m = 300
+    got = _unvec(native.dbg_field_op(field, 3, _vec(a[:m]), None, m))
+    assert got == [bn254.inv(x, mod) for x in a[:m]]  # inv(0) == 0 as in py_ecc
+
+
+def test_g1_add_all_cases(native):
+    rng = random.Random(7)
+    pts = [bn254.g1_mul(bn254.G1, rng.randrange(1, R)) for _ in range(40)]
+    a, b = [], []
+    for i in range(0, 40, 2):
+        a.append(pts[i]); b.append(pts[i + 1])          # generic
+    a += [None, pts[0], None, pts[1], pts[2]]
+    b += [pts[0], None, None, pts[1], bn254.g1_neg(pts[2])]  # inf+P, P+inf, inf+inf, P+P, P+(-P)
+    n = len(a)
+    out = native.dbg_point_add(0, native.g1_vec_bytes(a), native.g1_vec_bytes(b), n)
+    got = [native.g1_from_bytes(out[64 * i:64 * i + 64]) for i in range(n)]
+    assert got == [bn254.g1_add(x, y) for x, y in zip(a, b)]
+
+
+def test_g2_add_all_cases(native):
+    rng = random.Random(8)
+    pts = [bn254.g2_mul(bn254.G2, rng.randrange(1, 1 << 64)) for _ in range(12)]
+    a = pts[0:6] + [None, pts[0], None, pts[1], pts[2]]
+    b = pts[6:12] + [pts[0], None, None, pts[1], bn254.g2_neg(pts[2])]
+    n = len(a)
+    enc = lambda v: b"".join(native.g2_bytes(p) for p in v)
+    out = native.dbg_point_add(1, enc(a), enc(b), n)
+    got = [native.g2_from_bytes(out[128 * i:128 * i + 128]) for i in range(n)]
+    assert got == [bn254.g2_add(x, y) for x, y in zip(a, b)]

@@ -1,0 +1,146 @@
+"""-m gpu: G1 / G2 MSM through the C ABI, bit-exact against the oracle's commit()-style loop
+(/root/reference/zkp/plonk/kzg.py:59-67) at sizes the oracle finishes in seconds, plus the edge
+distributions of SURVEY.md 8(d) and the size-independent check result == (sum k_i s_i) * G at the
+BASELINE sizes (points with known discrete logs generated on the device)."""
+import random
+
+import pytest
+
+from oracle import bn254, synthetic
+
+pytestmark = pytest.mark.gpu
+R = bn254.R
+
+
+def _points_g1(rng, n):
+    # cheap distinct points: running sums of a few random multiples
+    base = [bn254.g1_mul(bn254.G1, rng.randrange(1, R)) for _ in range(4)]
+    pts, acc = [], base[0]
+    for i in range(n):
+        acc = bn254.g1_add(acc, base[i % 4])
+        pts.append(acc)
+    return pts
+
+
+def _check_g1(native, pts, scalars):
+    got = native.g1_msm(native.g1_vec_bytes(pts), native.fr_vec_bytes(scalars), len(pts))
+    assert got == bn254.g1_msm(pts, scalars)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 33, 257, 1024])
+def test_g1_msm_random(native, n):
+    rng = random.Random(100 + n)
+    pts = _points_g1(rng, n)
+    scalars = [rng.randrange(R) for _ in range(n)]
+    _check_g1(native, pts, scalars)
+
+
+def test_g1_msm_empty_is_infinity(native):
+    assert native.g1_msm(b"", b"", 0) is None
+
+
+@pytest.mark.parametrize("c", [2, 5, 9, 13, 16])
+def test_g1_msm_every_window_width(native, c):
+    rng = random.Random(200 + c)
+    pts = _points_g1(rng, 300)
+    scalars = [rng.randrange(R) for _ in range(300)]
+    native.set_window_bits(c)
+    try:
+        _check_g1(native, pts, scalars)
+    finally:
+        native.set_window_bits(0)
+
+
+def test_g1_msm_edge_distributions(native):
+    rng = random.Random(5)
+    n = 200
+    pts = _points_g1(rng, n)
+    _check_g1(native, pts, [0] * n)                                   # all zero -> infinity
+    _check_g1(native, pts, [1] * n)                                   # all one
+    _check_g1(native, pts, [R - 1] * n)                               # all r-1
+    _check_g1(native, pts, [rng.randrange(R) if i % 2 else 0 for i in range(n)])  # 50% zeros
+    _check_g1(native, [pts[0]] * n, [rng.randrange(R) for _ in range(n)])        # all points equal
+    _check_g1(native, [pts[0]] * n, [12345] * n)                      # same point, same scalar (P+P in buckets)
+    pm = []
+    for i in range(n // 2):
+        pm += [pts[i], bn254.g1_neg(pts[i])]
+    _check_g1(native, pm, [777] * n)                                  # P / -P pairs -> infinity
+    _check_g1(native, pts, [(1 << 255) + 5, R, R + 1, 2 * R + 3] + [1] * (n - 4))  # unreduced scalars
+    with_inf = list(pts)
+    with_inf[3] = None
+    with_inf[77] = None
+    _check_g1(native, with_inf, [rng.randrange(R) for _ in range(n)])  # infinity points in the table
+    _check_g1(native, pts, [(1 << 16) - 1] * n)                        # digit carries
+    _check_g1(native, pts, [1 << 15] * n)                              # digit == B exactly
+
+
+def test_g1_msm_table_and_dev_paths_agree(native):
+    rng = random.Random(9)
+    n = 500
+    pts = _points_g1(rng, n)
+    scalars = [rng.randrange(R) for _ in range(n)]
+    want = bn254.g1_msm(pts[100:400], scalars[:300])
+    table = native.g1_table_load(native.g1_vec_bytes(pts), n)
+    assert native.g1_msm_table(table, 100, native.fr_vec_bytes(scalars[:300]), 300) == want
+    sc = native.scalars_load(native.fr_vec_bytes(scalars), n)
+    assert native.g1_msm_dev(table, 100, sc, 0, 300) == want
+    # shard form: two partial sums combined == whole
+    p0 = native.g1_msm_dev_partial(table, 100, sc, 0, 150)
+    p1 = native.g1_msm_dev_partial(table, 250, sc, 150, 150)
+    assert native.g1_combine_partials(p0 + p1, 2) == want
+    back = native.table_download(table, 0, n)
+    assert [native.g1_from_bytes(back[64 * i:64 * i + 64]) for i in range(n)] == pts
+
+
+@pytest.mark.parametrize("n", [1, 5, 64, 300])
+def test_g2_msm_random(native, n):
+    rng = random.Random(300 + n)
+    base = [bn254.g2_mul(bn254.G2, rng.randrange(1, 1 << 60)) for _ in range(3)]
+    pts, acc = [], base[0]
+    for i in range(n):
+        acc = bn254.g2_add(acc, base[i % 3])
+        pts.append(acc)
+    scalars = [rng.randrange(R) for _ in range(n)]
+    if n > 4:
+        scalars[2] = 0
+        pts[4] = None
+    got = native.g2_msm(native.g2_vec_bytes(pts), native.fr_vec_bytes(scalars), n)
+    assert got == bn254.g2_msm(pts, scalars)
+
+
+def test_fixed_base_mul_matches_oracle(native):
+    rng = random.Random(11)
+    scalars = [0, 1, 2, R - 1, R, R + 5] + [rng.randrange(R) for _ in range(60)]
+    t = native.g1_fixed_base_mul(native.g1_bytes(bn254.G1), native.fr_vec_bytes(scalars), len(scalars))
+    back = native.table_download(t, 0, len(scalars))
+    got = [native.g1_from_bytes(back[64 * i:64 * i + 64]) for i in range(len(scalars))]
+    assert got == [bn254.g1_mul(bn254.G1, s % R) for s in scalars]
+    sc2 = scalars[:12]
+    t2 = native.g2_fixed_base_mul(native.g2_bytes(bn254.G2), native.fr_vec_bytes(sc2), len(sc2))
+    back = native.table_download(t2, 0, len(sc2))
+    got = [native.g2_from_bytes(back[128 * i:128 * i + 128]) for i in range(len(sc2))]
+    assert got == [bn254.g2_mul(bn254.G2, s % R) for s in sc2]
+
+
+def test_synthetic_scalar_stream_matches_oracle(native):
+    h = native.scalars_generate(0x5EED0001, 5000)
+    got = native.fr_vec_from_bytes(native.scalars_download(h, 0, 5000))
+    assert got == synthetic.scalars(0x5EED0001, 5000)
+
+
+@pytest.mark.parametrize("log_n", [16, 20])
+def test_g1_msm_full_size_known_dlog(native, log_n):
+    """BASELINE config 2 sizes: P_i = s_i*G generated on the device, so the MSM has the O(n) check
+    result == (sum k_i*s_i mod r)*G (one oracle scalar multiplication)."""
+    n = 1 << log_n
+    s_h = native.scalars_generate(0x5EED0002, n)
+    k_h = native.scalars_generate(0x5EED0001, n)
+    table = native.g1_fixed_base_mul_dev(native.g1_bytes(bn254.G1), s_h, n)
+    # spot-check generated points against the oracle
+    s = synthetic.scalars(0x5EED0002, n)
+    k = synthetic.scalars(0x5EED0001, n)
+    for i in (0, 1, n // 3, n - 1):
+        assert native.g1_from_bytes(native.table_download(table, i, 1)) == bn254.g1_mul(bn254.G1, s[i])
+    got = native.g1_msm_dev(table, 0, k_h, 0, n)
+    total = sum(a * b for a, b in zip(k, s)) % R
+    assert got == bn254.g1_mul(bn254.G1, total)
