@@ -8,6 +8,8 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <utility>
+#include <vector>
 
 namespace zkp {
 
@@ -52,6 +54,38 @@ struct Context {
   cudaStream_t stream = nullptr;
   std::mutex mu;  // serialises entry points (Flask's dev server is threaded, ctypes drops the GIL)
   unsigned long long launches = 0;  // kernels launched by this library (bench.py "gpu_launches")
+};
+
+// Optional per-stage CUDA-event trace (ZKP_B200_TRACE=1): prints the device time between marks.
+struct StageTrace {
+  bool on;
+  cudaStream_t st;
+  std::vector<std::pair<std::string, cudaEvent_t>> ev;
+  explicit StageTrace(cudaStream_t s) : st(s) {
+    static const bool env = getenv("ZKP_B200_TRACE") && atoi(getenv("ZKP_B200_TRACE"));
+    on = env;
+    mark("start");
+  }
+  void mark(const char* name) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.emplace_back(name, e);
+  }
+  ~StageTrace() {
+    if (!on || ev.empty()) return;
+    cudaEventSynchronize(ev.back().second);
+    for (size_t i = 1; i < ev.size(); i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+      fprintf(stderr, "[zkp trace] %-18s %8.1f us\n", ev[i].first.c_str(), ms * 1e3);
+    }
+    float tot = 0;
+    cudaEventElapsedTime(&tot, ev.front().second, ev.back().second);
+    fprintf(stderr, "[zkp trace] %-18s %8.1f us\n", "TOTAL", tot * 1e3);
+    for (auto& kv : ev) cudaEventDestroy(kv.second);
+  }
 };
 
 Context& ctx();             // throws if zkp_init has not succeeded

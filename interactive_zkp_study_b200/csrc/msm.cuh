@@ -343,7 +343,9 @@ __global__ void __launch_bounds__(64) msm_ws2_kernel(const XYZZ<F>* __restrict__
                                                       XYZZ<F>* __restrict__ E_out) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t T = n_in / 2;
-  uint32_t chunk = t >> 1, role = t & 1;
+  // roles are split by warp (not by lane) so a warp never executes both formulas
+  uint32_t warp = t >> 5, lane = t & 31;
+  uint32_t chunk = (warp >> 1) * 32 + lane, role = warp & 1;
   if (chunk >= T * n_windows) return;
   uint32_t w = chunk / T, j = chunk % T;
   const XYZZ<F>* a = A + (uint64_t)w * n_in + 2 * (uint64_t)j;
@@ -442,6 +444,7 @@ struct MsmEngine {
     tile_sums.reserve((size_t)ntiles * 4);
     buckets.reserve((size_t)pl.nbuckets * sizeof(XYZZ<F>));
 
+    StageTrace tr(st);
     CUDA_CHECK(cudaMemsetAsync(hist.p, 0, (size_t)pl.nbuckets * 4, st));
     msm_digits_kernel<<<ceil_div(n, 256), 256, 0, st>>>(scalars, n, pl.c, pl.W, pl.B, codes.as<uint32_t>(),
                                                        hist.as<uint32_t>());
@@ -453,10 +456,12 @@ struct MsmEngine {
     scan_apply_kernel<<<ntiles, SCAN_BLOCK, 0, st>>>(hist.as<uint32_t>(), pl.nbuckets, tile_sums.as<uint32_t>(),
                                                     offsets.as<uint32_t>());
     CUDA_CHECK_LAUNCH();
+    tr.mark("digits+scan");
     CUDA_CHECK(cudaMemcpyAsync(cursor.p, offsets.p, ((size_t)pl.nbuckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
     msm_scatter_kernel<<<ceil_div(total, 256), 256, 0, st>>>(codes.as<uint32_t>(), total, n, cursor.as<uint32_t>(),
                                                             sorted.as<uint32_t>());
     CUDA_CHECK_LAUNCH();
+    tr.mark("scatter");
     // tasks: count per bucket -> scan -> length histogram -> emit sorted by length
     ntask.reserve(((size_t)pl.nbuckets + 1) * 4);
     task_base.reserve(((size_t)pl.nbuckets + 1) * 4);
@@ -486,6 +491,7 @@ struct MsmEngine {
     CUDA_CHECK_LAUNCH();
     // the task count is data dependent: launch for the upper bound, threads past
     // task_base[nbuckets] exit at once (no host round trip in the middle of the pipeline)
+    tr.mark("tasks");
     const uint32_t* d_ntasks = task_base.as<uint32_t>() + pl.nbuckets;
     if (compact_accumulate)
       msm_accumulate_kernel<FC><<<ceil_div(max_tasks, 128), 128, 0, st>>>(
@@ -495,6 +501,7 @@ struct MsmEngine {
       msm_accumulate_kernel<F><<<ceil_div(max_tasks, 128), 128, 0, st>>>(pts, sorted.as<uint32_t>(), tasks.as<uint4>(),
                                                                         d_ntasks, partials.as<XYZZ<F>>());
     CUDA_CHECK_LAUNCH();
+    tr.mark("accumulate");
     msm_bucket_fold_kernel<FC><<<ceil_div(pl.nbuckets, 128), 128, 0, st>>>(
         partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(), pl.nbuckets, buckets.as<XYZZ<FC>>());
     CUDA_CHECK_LAUNCH();
@@ -505,6 +512,7 @@ struct MsmEngine {
     const XYZZ<FC>* A = buckets.as<XYZZ<FC>>();
     const XYZZ<FC>* E = nullptr;
     int pp = 0;
+    tr.mark("fold");
     while (n_in > 1) {
       // wide levels (many items): radix reduce_L running sums, fewest group operations per bucket;
       // narrow levels: radix 2 on two threads, shortest dependency chain.
@@ -520,7 +528,7 @@ struct MsmEngine {
         msm_ws_level_kernel<FC><<<ceil_div((uint64_t)T * pl.W, 64), 64, 0, st>>>(
             A, E, n_in, L, logL, pl.W, lvlA[pp].template as<XYZZ<FC>>(), lvlE[pp].template as<XYZZ<FC>>());
       else
-        msm_ws2_kernel<FC><<<ceil_div((uint64_t)T * pl.W * 2, 64), 64, 0, st>>>(
+        msm_ws2_kernel<FC><<<ceil_div((uint64_t)ceil_div((uint64_t)T * pl.W, 32) * 64, 64), 64, 0, st>>>(
             A, E, n_in, pl.W, lvlA[pp].template as<XYZZ<FC>>(), lvlE[pp].template as<XYZZ<FC>>());
       CUDA_CHECK_LAUNCH();
       launches++;
@@ -528,6 +536,7 @@ struct MsmEngine {
       E = lvlE[pp].template as<XYZZ<FC>>();
       n_in = T;
       pp ^= 1;
+      tr.mark(wide ? "ws wide" : "ws2");
     }
     // n_in == 1: V_w = E_w (c == 1 never happens; for B == 1 the single bucket has weight 1 = itself)
     const XYZZ<FC>* wsum = E ? E : A;
@@ -536,6 +545,7 @@ struct MsmEngine {
                                           want_xyzz ? reinterpret_cast<XYZZ<FC>*>(out_xyzz) : nullptr);
     CUDA_CHECK_LAUNCH();
     launches++;
+    tr.mark("horner+affine");
     return launches;
   }
 };

@@ -1,8 +1,347 @@
-// placeholder until the NTT lands (next commit)
+// Fr number-theoretic transform on sm_100a.  Replaces the recursive radix-2 Python FFT of the
+// reference: fft (/root/reference/zkp/plonk/polynomial.py:292-341), ifft (:344-378),
+// coset_fft / coset_ifft (/root/reference/zkp/plonk/utils.py:145-205).  Natural order in and out,
+// arbitrary root `omega` of order n (the reference passes get_root_of_unity(n) or its inverse).
+//
+// Algorithm: decimation-in-time radix-2 butterflies on the bit-reversed input, grouped into passes
+// of up to 10 stages that run out of shared memory.  Pass 1 gathers the bit-reversed input
+// (32-byte elements = one DRAM sector each) and writes contiguous 32 KB tiles; later passes work on
+// tiles of (2^S strided rows) x (>= 8 contiguous elements = 256-byte runs).  Shared memory is
+// limb-major (SoA) so consecutive threads hit consecutive banks.  Twiddles omega^i, i < n/2, are
+// precomputed on the device in Montgomery form and cached per (omega, n); because they are
+// Montgomery constants, the data keeps whatever form it came in (canonical host data needs no
+// conversion).  The n^-1 factor of the inverse and the coset scalings are fused into the
+// first-pass load / last-pass store.
+#include <cstring>
+#include <map>
+#include <vector>
+#include "ntt.cuh"
 #include "registry.cuh"
-using namespace zkp;
-static int nyi(const char* f) { set_last_error(std::string(f) + ": not implemented yet"); return ZKP_ERR_INVALID_ARGUMENT; }
-extern "C" {
-int zkp_fr_ntt(uint8_t*, uint32_t, const uint8_t*, int, const uint8_t*) { return nyi("zkp_fr_ntt"); }
-int zkp_fr_ntt_dev(uint64_t, uint64_t, uint32_t, const uint8_t*, int, const uint8_t*) { return nyi("zkp_fr_ntt_dev"); }
+
+namespace zkp {
+
+static constexpr int NTT_LOG_TILE = 10;  // elements per block tile (2^10 x 32 B = 32 KB shared)
+static constexpr int NTT_Q = 3;          // contiguous run of 2^3 elements in the strided passes
+
+// ------------------------------------------------------------------ small power tables
+// out[k] = x^(2^k) (Montgomery), k < 32; x canonical on input.  invert: start from x^-1.
+__global__ void pow2_table_kernel(Fr x_canon, int invert, Fr* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Fr x = x_canon.to_mont();
+  if (invert) x = x.inv();
+  for (int k = 0; k < 32; k++) {
+    out[k] = x;
+    x = x.sqr();
+  }
 }
+
+// x^e from the pow2 table (e < 2^32)
+__device__ __forceinline__ Fr pow_from_table(const Fr* __restrict__ tab, uint32_t e) {
+  Fr r = Fr::one();
+  bool first = true;
+  for (int k = 0; e; k++, e >>= 1) {
+    if (e & 1) {
+      if (first) { r = tab[k]; first = false; }
+      else r = r * tab[k];
+    }
+  }
+  return r;
+}
+
+__global__ void twiddle_table_kernel(const Fr* __restrict__ pow2tab, uint32_t count, Fr* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = pow_from_table(pow2tab, i);
+}
+
+__global__ void scale_by_powers_kernel(Fr* __restrict__ v, uint64_t n, const Fr* __restrict__ pow2tab) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && i) v[i] = v[i] * pow_from_table(pow2tab, (uint32_t)i);
+}
+
+// ------------------------------------------------------------------ the pass kernel
+struct NttPassArgs {
+  const Fr* src;
+  Fr* dst;
+  const Fr* tw;       // omega^i, i < n/2
+  uint32_t log_n;
+  uint32_t s0;        // stages already done
+  uint32_t S;         // stages in this pass
+  uint32_t log_g;     // log2 of sub-transforms per tile; tile = 2^(S+log_g) elements
+  int bitrev_in;      // first pass: gather src[bitrev(i)]
+  const Fr* pre_pow2;   // forward coset: multiply input j (natural index) by shift^j   (first pass)
+  const Fr* post_pow2;  // inverse coset: multiply output j by shift^-j                 (last pass)
+  int scale_n_inv;      // last pass of an inverse: multiply by n^-1
+  Fr n_inv;             // Montgomery
+};
+
+__device__ __forceinline__ Fr lds_elem(const uint32_t* sm, uint32_t tile, uint32_t idx) {
+  Fr r;
+#pragma unroll
+  for (int l = 0; l < 8; l++) r.v[l] = sm[l * tile + idx];
+  return r;
+}
+__device__ __forceinline__ void sts_elem(uint32_t* sm, uint32_t tile, uint32_t idx, const Fr& x) {
+#pragma unroll
+  for (int l = 0; l < 8; l++) sm[l * tile + idx] = x.v[l];
+}
+
+__global__ void __launch_bounds__(512) ntt_pass_kernel(NttPassArgs a) {
+  extern __shared__ uint32_t sm[];
+  const uint32_t log_tile = a.S + a.log_g;
+  const uint32_t tile = 1u << log_tile;
+  const uint32_t G = 1u << a.log_g;
+  const uint32_t n = 1u << a.log_n;
+  const bool first = a.s0 == 0;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nthreads = blockDim.x;  // tile / 2 (or 1 when tile == 1)
+
+  // ---- global index of local slot l
+  // first pass : contiguous tile, l = g * 2^S + mid, global = blockIdx * tile + l
+  // later pass : global = hi * 2^(s0+S) + mid * 2^s0 + (lg * G + g), l = mid * G + g
+  uint64_t tile_base;
+  uint32_t lo_base = 0;
+  if (first) {
+    tile_base = (uint64_t)blockIdx.x * tile;
+  } else {
+    uint32_t groups = (1u << a.s0) >> a.log_g;  // lo groups per hi
+    uint32_t hi = blockIdx.x / groups, lg = blockIdx.x % groups;
+    lo_base = lg << a.log_g;
+    tile_base = ((uint64_t)hi << (a.s0 + a.S)) + lo_base;
+  }
+  auto global_of = [&](uint32_t l) -> uint64_t {
+    if (first) return tile_base + l;
+    uint32_t mid = l >> a.log_g, g = l & (G - 1);
+    return tile_base + ((uint64_t)mid << a.s0) + g;
+  };
+
+  // ---- load
+  for (uint32_t l = tid; l < tile; l += nthreads) {
+    uint64_t gi = global_of(l);
+    Fr x;
+    if (a.bitrev_in) {
+      uint32_t src_i = a.log_n ? (__brev((uint32_t)gi) >> (32 - a.log_n)) : 0;
+      x = a.src[src_i];
+      if (a.pre_pow2 && src_i) x = x * pow_from_table(a.pre_pow2, src_i);
+    } else {
+      x = a.src[gi];
+    }
+    sts_elem(sm, tile, l, x);
+  }
+  __syncthreads();
+
+  // ---- S butterfly stages
+  for (uint32_t u = 1; u <= a.S; u++) {
+    const uint32_t h = 1u << (u - 1);  // half size in `mid` units
+    for (uint32_t t = tid; t < tile / 2; t += nthreads) {
+      uint32_t bf, g;
+      if (first) { g = t >> (a.S - 1); bf = t & ((1u << (a.S - 1)) - 1); }
+      else { bf = t >> a.log_g; g = t & (G - 1); }
+      uint32_t mid = ((bf >> (u - 1)) << u) | (bf & (h - 1));
+      uint32_t l0 = first ? ((g << a.S) + mid) : ((mid << a.log_g) + g);
+      uint32_t l1 = first ? (l0 + h) : (l0 + (h << a.log_g));
+      // global stage s = s0 + u, half m = 2^(s-1); exponent = (i mod m) * n / (2m)
+      uint32_t s = a.s0 + u;
+      uint32_t imod = first ? (mid & (h - 1)) : (((mid & (h - 1)) << a.s0) + lo_base + g);
+      uint32_t e = imod << (a.log_n - s);
+      Fr x0 = lds_elem(sm, tile, l0);
+      Fr x1 = lds_elem(sm, tile, l1);
+      if (e) x1 = x1 * a.tw[e];
+      sts_elem(sm, tile, l0, x0 + x1);
+      sts_elem(sm, tile, l1, x0 - x1);
+    }
+    __syncthreads();
+  }
+
+  // ---- store
+  const bool last = (a.s0 + a.S) == a.log_n;
+  for (uint32_t l = tid; l < tile; l += nthreads) {
+    uint64_t gi = global_of(l);
+    Fr x = lds_elem(sm, tile, l);
+    if (last) {
+      if (a.scale_n_inv) x = x * a.n_inv;
+      if (a.post_pow2 && gi) x = x * pow_from_table(a.post_pow2, (uint32_t)gi);
+    }
+    a.dst[gi] = x;
+  }
+  (void)n;
+}
+
+// ------------------------------------------------------------------ caches
+struct KeyLess {
+  bool operator()(const std::vector<uint8_t>& x, const std::vector<uint8_t>& y) const { return x < y; }
+};
+static std::map<std::vector<uint8_t>, DevBuf> g_pow2_cache;   // key: x (32) + inverted (1)
+static std::map<std::vector<uint8_t>, DevBuf> g_twiddle_cache;  // key: omega (32) + inverted (1) + log_n (1)
+static size_t g_twiddle_bytes = 0;
+
+const Fr* pow2_table(Context& c, const FrBytes& x, bool inverted, int* launches) {
+  std::vector<uint8_t> key(x.b, x.b + 32);
+  key.push_back(inverted ? 1 : 0);
+  auto it = g_pow2_cache.find(key);
+  if (it != g_pow2_cache.end()) return it->second.as<Fr>();
+  DevBuf& buf = g_pow2_cache[key];
+  buf.reserve(32 * sizeof(Fr));
+  Fr xv;
+  memcpy(xv.v, x.b, 32);
+  pow2_table_kernel<<<1, 32, 0, c.stream>>>(xv, inverted ? 1 : 0, buf.as<Fr>());
+  CUDA_CHECK_LAUNCH();
+  if (launches) (*launches)++;
+  return buf.as<Fr>();
+}
+
+static const Fr* twiddle_table(Context& c, const FrBytes& omega, bool inverted, uint32_t log_n, int* launches) {
+  std::vector<uint8_t> key(omega.b, omega.b + 32);
+  key.push_back(inverted ? 1 : 0);
+  key.push_back((uint8_t)log_n);
+  auto it = g_twiddle_cache.find(key);
+  if (it != g_twiddle_cache.end()) return it->second.as<Fr>();
+  // bound the cache (callers use a handful of domains: n, 2n..8n and their inverses)
+  if (g_twiddle_bytes > (size_t(6) << 30)) {
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    for (auto& kv : g_twiddle_cache) kv.second.release();
+    g_twiddle_cache.clear();
+    g_twiddle_bytes = 0;
+  }
+  const Fr* p2 = pow2_table(c, omega, inverted, launches);
+  uint32_t count = log_n ? (1u << (log_n - 1)) : 1;
+  DevBuf& buf = g_twiddle_cache[key];
+  buf.reserve((size_t)count * sizeof(Fr));
+  g_twiddle_bytes += (size_t)count * sizeof(Fr);
+  twiddle_table_kernel<<<ceil_div(count, 256), 256, 0, c.stream>>>(p2, count, buf.as<Fr>());
+  CUDA_CHECK_LAUNCH();
+  if (launches) (*launches)++;
+  return buf.as<Fr>();
+}
+
+int scale_by_powers(Context& c, Fr* v, uint64_t n, const Fr* pow2tab) {
+  if (n <= 1) return 0;
+  scale_by_powers_kernel<<<ceil_div(n, 256), 256, 0, c.stream>>>(v, n, pow2tab);
+  CUDA_CHECK_LAUNCH();
+  return 1;
+}
+
+// n^-1 mod r in Montgomery form, computed on the host: n = 2^k so n^-1 = ((r+1)/2)^k; the host only
+// shifts/adds 256-bit integers here (no field library needed): inv2^k by repeated halving of 1.
+static void host_n_inv_mont(uint32_t log_n, Fr* out) {
+  // value = R1 (Montgomery one) halved log_n times mod r: (x even) ? x/2 : (x + r)/2
+  uint32_t x[9];
+  for (int i = 0; i < 8; i++) x[i] = FrParams::R1[i];
+  x[8] = 0;
+  for (uint32_t k = 0; k < log_n; k++) {
+    if (x[0] & 1) {
+      uint64_t carry = 0;
+      for (int i = 0; i < 8; i++) {
+        uint64_t t = (uint64_t)x[i] + FrParams::MOD[i] + carry;
+        x[i] = (uint32_t)t;
+        carry = t >> 32;
+      }
+      x[8] = (uint32_t)carry;
+    }
+    for (int i = 0; i < 8; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+    x[8] = 0;
+  }
+  for (int i = 0; i < 8; i++) out->v[i] = x[i];
+}
+
+int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes& omega, bool inverse,
+               const FrBytes* coset_shift) {
+  if (log_n > FrParams::TWO_ADICITY) throw InvalidArgument("ntt: log_n exceeds the 2-adicity of Fr (28)");
+  int launches = 0;
+  const uint32_t n = 1u << log_n;
+  const Fr* tw = twiddle_table(c, omega, inverse, log_n, &launches);
+  const Fr* pre = nullptr;
+  const Fr* post = nullptr;
+  if (coset_shift) {
+    if (inverse) post = pow2_table(c, *coset_shift, true, &launches);
+    else pre = pow2_table(c, *coset_shift, false, &launches);
+  }
+  NttPassArgs a;
+  a.tw = tw;
+  a.log_n = log_n;
+  a.pre_pow2 = pre;
+  a.post_pow2 = post;
+  a.scale_n_inv = inverse ? 1 : 0;
+  host_n_inv_mont(log_n, &a.n_inv);
+
+  // pass 1: bit-reversed gather data -> scratch, stages 1..S1 on contiguous tiles
+  uint32_t S1 = log_n < (uint32_t)NTT_LOG_TILE ? log_n : (uint32_t)NTT_LOG_TILE;
+  a.src = data;
+  a.dst = scratch;
+  a.s0 = 0;
+  a.S = S1;
+  a.log_g = log_n < (uint32_t)NTT_LOG_TILE ? 0 : 0;
+  a.bitrev_in = 1;
+  {
+    uint32_t tile = 1u << (a.S + a.log_g);
+    uint32_t threads = tile >= 2 ? tile / 2 : 1;
+    ntt_pass_kernel<<<n / tile, threads, tile * 32, c.stream>>>(a);
+    CUDA_CHECK_LAUNCH();
+    launches++;
+  }
+  uint32_t done = S1;
+  a.bitrev_in = 0;
+  a.pre_pow2 = nullptr;
+  a.src = scratch;
+  a.dst = scratch;  // in place: every tile reads and writes exactly its own elements
+  while (done < log_n) {
+    uint32_t rem = log_n - done;
+    uint32_t S = rem < (uint32_t)(NTT_LOG_TILE - NTT_Q) ? rem : (uint32_t)(NTT_LOG_TILE - NTT_Q);
+    a.s0 = done;
+    a.S = S;
+    a.log_g = NTT_LOG_TILE - S;  // >= NTT_Q and <= s0 (s0 >= 10)
+    if (a.log_g > a.s0) a.log_g = a.s0;
+    uint32_t tile = 1u << (a.S + a.log_g);
+    ntt_pass_kernel<<<n / tile, tile / 2, tile * 32, c.stream>>>(a);
+    CUDA_CHECK_LAUNCH();
+    launches++;
+    done += S;
+  }
+  CUDA_CHECK(cudaMemcpyAsync(data, scratch, (size_t)n * sizeof(Fr), cudaMemcpyDeviceToDevice, c.stream));
+  return launches;
+}
+
+}  // namespace zkp
+
+using namespace zkp;
+
+static DevBuf g_ntt_data, g_ntt_scratch;
+
+extern "C" {
+
+int zkp_fr_ntt(uint8_t* data, uint32_t log_n, const uint8_t omega[32], int inverse, const uint8_t* coset_shift) {
+  return guarded([&](Context& c) {
+    if (!data || !omega) throw InvalidArgument("zkp_fr_ntt: null argument");
+    if (log_n > 28) throw InvalidArgument("zkp_fr_ntt: log_n must be <= 28");
+    size_t bytes = (size_t(1) << log_n) * 32;
+    g_ntt_data.reserve(bytes);
+    g_ntt_scratch.reserve(bytes);
+    FrBytes w, cs;
+    memcpy(w.b, omega, 32);
+    if (coset_shift) memcpy(cs.b, coset_shift, 32);
+    CUDA_CHECK(cudaMemcpyAsync(g_ntt_data.p, data, bytes, cudaMemcpyHostToDevice, c.stream));
+    c.launches += ntt_device(c, g_ntt_data.as<Fr>(), g_ntt_scratch.as<Fr>(), log_n, w, inverse != 0,
+                             coset_shift ? &cs : nullptr);
+    CUDA_CHECK(cudaMemcpyAsync(data, g_ntt_data.p, bytes, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int zkp_fr_ntt_dev(uint64_t scalars, uint64_t offset, uint32_t log_n, const uint8_t omega[32], int inverse,
+                   const uint8_t* coset_shift) {
+  return guarded([&](Context& c) {
+    Resource* s = need(scalars, HandleKind::Scalars, "zkp_fr_ntt_dev");
+    if (!omega) throw InvalidArgument("zkp_fr_ntt_dev: null omega");
+    if (log_n > 28) throw InvalidArgument("zkp_fr_ntt_dev: log_n must be <= 28");
+    uint64_t n = uint64_t(1) << log_n;
+    if (offset + n > s->n) throw InvalidArgument("zkp_fr_ntt_dev: range out of bounds");
+    g_ntt_scratch.reserve(n * 32);
+    FrBytes w, cs;
+    memcpy(w.b, omega, 32);
+    if (coset_shift) memcpy(cs.b, coset_shift, 32);
+    c.launches += ntt_device(c, s->buf.as<Fr>() + offset, g_ntt_scratch.as<Fr>(), log_n, w, inverse != 0,
+                             coset_shift ? &cs : nullptr);
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,29 @@
+// Internal interface of the Fr NTT engine (ntt.cu), shared with the polynomial layer (poly.cu).
+#pragma once
+#include "common.cuh"
+#include "ff.cuh"
+
+namespace zkp {
+
+// Canonical little-endian Fr element on the host.
+struct FrBytes {
+  uint8_t b[32];
+  bool operator==(const FrBytes& o) const { return memcmp(b, o.b, 32) == 0; }
+};
+
+// In-place transform of a device vector of n = 2^log_n elements, natural order in and out.
+// The data may be in canonical or Montgomery form (the transform is linear and the twiddles are
+// Montgomery constants, so the form is preserved).
+//   forward:  out[k] = sum_j in[j] * omega^(jk), optionally pre-scaled in[j] *= shift^j
+//   inverse:  same with omega^-1, scaled by n^-1, optionally post-scaled out[j] *= shift^-j
+// `scratch` must hold n elements.  Returns the number of kernels launched.
+int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes& omega, bool inverse,
+               const FrBytes* coset_shift);
+
+// x^(2^k), k < 32, in Montgomery form on the device (cached per x); `inverted`: of x^-1 instead.
+const Fr* pow2_table(Context& c, const FrBytes& x, bool inverted, int* launches);
+
+// v[i] *= x^i   (powers from a pow2 table)
+int scale_by_powers(Context& c, Fr* v, uint64_t n, const Fr* pow2tab);
+
+}  // namespace zkp
