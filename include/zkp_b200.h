@@ -112,13 +112,18 @@ int zkp_fr_ntt(uint8_t* data, uint32_t log_n, const uint8_t omega[32], int inver
 int zkp_fr_ntt_dev(uint64_t scalars, uint64_t offset, uint32_t log_n, const uint8_t omega[32], int inverse,
                    const uint8_t* coset_shift);
 
-/* op: 0 add, 1 sub, 2 mul (pointwise), out may alias a or b.  Polynomial.__add__/__sub__
- * (polynomial.py:108-136) and the evaluation-form products behind the quotients. */
+/* op: 0 add, 1 sub, 2 mul (pointwise), 3 scale (out[i] = a[i] * b[0]); out may alias a or b.
+ * Polynomial.__add__/__sub__/scalar __mul__ (polynomial.py:108-151) and the evaluation-form
+ * products behind the quotients. */
 int zkp_fr_vec_op(int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
 /* out[i] = a[i]^-1, inv(0) = 0 (py_ecc prime_field_inv) */
 int zkp_fr_batch_inverse(const uint8_t* a, uint64_t n, uint8_t* out);
 /* Horner evaluation p(x), Polynomial.evaluate zkp/plonk/polynomial.py:85-106 */
 int zkp_fr_poly_eval(const uint8_t* coeffs, uint64_t n, const uint8_t x[32], uint8_t out[32]);
+
+/* out[j] = sum_i vec[i] * mat[i*cols + j]: _multiply_vec_matrix (zkp/groth16/poly_utils.py:52-59), the
+ * R.Ax / R.Bx / R.Cx products of hxr and the u_j = sum_i Rx_i*Ax_ij scalars of proof_a/b/c. */
+int zkp_fr_vec_matrix(const uint8_t* vec, const uint8_t* mat, uint64_t rows, uint64_t cols, uint8_t* out);
 
 /* ---- quotients ----------------------------------------------------------------------------- */
 /* Groth16 hxr (zkp/groth16/poly_utils.py:116-125): P = a*b - c (len(a)=len(b)=len(c)=len),

@@ -251,6 +251,12 @@ def fr_vec_op(op, a_bytes, b_bytes, n):
     return bytes(out)
 
 
+def fr_vec_matrix(vec_bytes, mat_bytes, rows, cols):
+    out = bytearray(32 * cols)
+    check(_lib.lib().zkp_fr_vec_matrix(buf(vec_bytes), buf(mat_bytes), rows, cols, buf(out)))
+    return bytes(out)
+
+
 def fr_batch_inverse(a_bytes, n):
     out = bytearray(32 * n)
     check(_lib.lib().zkp_fr_batch_inverse(buf(a_bytes), n, buf(out)))
