@@ -118,6 +118,9 @@ int zkp_fr_ntt_dev(uint64_t scalars, uint64_t offset, uint32_t log_n, const uint
 int zkp_fr_vec_op(int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
 /* out[i] = a[i]^-1, inv(0) = 0 (py_ecc prime_field_inv) */
 int zkp_fr_batch_inverse(const uint8_t* a, uint64_t n, uint8_t* out);
+/* out[0] = 1, out[i] = a[0]*...*a[i-1]: the running products of SRS.generate (zkp/plonk/srs.py:78-82,
+ * tau^i) and of the permutation accumulator (zkp/plonk/permutation.py:120-135) as a parallel scan. */
+int zkp_fr_prefix_product(const uint8_t* a, uint64_t n, uint8_t* out);
 /* Horner evaluation p(x), Polynomial.evaluate zkp/plonk/polynomial.py:85-106 */
 int zkp_fr_poly_eval(const uint8_t* coeffs, uint64_t n, const uint8_t x[32], uint8_t out[32]);
 

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "zkp_fr_ntt_dev": (c_int, [u64, u64, u32, vp, c_int, vp]),
     "zkp_fr_vec_op": (c_int, [c_int, vp, vp, u64, vp]),
     "zkp_fr_batch_inverse": (c_int, [vp, u64, vp]),
+    "zkp_fr_prefix_product": (c_int, [vp, u64, vp]),
     "zkp_fr_poly_eval": (c_int, [vp, u64, vp, vp]),
     "zkp_fr_vec_matrix": (c_int, [vp, vp, u64, u64, vp]),
     "zkp_groth16_quotient": (c_int, [vp, vp, vp, u64, vp, u64, vp, vp]),

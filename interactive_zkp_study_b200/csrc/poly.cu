@@ -234,6 +234,80 @@ __global__ void fr_div_vanishing_kernel(const Fr* __restrict__ a, uint64_t la, u
   (void)lq;
 }
 
+
+// ------------------------------------------------------------------ exclusive prefix product
+// out[0] = 1, out[i] = in[0] * ... * in[i-1]  (canonical in and out).  Tiles of 1024 elements:
+// tile products -> single-block scan of the tile products -> per-tile scan.  Replaces running
+// products such as tau^i (srs.py:78-82) and the accumulator z (permutation.py:120-135).
+static constexpr int PP_THREADS = 256, PP_ITEMS = 4, PP_TILE = PP_THREADS * PP_ITEMS;
+
+// inclusive block scan (Hillis-Steele in shared memory) of one Montgomery value per thread
+__device__ __forceinline__ Fr block_inclusive_product(Fr v, Fr* sm) {
+  sm[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 1; o < PP_THREADS; o <<= 1) {
+    Fr t = v;
+    if ((int)threadIdx.x >= o) t = sm[threadIdx.x - o] * v;
+    __syncthreads();
+    v = t;
+    sm[threadIdx.x] = v;
+    __syncthreads();
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(PP_THREADS) pp_tile_products_kernel(const Fr* __restrict__ in, uint64_t n,
+                                                                       Fr* __restrict__ tile_prod) {
+  __shared__ Fr sm[PP_THREADS];
+  uint64_t base = (uint64_t)blockIdx.x * PP_TILE + (uint64_t)threadIdx.x * PP_ITEMS;
+  Fr p = Fr::one();
+#pragma unroll
+  for (int k = 0; k < PP_ITEMS; k++)
+    if (base + k < n) p = p * in[base + k].to_mont();
+  Fr inc = block_inclusive_product(p, sm);
+  if (threadIdx.x == PP_THREADS - 1) tile_prod[blockIdx.x] = inc;
+}
+
+// single block: tile_prod[i] <- exclusive prefix product (Montgomery)
+__global__ void __launch_bounds__(PP_THREADS) pp_tile_scan_kernel(Fr* __restrict__ tile_prod, uint64_t ntiles) {
+  __shared__ Fr sm[PP_THREADS];
+  __shared__ Fr carry;
+  if (threadIdx.x == 0) carry = Fr::one();
+  __syncthreads();
+  for (uint64_t base = 0; base < ntiles; base += PP_THREADS) {
+    uint64_t i = base + threadIdx.x;
+    Fr v = i < ntiles ? tile_prod[i] : Fr::one();
+    Fr inc = block_inclusive_product(v, sm);
+    Fr c = carry;
+    Fr prev = threadIdx.x ? sm[threadIdx.x - 1] : Fr::one();
+    __syncthreads();
+    if (i < ntiles) tile_prod[i] = c * prev;
+    if (threadIdx.x == PP_THREADS - 1) carry = c * inc;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(PP_THREADS) pp_apply_kernel(const Fr* __restrict__ in, uint64_t n,
+                                                               const Fr* __restrict__ tile_off, Fr* __restrict__ out) {
+  __shared__ Fr sm[PP_THREADS];
+  uint64_t base = (uint64_t)blockIdx.x * PP_TILE + (uint64_t)threadIdx.x * PP_ITEMS;
+  Fr x[PP_ITEMS];
+  Fr p = Fr::one();
+#pragma unroll
+  for (int k = 0; k < PP_ITEMS; k++) {
+    x[k] = (base + k < n) ? in[base + k].to_mont() : Fr::one();
+    p = p * x[k];
+  }
+  block_inclusive_product(p, sm);
+  Fr run = tile_off[blockIdx.x];
+  if (threadIdx.x) run = run * sm[threadIdx.x - 1];
+#pragma unroll
+  for (int k = 0; k < PP_ITEMS; k++) {
+    if (base + k < n) out[base + k] = run.from_mont();
+    run = run * x[k];
+  }
+}
+
 // ------------------------------------------------------------------ device-level polynomial ops (Montgomery)
 // out[0..out_len) = (a * b)[0..out_len); a, b, out device Montgomery; out must not alias a or b.
 static int poly_mul_dev(Context& c, const Fr* a, uint64_t la, const Fr* b, uint64_t lb, Fr* out, uint64_t out_len) {
@@ -418,6 +492,28 @@ int zkp_fr_batch_inverse(const uint8_t* a, uint64_t n, uint8_t* out) {
     fr_batch_inverse_kernel<<<ceil_div(T, 128), 128, 0, c.stream>>>(da, n, T, 0, dout);
     CUDA_CHECK_LAUNCH();
     c.launches++;
+    CUDA_CHECK(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int zkp_fr_prefix_product(const uint8_t* a, uint64_t n, uint8_t* out) {
+  return guarded([&](Context& c) {
+    if (n && (!a || !out)) throw InvalidArgument("zkp_fr_prefix_product: null argument");
+    if (!n) return;
+    ArenaScope scope;
+    uint64_t ntiles = (n + PP_TILE - 1) / PP_TILE;
+    Fr* da = g_arena.alloc(n);
+    Fr* dout = g_arena.alloc(n);
+    Fr* tiles = g_arena.alloc(ntiles);
+    CUDA_CHECK(cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, c.stream));
+    pp_tile_products_kernel<<<(unsigned)ntiles, PP_THREADS, 0, c.stream>>>(da, n, tiles);
+    CUDA_CHECK_LAUNCH();
+    pp_tile_scan_kernel<<<1, PP_THREADS, 0, c.stream>>>(tiles, ntiles);
+    CUDA_CHECK_LAUNCH();
+    pp_apply_kernel<<<(unsigned)ntiles, PP_THREADS, 0, c.stream>>>(da, n, tiles, dout);
+    CUDA_CHECK_LAUNCH();
+    c.launches += 3;
     CUDA_CHECK(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
   });

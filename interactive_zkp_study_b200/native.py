@@ -263,6 +263,12 @@ def fr_batch_inverse(a_bytes, n):
     return bytes(out)
 
 
+def fr_prefix_product(a_bytes, n):
+    out = bytearray(32 * n)
+    check(_lib.lib().zkp_fr_prefix_product(buf(a_bytes), n, buf(out)))
+    return bytes(out)
+
+
 def fr_poly_eval(coeff_bytes, n, x):
     out = bytearray(32)
     check(_lib.lib().zkp_fr_poly_eval(buf(coeff_bytes), n, buf(fe_bytes(x)), buf(out)))

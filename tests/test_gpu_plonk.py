@@ -1,0 +1,229 @@
+"""-m gpu: the PLONK drop-in modules (same API as /root/reference/zkp/plonk/*) against the golden
+fixtures the reference itself produced (tests/golden/plonk_*.json, each accepted by the reference's
+verifier when it was minted) and the oracle.  Modelled on /root/reference/tests/plonk/
+test_foundation.py (fft/ifft/poly), test_crypto.py (commit) and test_prover.py / test_e2e.py."""
+import copy
+
+import pytest
+
+from oracle import bn254, ref_path
+from tests.util import g1, ints, load
+
+pytestmark = pytest.mark.gpu
+R = bn254.R
+
+CASES = ["plonk_n1.json", "plonk_x3.json", "plonk_chain16.json"]
+
+
+class FixedSecrets:
+    """Replays the blinding scalars of the golden run (the rounds call secrets.randbelow)."""
+
+    def __init__(self, values):
+        self.values = list(values)
+
+    def randbelow(self, n):
+        return self.values.pop(0)
+
+
+class StubGate:
+    def __init__(self, q_l, q_r, q_o, q_m, q_c):
+        self.q = (q_l, q_r, q_o, q_m, q_c)
+
+
+class StubCircuit:
+    """The four members preprocess() reads from a reference Circuit (circuit.py:100-247)."""
+
+    def __init__(self, f, FR):
+        sel = f["selectors"]
+        n_raw = f["n_raw"]
+        self.gates = [StubGate(*(FR(int(sel[k][i])) for k in ("q_l", "q_r", "q_o", "q_m", "q_c"))) for i in range(n_raw)]
+        self._sigma = list(f["sigma"])
+        self.num_public_inputs = f["num_public_inputs"]
+
+    @property
+    def n(self):
+        return len(self.gates)
+
+    def get_selector_polynomials(self):
+        return tuple([g.q[k] for g in self.gates] for k in range(5))
+
+    def build_copy_constraints(self):
+        return list(self._sigma)
+
+
+def _pt(p):
+    return None if p is None else (int(p[0]), int(p[1]))
+
+
+def _srs(f):
+    from interactive_zkp_study_b200.zkp.plonk.srs import SRS
+    from interactive_zkp_study_b200.compat import g1_from_ints, g2_from_ints
+    from tests.util import g2
+    return SRS([g1_from_ints(g1(p)) for p in f["g1_powers"]], [g2_from_ints(g2(p)) for p in f["g2_powers"]],
+               f["srs_max_degree"])
+
+
+def test_fft_family_matches_reference(native):
+    from interactive_zkp_study_b200.zkp.plonk.field import FR, get_root_of_unity, get_roots_of_unity
+    from interactive_zkp_study_b200.zkp.plonk.polynomial import Polynomial, fft, ifft
+    from interactive_zkp_study_b200.zkp.plonk.utils import coset_fft, coset_ifft
+    for case in load("primitives.json")["fft"]:
+        n = case["n"]
+        w = get_root_of_unity(n)
+        assert int(w) == int(case["omega"])
+        v = [FR(int(x)) for x in case["in"]]
+        out = fft(v, w)
+        assert all(isinstance(x, FR) for x in out)
+        assert [int(x) for x in out] == ints(case["fft"])
+        assert [int(x) for x in ifft(v, w)] == ints(case["ifft"])
+        assert [int(x) for x in coset_fft(v, w)] == ints(case["coset_fft"])
+        assert [int(x) for x in coset_ifft(v, w)] == ints(case["coset_ifft"])
+        assert [int(x) for x in coset_fft(v, w, FR(7))] == ints(case["coset_fft_k7"])
+        assert [int(x) for x in get_roots_of_unity(n)] == ref_path.get_roots_of_unity(n)
+        # fft agrees with Horner at every w^i (reference test_foundation.py:501-508); round trip (:524-541)
+        p = Polynomial(v)
+        assert [int(p.evaluate(w ** i)) for i in range(n)] == ints(case["fft"])
+        assert ifft(fft(v, w), w) == v
+    for bad in (0, 3, 6, (1 << 28) + 1, 1 << 29):
+        with pytest.raises(ValueError):
+            get_root_of_unity(bad)
+
+
+def test_polynomial_class_matches_reference(native):
+    from interactive_zkp_study_b200.zkp.plonk.field import FR
+    from interactive_zkp_study_b200.zkp.plonk.polynomial import Polynomial, poly_div, lagrange_basis
+    p = load("primitives.json")
+    for case in p["poly_mul"]:
+        a, b = Polynomial(ints(case["a"])), Polynomial(ints(case["b"]))
+        assert [int(x) for x in (a * b).coeffs] == ints(case["ab"])
+        assert [int(x) for x in (a + b).coeffs] == ref_path.poly_add(ints(case["a"]), ints(case["b"]))
+        assert [int(x) for x in (a - b).coeffs] == ref_path.poly_sub(ints(case["a"]), ints(case["b"]))
+        assert [int(x) for x in (a * FR(7)).coeffs] == ref_path.poly_scale(ints(case["a"]), 7)
+        assert [int(x) for x in (-a).coeffs] == ref_path.poly_sub([0], ints(case["a"]))
+    for case in p["poly_div"]:
+        q, r = poly_div(Polynomial(ints(case["a"])), Polynomial(ints(case["b"])))
+        assert [int(x) for x in q.coeffs] == ints(case["q"]) and [int(x) for x in r.coeffs] == ints(case["r"])
+    assert Polynomial([1, 2, 0, 0]).coeffs == [FR(1), FR(2)] and Polynomial([0, 0]).is_zero()
+    assert (Polynomial([1, 2]) - Polynomial([1, 2])).is_zero() and Polynomial([5]).degree == 0
+    with pytest.raises(ValueError):
+        poly_div(Polynomial([1, 2]), Polynomial.zero())
+    # x^2 - 1 = (x - 1)(x + 1)   (reference docstring example, polynomial.py:406-410)
+    q, r = poly_div(Polynomial([FR(-1), FR(0), FR(1)]), Polynomial([FR(-1), FR(1)]))
+    assert q == Polynomial([1, 1]) and r.is_zero()
+    dom = [FR(1), FR(2), FR(3), FR(9)]
+    for i in range(4):
+        L = lagrange_basis(dom, i)
+        assert [int(L.evaluate(d)) for d in dom] == [1 if j == i else 0 for j in range(4)]
+    with pytest.raises(ValueError, match="나누어 떨어지지"):
+        Polynomial([1, 2, 3, 4, 5]).divide_by_vanishing(2)
+    assert Polynomial.vanishing(4).divide_by_vanishing(4) == Polynomial.one()
+
+
+def test_commit_matches_reference(native):
+    from interactive_zkp_study_b200.zkp.plonk.field import FR, G1, ec_mul, ec_add
+    from interactive_zkp_study_b200.zkp.plonk.polynomial import Polynomial
+    from interactive_zkp_study_b200.zkp.plonk.kzg import commit
+    from interactive_zkp_study_b200.zkp.plonk.srs import SRS
+    p = load("primitives.json")
+    srs = SRS.generate(12, seed=42)                         # device fixed-base generation
+    assert [_pt(x) for x in srs.g1_powers] == [g1(x) for x in p["srs42"]["g1_powers"]]
+    assert int(srs.g2_powers[1][0].coeffs[0]) == int(p["srs42"]["g2_powers"][1][0][0])
+    for case in p["commit"]:
+        poly = Polynomial(ints(case["coeffs"]))
+        assert _pt(commit(poly, srs)) == g1(case["commitment"])
+    assert commit(Polynomial.zero(), srs) is None            # reference test_crypto.py:132-136
+    with pytest.raises(ValueError):
+        commit(Polynomial([1] * 14), srs)                    # degree 13 > 12 (test_crypto.py:138-144)
+    # commit vs explicit ec_add(ec_mul ...) and linearity (test_crypto.py:113-191)
+    a, b = Polynomial([3, 1, 4]), Polynomial([1, 5, 9, 2])
+    acc = None
+    for i, c in enumerate(a.coeffs):
+        acc = ec_add(acc, ec_mul(srs.g1_powers[i], c))
+    assert _pt(commit(a, srs)) == _pt(acc)
+    assert _pt(commit(a + b, srs)) == _pt(ec_add(commit(a, srs), commit(b, srs)))
+    assert _pt(ec_mul(G1, 2)) == g1(p["kat"]["two_G1"]) and ec_mul(G1, 0) is None and ec_mul(None, 5) is None
+    assert ec_add(ec_mul(G1, 5), ec_mul(G1, R - 5)) is None
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_preprocess_matches_reference(native, name):
+    from interactive_zkp_study_b200.zkp.plonk.field import FR
+    from interactive_zkp_study_b200.zkp.plonk.preprocessor import preprocess
+    f = load(name)
+    srs = _srs(f)
+    circuit = StubCircuit(f, FR)
+    pp = preprocess(circuit, srs)
+    assert pp.n == f["n"] and len(circuit.gates) == f["n"] and int(pp.omega) == int(f["omega"])
+    assert [int(x) for x in pp.domain] == ints(f["domain"])
+    for k in ("q_l", "q_r", "q_o", "q_m", "q_c", "s_sigma1", "s_sigma2", "s_sigma3"):
+        assert [int(x) for x in getattr(pp, k + "_poly").coeffs] == ints(f["pre"][k]), k
+        assert _pt(getattr(pp, k + "_comm")) == g1(f["pre_comm"][k]), k
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_prove_bit_exact_with_reference(native, name):
+    from interactive_zkp_study_b200.zkp.plonk.field import FR
+    from interactive_zkp_study_b200.zkp.plonk.preprocessor import preprocess
+    from interactive_zkp_study_b200.zkp.plonk import prover
+    from interactive_zkp_study_b200.zkp.plonk.prover import round1, round2
+    from interactive_zkp_study_b200.zkp.plonk.kzg import commit
+    f = load(name)
+    srs = _srs(f)
+    circuit = StubCircuit(f, FR)
+    pp = preprocess(circuit, srs)
+    sec = FixedSecrets(ints(f["blinds"]))
+    round1.secrets = sec
+    round2.secrets = sec
+    try:
+        state = prover.ProverState([FR(int(x)) for x in f["a_vals"]], [FR(int(x)) for x in f["b_vals"]],
+                                   [FR(int(x)) for x in f["c_vals"]], [FR(int(x)) for x in f["public_inputs"]], pp, srs)
+        for rnd in (prover.round1, prover.round2, prover.round3, prover.round4, prover.round5):
+            rnd.execute(state)
+    finally:
+        import secrets as real
+        round1.secrets = real
+        round2.secrets = real
+    for k, v in f["challenges"].items():
+        assert int(getattr(state, k)) == int(v), k
+    for k, v in f["polys"].items():
+        assert [int(x) for x in getattr(state, k + "_poly").coeffs] == ints(v), k
+    proof = state.build_proof()
+    for k, v in f["proof"].items():
+        got = getattr(proof, k)
+        if k.endswith("_comm"):
+            assert _pt(got) == g1(v), k
+            assert bn254.g1_is_on_curve(_pt(got))
+        else:
+            assert isinstance(got, FR) and int(got) == int(v), k
+    # proof.X_comm == commit(X_poly) (reference test_prover.py:257-262,336-340,399-404)
+    assert _pt(proof.a_comm) == _pt(commit(state.a_poly, srs))
+    assert _pt(proof.z_comm) == _pt(commit(state.z_poly, srs))
+    copy.deepcopy(proof)                                         # test_e2e.py:213 deep-copies proofs
+
+
+def test_invalid_witness_raises_like_reference(native):
+    """reference test_prover.py:746-747: a wrong witness makes round 3 raise ValueError."""
+    from interactive_zkp_study_b200.zkp.plonk.field import FR
+    from interactive_zkp_study_b200.zkp.plonk.preprocessor import preprocess
+    from interactive_zkp_study_b200.zkp.plonk import prover
+    f = load("plonk_x3.json")
+    srs = _srs(f)
+    pp = preprocess(StubCircuit(f, FR), srs)
+    a = [FR(int(x)) for x in f["a_vals"]]
+    a[0] = a[0] + FR(1)
+    with pytest.raises(ValueError, match="나누어 떨어지지 않"):
+        prover.prove(None, a, [FR(int(x)) for x in f["b_vals"]], [FR(int(x)) for x in f["c_vals"]], [], pp, srs)
+
+
+def test_prove_is_randomised_but_consistent(native):
+    """PLONK blinding is random: two proofs differ, each satisfies X_comm == commit(X)."""
+    from interactive_zkp_study_b200.zkp.plonk.field import FR
+    from interactive_zkp_study_b200.zkp.plonk.preprocessor import preprocess
+    from interactive_zkp_study_b200.zkp.plonk import prover
+    f = load("plonk_x3.json")
+    srs = _srs(f)
+    pp = preprocess(StubCircuit(f, FR), srs)
+    args = ([FR(int(x)) for x in f["a_vals"]], [FR(int(x)) for x in f["b_vals"]], [FR(int(x)) for x in f["c_vals"]], [], pp, srs)
+    p1, p2 = prover.prove(None, *args), prover.prove(None, *args)
+    assert _pt(p1.a_comm) != _pt(p2.a_comm)
+    assert bn254.g1_is_on_curve(_pt(p1.W_zeta_comm)) and bn254.g1_is_on_curve(_pt(p2.W_zeta_omega_comm))
