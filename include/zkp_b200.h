@@ -140,6 +140,16 @@ int zkp_fr_poly_mul(const uint8_t* a, uint64_t a_len, const uint8_t* b, uint64_t
 int zkp_fr_poly_divmod(const uint8_t* a, uint64_t a_len, const uint8_t* b, uint64_t b_len, uint8_t* q_out,
                        uint8_t* r_out);
 
+/* ---- measurement helpers (bench.py) -----------------------------------------------------------
+ * Per-stage CUDA-event profile of the most recent MSM (events recorded on the library stream).
+ * zkp_msm_last_profile sums the stages whose name contains `stage` ("accumulate", "ws", "horner",
+ * "digits", "scatter", "tasks", "fold"; NULL = the whole MSM), in microseconds. */
+int zkp_msm_profile(int enable);
+int zkp_msm_last_profile(const char* stage, float* out_us);
+/* Page-locked host staging buffers for the end-to-end measurement (H2D from pinned memory). */
+int zkp_pinned_alloc(uint64_t bytes, void** out);
+int zkp_pinned_free(void* p);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* Dependent-free integer-MAD microbenchmark: variant 0 = IMAD.WIDE.U32 (the roofline unit),
  * 1 = IMAD (32-bit lo), 2 = IMAD.HI.  Returns G(limb-MAC)/s over the whole chip. */

@@ -69,6 +69,10 @@ PROTOTYPES = {
     "zkp_groth16_quotient": (c_int, [vp, vp, vp, u64, vp, u64, vp, vp]),
     "zkp_fr_poly_mul": (c_int, [vp, u64, vp, u64, vp]),
     "zkp_fr_poly_divmod": (c_int, [vp, u64, vp, u64, vp, vp]),
+    "zkp_msm_profile": (c_int, [c_int]),
+    "zkp_msm_last_profile": (c_int, [ctypes.c_char_p, f32p]),
+    "zkp_pinned_alloc": (c_int, [u64, ctypes.POINTER(ctypes.c_void_p)]),
+    "zkp_pinned_free": (c_int, [vp]),
     "zkp_imad_peak": (c_int, [c_int, f64p, f64p]),
     "zkp_dbg_field_op": (c_int, [c_int, c_int, vp, vp, u64, vp]),
     "zkp_dbg_point_add": (c_int, [c_int, vp, vp, u64, vp]),
@@ -138,4 +142,6 @@ def buf(b):
         return ctypes.cast((ctypes.c_char * len(b)).from_buffer(b), ctypes.c_void_p) if len(b) else None
     if isinstance(b, bytes):
         return ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p)
+    if isinstance(b, (int, ctypes.c_void_p)):  # raw address (pinned staging buffer)
+        return b
     raise TypeError("expected bytes or bytearray")

@@ -13,6 +13,10 @@ static std::mutex g_err_mu;
 static std::string g_last_error;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 
+static StageProfile g_last_profile;
+int g_msm_profile_enabled = 0;
+StageProfile& last_msm_profile() { return g_last_profile; }
+
 Context& ctx() {
   if (!g_ready) throw std::runtime_error("zkp_init has not been called successfully");
   return g_ctx;
@@ -292,6 +296,38 @@ int zkp_scalars_download(uint64_t scalars, uint64_t offset, uint64_t n, uint8_t*
     CUDA_CHECK(cudaMemcpyAsync(out, r->buf.as<uint8_t>() + offset * 32, n * 32, cudaMemcpyDeviceToHost, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
   });
+}
+
+int zkp_msm_profile(int enable) {
+  g_msm_profile_enabled = enable ? 1 : 0;
+  return ZKP_OK;
+}
+
+// Sums, over the stages of the last MSM, the device time of every stage whose name contains `stage`
+// (NULL or "" = whole MSM).  Stage names: "digits+scan", "scatter", "tasks", "accumulate", "fold",
+// "ws wide", "ws2", "horner+affine".
+int zkp_msm_last_profile(const char* stage, float* out_us) {
+  if (!out_us) return ZKP_ERR_INVALID_ARGUMENT;
+  const StageProfile& p = last_msm_profile();
+  if (!stage || !*stage) {
+    *out_us = p.total_us;
+    return ZKP_OK;
+  }
+  float acc = 0;
+  for (auto& kv : p.stages)
+    if (kv.first.find(stage) != std::string::npos) acc += kv.second;
+  *out_us = acc;
+  return ZKP_OK;
+}
+
+int zkp_pinned_alloc(uint64_t bytes, void** out) {
+  return guarded([&](Context&) {
+    if (!out) throw InvalidArgument("zkp_pinned_alloc: null out");
+    CUDA_CHECK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  });
+}
+int zkp_pinned_free(void* p) {
+  return guarded([&](Context&) { CUDA_CHECK(cudaFreeHost(p)); });
 }
 
 int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effective) {

@@ -56,14 +56,23 @@ struct Context {
   unsigned long long launches = 0;  // kernels launched by this library (bench.py "gpu_launches")
 };
 
-// Optional per-stage CUDA-event trace (ZKP_B200_TRACE=1): prints the device time between marks.
+// Per-stage CUDA-event profile of the last MSM (enabled by zkp_msm_profile(1) or ZKP_B200_TRACE=1):
+// device time between marks, kept for zkp_msm_last_profile and optionally printed.
+struct StageProfile {
+  std::vector<std::pair<std::string, float>> stages;  // (name, microseconds)
+  float total_us = 0;
+};
+StageProfile& last_msm_profile();
+extern int g_msm_profile_enabled;
+
 struct StageTrace {
-  bool on;
+  bool on, print;
   cudaStream_t st;
   std::vector<std::pair<std::string, cudaEvent_t>> ev;
   explicit StageTrace(cudaStream_t s) : st(s) {
     static const bool env = getenv("ZKP_B200_TRACE") && atoi(getenv("ZKP_B200_TRACE"));
-    on = env;
+    print = env;
+    on = env || g_msm_profile_enabled;
     mark("start");
   }
   void mark(const char* name) {
@@ -76,14 +85,18 @@ struct StageTrace {
   ~StageTrace() {
     if (!on || ev.empty()) return;
     cudaEventSynchronize(ev.back().second);
+    StageProfile& prof = last_msm_profile();
+    prof.stages.clear();
     for (size_t i = 1; i < ev.size(); i++) {
       float ms = 0;
       cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
-      fprintf(stderr, "[zkp trace] %-18s %8.1f us\n", ev[i].first.c_str(), ms * 1e3);
+      prof.stages.emplace_back(ev[i].first, ms * 1e3f);
+      if (print) fprintf(stderr, "[zkp trace] %-18s %8.1f us\n", ev[i].first.c_str(), ms * 1e3);
     }
     float tot = 0;
     cudaEventElapsedTime(&tot, ev.front().second, ev.back().second);
-    fprintf(stderr, "[zkp trace] %-18s %8.1f us\n", "TOTAL", tot * 1e3);
+    prof.total_us = tot * 1e3f;
+    if (print) fprintf(stderr, "[zkp trace] %-18s %8.1f us\n", "TOTAL", tot * 1e3);
     for (auto& kv : ev) cudaEventDestroy(kv.second);
   }
 };

@@ -102,6 +102,42 @@ def imad_peak(variant=0):
     return g.value
 
 
+def msm_profile(enable):
+    check(_lib.lib().zkp_msm_profile(1 if enable else 0))
+
+
+def msm_last_profile(stage=None):
+    """Device microseconds of the named stage(s) of the most recent MSM (None = whole MSM)."""
+    us = ctypes.c_float()
+    check(_lib.lib().zkp_msm_last_profile(stage.encode() if stage else None, ctypes.byref(us)))
+    return us.value
+
+
+class PinnedBuffer:
+    """Page-locked host memory (cudaHostAlloc) exposed as a writable ctypes array."""
+
+    def __init__(self, nbytes):
+        p = ctypes.c_void_p()
+        check(_lib.lib().zkp_pinned_alloc(nbytes, ctypes.byref(p)))
+        self.addr = p.value
+        self.nbytes = nbytes
+        self.view = (ctypes.c_char * nbytes).from_address(self.addr)
+
+    def write(self, data, offset=0):
+        ctypes.memmove(self.addr + offset, data, len(data))
+
+    def free(self):
+        if self.addr:
+            _lib.lib().zkp_pinned_free(self.addr)
+            self.addr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def set_window_bits(c):
     check(_lib.lib().zkp_msm_set_window_bits(int(c)))
 

@@ -1,0 +1,58 @@
+"""CPU: the C ABI builds, loads, and exports exactly what include/zkp_b200.h declares; without a
+GPU every compute entry point fails loudly (there is no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "zkp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(zkp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from interactive_zkp_study_b200 import _lib
+    lib = _lib.load_library()
+    names = _declared()
+    assert len(names) >= 40
+    for name in names:
+        assert hasattr(lib, name), name
+    assert sorted(_lib.PROTOTYPES) == names  # the ctypes table and the header agree
+
+
+def test_header_cites_the_reference_interface():
+    src = open(os.path.join(ROOT, "include", "zkp_b200.h")).read()
+    for cite in ("zkp/plonk/kzg.py:59-67", "zkp/groth16/proving.py", "zkp/plonk/polynomial.py:292-341",
+                 "zkp/groth16/poly_utils.py:116-125", "zkp/plonk/srs.py:78-82"):
+        assert cite in src
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="a GPU is present")
+def test_no_cpu_fallback_without_a_gpu():
+    from interactive_zkp_study_b200 import _lib, native
+    lib = _lib.load_library()
+    out = (ctypes.c_uint8 * 64)()
+    inf = ctypes.c_int()
+    rc = lib.zkp_g1_msm(None, None, 0, out, ctypes.byref(inf))
+    assert rc == -2                                   # ZKP_ERR_NOT_INITIALISED
+    assert b"no CPU fallback" in lib.zkp_last_error()
+    with pytest.raises(native.ZkpB200Error):
+        native.g1_msm(b"", b"", 0)
+    from interactive_zkp_study_b200.zkp.plonk.polynomial import Polynomial
+    with pytest.raises(native.ZkpB200Error):
+        Polynomial([1, 2]) * Polynomial([3, 4])
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "interactive_zkp_study_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
+                assert "oracle." not in text.replace("oracle/", ""), os.path.join(dirpath, f)

@@ -1,0 +1,128 @@
+"""CPU: host-side logic of the drop-in layer that needs no device -- byte encodings, the compat
+field types, Polynomial trimming/degree, error behaviour, the multi-rank shard arithmetic (gloo)."""
+import os
+import socket
+
+import pytest
+
+from interactive_zkp_study_b200 import native
+from interactive_zkp_study_b200.compat import FQ, FQ2, FR, curve_order, field_modulus
+
+
+def test_encodings_round_trip():
+    assert native.fe_bytes(1) == b"\x01" + bytes(31)
+    v = [0, 1, curve_order - 1, 1 << 200]
+    assert native.fr_vec_from_bytes(native.fr_vec_bytes(v)) == v
+    p = (FQ(1), FQ(2))
+    assert native.g1_from_bytes(native.g1_bytes(p)) == (1, 2)
+    assert native.g1_bytes(None) == bytes(64) and native.g1_from_bytes(bytes(64)) is None
+    q = (FQ2([1, 2]), FQ2([3, 4]))
+    assert native.g2_from_bytes(native.g2_bytes(q)) == ((1, 2), (3, 4))
+    assert native.g2_bytes(((1, 2), (3, 4))) == native.g2_bytes(q)
+
+
+def test_compat_field_semantics_match_py_ecc():
+    a, b = FR(5), FR(curve_order - 2)
+    assert int(a + b) == 3 and int(a - b) == 7 and int(a * 3) == 15 and int(3 * a) == 15
+    assert int(FR(-1)) == curve_order - 1 and int(-a) == curve_order - 5
+    assert a / a == FR(1) and int(FR(0) / FR(0)) == 0       # inv(0) == 0
+    assert int(FR(1) / a * a) == 1 and int(2 / FR(2)) == 1
+    assert a ** 0 == FR(1) and int(a ** 3) == 125 and a == 5 and a != 6
+    assert int(FQ(field_modulus + 4)) == 4 and isinstance(a + 1, FR) and not isinstance(FQ(1) + 1, FR)
+    with pytest.raises(TypeError):
+        a == "5"
+    with pytest.raises(TypeError):
+        FR(1.5)
+
+
+def test_polynomial_host_behaviour():
+    from interactive_zkp_study_b200.zkp.plonk.polynomial import Polynomial
+    from interactive_zkp_study_b200.zkp.plonk.field import get_root_of_unity
+    p = Polynomial([1, 2, 0, 0])
+    assert [int(c) for c in p.coeffs] == [1, 2] and p.degree == 1 and len(p) == 2 and not p.is_zero()
+    assert Polynomial().is_zero() and Polynomial([0, 0, 0]).degree == 0 and Polynomial.zero() == Polynomial([0])
+    assert Polynomial([3]) == 3 and Polynomial([3]) == FR(3) and (Polynomial([1]) == "x") is False
+    assert repr(Polynomial([1, 0, 3])) == "Poly(1 + 3*x^2)" and repr(Polynomial.zero()) == "Poly(0)"
+    assert [int(c) for c in Polynomial.vanishing(4).coeffs] == [curve_order - 1, 0, 0, 0, 1]
+    assert int(get_root_of_unity(1)) == 1
+    assert int(get_root_of_unity(4)) == 21888242871839275217838484774961031246007050428528088939761107053157389710902
+    for bad in (0, 3, 12, (1 << 28) + 1):
+        with pytest.raises(ValueError):
+            get_root_of_unity(bad)
+
+
+def test_transcript_bytes_follow_the_reference_layout():
+    import hashlib
+    from interactive_zkp_study_b200.zkp.plonk.transcript import Transcript
+    t = Transcript()
+    t.append_point(b"a_comm", (FQ(1), FQ(2)))
+    t.append_point(b"b_comm", None)
+    t.append_scalar(b"x", FR(7))
+    state = b"plonk" + b"a_comm" + (1).to_bytes(32, "big") + (2).to_bytes(32, "big") + b"b_comm" + bytes(64) + \
+        b"x" + (7).to_bytes(32, "big") + b"beta"
+    want = int.from_bytes(hashlib.sha256(state).digest(), "big") % curve_order
+    assert int(t.challenge_scalar(b"beta")) == want
+    assert bytes(t.state) == state + hashlib.sha256(state).digest()
+
+
+def test_commit_degree_check_precedes_any_device_work():
+    from interactive_zkp_study_b200.zkp.plonk.polynomial import Polynomial
+    from interactive_zkp_study_b200.zkp.plonk.kzg import commit
+    from interactive_zkp_study_b200.zkp.plonk.srs import SRS
+    srs = SRS([(FQ(1), FQ(2))] * 3, [None, None], 2)
+    with pytest.raises(ValueError, match="SRS"):
+        commit(Polynomial([1, 2, 3, 4]), srs)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from oracle import bn254, synthetic
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 24                                   # points per rank
+    # same partition bench.py uses: rank r owns global indices [r*n, (r+1)*n)
+    s = synthetic.scalars(0x5EED0002, n * world)[rank * n:(rank + 1) * n]
+    k = synthetic.scalars(0x5EED0001, n * world)[rank * n:(rank + 1) * n]
+    pts = [bn254.g1_mul(bn254.G1, x) for x in s]
+    part = bn254.g1_msm(pts, k)             # the per-rank partial sum (CPU stand-in for the GPU shard)
+    enc = (b"\x00" * 64) if part is None else part[0].to_bytes(32, "little") + part[1].to_bytes(32, "little")
+    t = torch.frombuffer(bytearray(enc), dtype=torch.uint8)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)                  # the one exchange step of the sharded MSM
+    if rank == 0:
+        acc = None
+        for o in out:
+            b = bytes(o.numpy().tobytes())
+            p = None if b == bytes(64) else (int.from_bytes(b[:32], "little"), int.from_bytes(b[32:], "little"))
+            acc = bn254.g1_add(acc, p)
+        s_all = synthetic.scalars(0x5EED0002, n * world)
+        k_all = synthetic.scalars(0x5EED0001, n * world)
+        want = bn254.g1_mul(bn254.G1, sum(a * b for a, b in zip(s_all, k_all)) % bn254.R)
+        q.put(acc == want)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_msm_partition_and_combine_world2_gloo():
+    """N>1 path on CPU (gloo, world_size 2): contiguous point ranges, one gathered partial per rank,
+    fold on rank 0 == the unsharded MSM."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok is True
