@@ -30,11 +30,15 @@ UNIT = "Mpts/s"
 SEED_SCALARS = 0x5EED0001
 SEED_POINTS = 0x5EED0002
 MACS_PER_FP_MUL = 136                      # 8-limb CIOS: 8*(8+1+8) limb-MACs   
-ACC_MACS_PER_POINT = 160 * MACS_PER_FP_MUL  # 16 windows x 10 Fp-mul (XYZZ mixed add) = 21 760
+MODEL_ACC_MACS_PER_POINT = 160 * MACS_PER_FP_MUL  # SURVEY model: 16 windows x 10 Fp-mul (XYZZ mixed add) = 21 760
+
+
+def windows_for(c):
+    return (255 + c - 1) // c
 
 
 def msm_macs_per_point(n):
-    return ACC_MACS_PER_POINT + 14 * MACS_PER_FP_MUL * (1 << 20) / n  # + bucket reduction, amortised
+    return MODEL_ACC_MACS_PER_POINT + 14 * MACS_PER_FP_MUL * (1 << 20) / n  # + bucket reduction, amortised
 
 
 # ------------------------------------------------------------------ clocks sampling
@@ -52,7 +56,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -204,6 +208,24 @@ def run_ours(args):
         return nat.scalars_generate((seed + 64 * first) & ((1 << 64) - 1), count)
     s_h = stream(SEED_POINTS, rank * n, n)
     table = nat.g1_fixed_base_mul_dev(G1, s_h, n)
+    plain_ms = None
+    pre_c = 0 if args.plain else max(4, min(20, args.log_n - 3))
+    if pre_c:
+        # first the plain-table number (no precomputation), for the record
+        kk = stream(SEED_SCALARS + 0x9000, rank * n, n)
+        for _ in range(3):
+            nat.g1_msm_dev_partial(table, 0, kk, 0, n)
+        nat.sync()
+        nat.timer_start()
+        for _ in range(5):
+            nat.g1_msm_dev_partial(table, 0, kk, 0, n)
+        plain_ms = nat.timer_stop() / 5
+        kk.free()
+        # static table -> window-precomputed layout, once (like loading the SRS)
+        t0 = time.perf_counter()
+        nat.table_precompute(table, pre_c)
+        precompute_s = time.perf_counter() - t0
+    W_actual = windows_for(pre_c if pre_c else 16)
     n_vec = 4                            # rotate scalar vectors so no step reuses cached digits
     k_h = [stream(SEED_SCALARS + 0x1000 * v, rank * n, n) for v in range(n_vec)]
 
@@ -312,7 +334,8 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (bucket accumulation) against the measured integer peak
     acc_s = acc_us / steps * 1e-6
     peak_gmacs = max(peak["imad_hi_u32"], peak["imad_wide_u32"])
-    achieved = n * ACC_MACS_PER_POINT / acc_s / 1e12
+    acc_macs = n * W_actual * 10 * MACS_PER_FP_MUL   # the mixed additions this launch really performs
+    achieved = acc_macs / acc_s / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "accumulate_traffic.json")
     if os.path.exists(tpath):
@@ -324,16 +347,18 @@ def run_ours(args):
         "bound": "imad", "kernel": "msm_accumulate_kernel<Fp>", "achieved": achieved, "peak": peak_gmacs / 1e3,
         "unit": "T limb-MAC/s (one IMAD.WIDE.U32 = 32x32+64->64)", "frac": achieved / (peak_gmacs / 1e3),
         "traffic": traffic,
-        "algorithmic_macs_per_launch": n * ACC_MACS_PER_POINT,
+        "algorithmic_macs_per_launch": acc_macs,
+        "algorithmic_note": "%d windows x 10 Fp-mul (XYZZ mixed add) x 136 limb-MAC per point; the SURVEY 8d model "
+                            "(16 windows, 21 760 MAC/pt) is used for whole_msm.frac" % W_actual,
         "kernel_ms": acc_s * 1e3, "kernel_share_of_step": acc_us / max(msm_us, 1e-9),
         "peak_source": "measured live on this GPU by zkp_imad_peak (dependent-free IMAD.HI.U32 / IMAD.WIDE.U32 chains); "
                        "MEASURED_PEAKS.json has no integer peak",
         "peaks_gmacs": peak,
         "whole_msm": {"macs_per_point_model": msm_macs_per_point(n),
                       "frac": (n * msm_macs_per_point(n) / (msm_us / steps * 1e-6) / 1e12) / (peak_gmacs / 1e3)},
-        "hbm_view": {"algorithmic_bytes_per_launch": n * 16 * 68,
-                     "achieved_gbs": n * 16 * 68 / acc_s / 1e9,
-                     "note": "16 windows x (64 B point gather + 4 B index) per point: far below the HBM roof, the kernel is integer bound"},
+        "hbm_view": {"algorithmic_bytes_per_launch": n * W_actual * 68,
+                     "achieved_gbs": n * W_actual * 68 / acc_s / 1e9,
+                     "note": "windows x (64 B point gather + 4 B index) per point: far below the HBM roof, the kernel is integer bound"},
     }
     base = cpu_baseline(nat, table, k_h[0]) if world == 1 else None
     line = {
@@ -344,7 +369,12 @@ def run_ours(args):
             "workload": "BN254 G1 MSM, 2^%d synthetic points per GPU (configs[1]); P_i = s_i*G, scalars uniform in [0,r)" % args.log_n,
             "points_per_gpu": n, "total_points": total_points,
             "sharding": "contiguous point ranges, one 128 B XYZZ partial per rank gathered over NCCL" if world > 1 else "single GPU",
-            "l2": "working set (points 64 MiB + scalars + 2x64 MiB digit/index arrays + 64 MiB buckets) exceeds the 126 MB L2; "
+            "table": ("window-precomputed static table T[w][i] = 2^(%d w) P_i, %d windows, %.0f MiB per GPU, built once in %.0f ms "
+                      "(zkp_g1_table_precompute; SRS/CRS tables are fixed per circuit)" % (pre_c, W_actual, W_actual * n * 64 / 2**20, precompute_s * 1e3))
+                     if pre_c else "plain affine table, 64 B/point",
+            "plain_table": None if plain_ms is None else {"ms_per_step": plain_ms, "value": n / plain_ms / 1e3, "unit": UNIT,
+                                                          "note": "same MSM without the precomputed windows (16 windows + Horner), this rank only"},
+            "l2": "working set (point table + scalars + 2x60 MiB digit/index arrays + bucket partials) exceeds the 126 MB L2; "
                   "a different scalar vector every step",
             "device": info["name"],
         },
@@ -369,6 +399,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=20, help="log2 of the points per GPU")
     ap.add_argument("--no-verify", dest="verify", action="store_false")
+    ap.add_argument("--plain", action="store_true", help="do not precompute the window table")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

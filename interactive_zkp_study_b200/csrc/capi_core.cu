@@ -98,6 +98,7 @@ __global__ void dbg_field_op_kernel(int op, const FE* a, const FE* b, uint64_t n
     case 1: r = x - y; break;
     case 2: r = x * y; break;
     case 3: r = x.inv(); break;
+    case 5: r = x.inv_fermat(); break;
     default: r = x.sqr(); break;
   }
   out[i] = r.from_mont();
@@ -368,7 +369,7 @@ int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effecti
 
 int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out) {
   return guarded([&](Context& c) {
-    if (!a || !out || op < 0 || op > 4) throw InvalidArgument("zkp_dbg_field_op: bad argument");
+    if (!a || !out || op < 0 || op > 5) throw InvalidArgument("zkp_dbg_field_op: bad argument");
     if (n == 0) return;
     DevBuf da, db, dout;
     da.reserve(n * 32);

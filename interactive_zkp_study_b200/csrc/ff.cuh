@@ -285,8 +285,101 @@ struct __align__(16) Mont256 {
     return acc;
   }
 
-  // Fermat inverse a^(MOD-2); inv(0) = 0 as in py_ecc's prime_field_inv.
+  // Inverse, inv(0) = 0 as in py_ecc's prime_field_inv.  Binary extended Euclid on the integer held in
+  // the limbs (shifts, adds and subtractions only: ~4x shorter than the 254-squaring Fermat chain for
+  // a lone thread), then one Montgomery product by R^3 to land back in Montgomery form:
+  // (aR)^-1 * R^3 * R^-1 = a^-1 R.
   __device__ __noinline__ Mont256 inv() const {
+    if (is_zero()) return *this;
+    uint32_t u[8], w[8], x1[8], x2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      u[i] = v[i];
+      w[i] = P::MOD_(i);
+      x1[i] = i == 0 ? 1u : 0u;
+      x2[i] = 0u;
+    }
+    auto is_one = [](const uint32_t (&a)[8]) {
+      uint32_t o = a[0] ^ 1u;
+#pragma unroll
+      for (int i = 1; i < 8; i++) o |= a[i];
+      return o == 0;
+    };
+    auto shr1 = [](uint32_t (&a)[8], uint32_t top) {
+#pragma unroll
+      for (int i = 0; i < 7; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+      a[7] = (a[7] >> 1) | (top << 31);
+    };
+    auto halve_mod = [&](uint32_t (&a)[8]) {  // a <- a / 2 mod MOD
+      uint32_t carry = 0;
+      if (a[0] & 1u) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          c += (uint64_t)a[i] + P::MOD_(i);
+          a[i] = (uint32_t)c;
+          c >>= 32;
+        }
+        carry = (uint32_t)c;
+      }
+      shr1(a, carry);
+    };
+    auto geq = [](const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+#pragma unroll
+      for (int i = 7; i >= 0; i--) {
+        if (a[i] != b[i]) return a[i] > b[i];
+      }
+      return true;
+    };
+    auto sub = [](uint32_t (&a)[8], const uint32_t (&b)[8]) {  // a <- a - b, returns borrow
+      uint64_t br = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)a[i] - b[i] - br;
+        a[i] = (uint32_t)d;
+        br = (d >> 63) & 1u;
+      }
+      return (uint32_t)br;
+    };
+    auto sub_mod = [&](uint32_t (&a)[8], const uint32_t (&b)[8]) {  // a <- a - b mod MOD
+      if (sub(a, b)) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          c += (uint64_t)a[i] + P::MOD_(i);
+          a[i] = (uint32_t)c;
+          c >>= 32;
+        }
+      }
+    };
+    while (!is_one(u) && !is_one(w)) {
+      while (!(u[0] & 1u)) {
+        shr1(u, 0);
+        halve_mod(x1);
+      }
+      while (!(w[0] & 1u)) {
+        shr1(w, 0);
+        halve_mod(x2);
+      }
+      if (geq(u, w)) {
+        sub(u, w);
+        sub_mod(x1, x2);
+      } else {
+        sub(w, u);
+        sub_mod(x2, x1);
+      }
+    }
+    Mont256 r, r3;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      r.v[i] = is_one(u) ? x1[i] : x2[i];
+      r3.v[i] = P::R3_(i);
+    }
+    return r * r3;
+  }
+
+  // Fermat inverse a^(MOD-2), kept as an independent cross-check of inv() (tests).
+  __device__ __noinline__ Mont256 inv_fermat() const {
     uint32_t e[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) e[i] = P::MOD_(i);

@@ -26,6 +26,7 @@
 namespace zkp {
 
 static constexpr uint32_t MSM_INVALID = 0xffffffffu;
+static constexpr int MSM_MAX_C = 20;
 static constexpr int MSM_SCALAR_BITS = 255;  // 254-bit scalars + 1 for the signed-digit carry
 
 struct MsmPlan {
@@ -43,7 +44,7 @@ inline MsmPlan msm_plan(uint64_t n, int force_c = 0) {
     while ((1ull << (lg + 1)) <= n) lg++;
     c = lg - 4;
     if (c < 4) c = 4;
-    if (c > 16) c = 16;
+    if (c > 16) c = 16;  // automatic choice; explicit widths up to MSM_MAX_C are accepted
   }
   MsmPlan p;
   p.c = c;
@@ -54,8 +55,10 @@ inline MsmPlan msm_plan(uint64_t n, int force_c = 0) {
 }
 
 // ---------------------------------------------------------------- stage 1: digits + histogram
+// wstride: distance between the bucket sets of consecutive windows (B for a plain table; 0 for a
+// window-precomputed table, where all windows share one bucket set).
 static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, int c, int W, uint32_t B,
-                                  uint32_t* __restrict__ codes, uint32_t* __restrict__ hist) {
+                                  uint32_t wstride, uint32_t* __restrict__ codes, uint32_t* __restrict__ hist) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t s[9];
@@ -93,10 +96,10 @@ static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, u
     if (v > B) {  // digit = v - 2^c  (negative), |digit| = 2^c - v in [1, B-1]
       uint32_t mag = (1u << c) - v;
       carry = 1;
-      if (mag != 0) code = (((uint32_t)w * B + (mag - 1)) << 1) | 1u;
+      if (mag != 0) code = (((uint32_t)w * wstride + (mag - 1)) << 1) | 1u;
     } else {
       carry = 0;
-      if (v != 0) code = (((uint32_t)w * B + (v - 1)) << 1);
+      if (v != 0) code = (((uint32_t)w * wstride + (v - 1)) << 1);
     }
     codes[(uint64_t)w * n + i] = code;
     if (code != MSM_INVALID) atomicAdd(&hist[code >> 1], 1u);
@@ -183,13 +186,17 @@ static __global__ void scan_apply_kernel(const uint32_t* __restrict__ in, uint32
 }
 
 // ---------------------------------------------------------------- stage 2: scatter
+// Plain table: the entry is the point index i.  Window-precomputed table (pre_stride != 0): the entry
+// is the index of 2^(c*w) * P_i inside the [w][i] table, w * pre_stride + pre_offset + i.
 static __global__ void msm_scatter_kernel(const uint32_t* __restrict__ codes, uint64_t total, uint64_t n,
-                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted,
+                                   uint32_t pre_stride, uint32_t pre_offset) {
   uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   uint32_t code = codes[idx];
   if (code == MSM_INVALID) return;
   uint32_t i = (uint32_t)(idx % n);
+  if (pre_stride) i += (uint32_t)(idx / n) * pre_stride + pre_offset;
   uint32_t pos = atomicAdd(&cursor[code >> 1], 1u);
   sorted[pos] = i | ((code & 1u) << 31);
 }
@@ -290,18 +297,100 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<F>* __
   partials[task.w] = acc;
 }
 
-// buckets[b] = sum of its tasks' partial sums (usually exactly one)
+// buckets[b] = sum of its tasks' partial sums (usually exactly one).  Buckets with more than
+// MSM_FOLD_SERIAL partials (skewed scalars, or a top window that only uses a few buckets) are queued
+// for the block-per-bucket kernel below so that no single thread walks thousands of partials.
+static constexpr uint32_t MSM_FOLD_SERIAL = 24;
 template <class F>
 __global__ void __launch_bounds__(128) msm_bucket_fold_kernel(const XYZZ<F>* __restrict__ partials,
                                                                const uint32_t* __restrict__ task_base, uint32_t nbuckets,
-                                                               XYZZ<F>* __restrict__ buckets) {
+                                                               XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ heavy_count,
+                                                               uint32_t* __restrict__ heavy_list) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbuckets) return;
   uint32_t t0 = task_base[b], t1 = task_base[b + 1];
+  if (t1 - t0 > MSM_FOLD_SERIAL) {
+    heavy_list[atomicAdd(heavy_count, 1u)] = b;
+    return;
+  }
   XYZZ<F> acc = XYZZ<F>::inf();
   if (t1 > t0) acc = partials[t0];
   for (uint32_t t = t0 + 1; t < t1; t++) acc.add(partials[t]);
   buckets[b] = acc;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) msm_bucket_fold_heavy_kernel(const XYZZ<F>* __restrict__ partials,
+                                                                     const uint32_t* __restrict__ task_base,
+                                                                     const uint32_t* __restrict__ heavy_count,
+                                                                     const uint32_t* __restrict__ heavy_list,
+                                                                     XYZZ<F>* __restrict__ buckets) {
+  __shared__ XYZZ<F> sm[128];
+  uint32_t count = *heavy_count;
+  for (uint32_t h = blockIdx.x; h < count; h += gridDim.x) {
+    uint32_t b = heavy_list[h];
+    uint32_t t0 = task_base[b], t1 = task_base[b + 1];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t t = t0 + threadIdx.x; t < t1; t += 128) acc.add(partials[t]);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {
+      if ((int)threadIdx.x < s) {
+        acc.add(sm[threadIdx.x + s]);
+        sm[threadIdx.x] = acc;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) buckets[b] = acc;
+    __syncthreads();
+  }
+}
+
+// Window-precomputed tables: T[w][i] = 2^(c*w) * P_i, so every window's digits weigh the same and all
+// windows share ONE bucket set (no per-window sums, no final doubling chain).
+// cur[i] <- 2^c * cur[i]   (XYZZ, c doublings)
+template <class F>
+__global__ void __launch_bounds__(128) msm_pre_shift_kernel(XYZZ<F>* __restrict__ cur, uint64_t n, int c) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  XYZZ<F> p = cur[i];
+  if (!p.is_inf())
+    for (int k = 0; k < c; k++) p = p.dbl();
+  cur[i] = p;
+}
+template <class F>
+__global__ void msm_pre_lift_kernel(const Affine<F>* __restrict__ pts, uint64_t n, XYZZ<F>* __restrict__ cur) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cur[i] = XYZZ<F>::from_affine(pts[i]);
+}
+// out[i] = affine(cur[i]) with one inversion per PRE_BATCH points (Montgomery's trick, strided).
+static constexpr int PRE_BATCH = 16;
+template <class F>
+__global__ void __launch_bounds__(128) msm_pre_affine_kernel(const XYZZ<F>* __restrict__ cur, uint64_t n, uint64_t T,
+                                                              Affine<F>* __restrict__ out) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  F pre[PRE_BATCH];
+  F acc = F::one();
+  int cnt = 0;
+  for (uint64_t i = t; i < n && cnt < PRE_BATCH; i += T, cnt++) {
+    pre[cnt] = acc;
+    const XYZZ<F>& p = cur[i];
+    if (!p.zz.is_zero()) acc = acc * (p.zz * p.zzz);
+  }
+  F inv = acc.inv();
+  for (int k = cnt - 1; k >= 0; k--) {
+    uint64_t i = t + (uint64_t)k * T;
+    XYZZ<F> p = cur[i];
+    Affine<F> a = Affine<F>::inf();
+    if (!p.zz.is_zero()) {
+      F d = inv * pre[k];         // 1 / (zz * zzz)
+      inv = inv * (p.zz * p.zzz);
+      a.x = p.x * (d * p.zzz);    // x / zz
+      a.y = p.y * (d * p.zz);     // y / zzz
+    }
+    out[i] = a;
+  }
 }
 
 // ---------------------------------------------------------------- stage 4: weighted-sum recursion
@@ -409,7 +498,7 @@ template <class F>
 struct MsmEngine {
   using FC = typename CompactOf<F>::type;  // same layout, out-of-line products (small code)
   DevBuf codes, sorted, hist, offsets, cursor, tile_sums, buckets, lvlA[2], lvlE[2], result, flag;
-  DevBuf ntask, task_base, len_bins, tasks, partials;
+  DevBuf ntask, task_base, len_bins, tasks, partials, folded, heavy;
   int reduce_L = 8;
   uint32_t wide_threshold = 1u << 17;  // items (all windows) above which a level is throughput bound
   bool compact_accumulate = false;
@@ -417,8 +506,34 @@ struct MsmEngine {
   // pts: device, affine Montgomery; scalars: device, canonical.  Leaves the affine canonical result
   // in `result` (and the infinity flag in `flag`), or the XYZZ Montgomery partial sum when
   // want_xyzz (multi-GPU shards).  Returns the number of kernels launched.
+  // Builds the window-precomputed table T[w][i] = 2^(c*w) * P_i (w < W, affine Montgomery) from the n
+  // plain points in `src`.  `dst` must hold W*n points; dst[0..n) may alias src.
+  int precompute(const Affine<F>* src, uint64_t n, int c, Affine<F>* dst, cudaStream_t st) {
+    MsmPlan pl = msm_plan(n, c);
+    DevBuf cur;
+    cur.reserve((size_t)n * sizeof(XYZZ<F>));
+    int launches = 0;
+    if (dst != src) CUDA_CHECK(cudaMemcpyAsync(dst, src, n * sizeof(Affine<F>), cudaMemcpyDeviceToDevice, st));
+    msm_pre_lift_kernel<F><<<ceil_div(n, 256), 256, 0, st>>>(src, n, cur.as<XYZZ<F>>());
+    CUDA_CHECK_LAUNCH();
+    launches++;
+    uint64_t T = (n + PRE_BATCH - 1) / PRE_BATCH;
+    for (int w = 1; w < pl.W; w++) {
+      msm_pre_shift_kernel<F><<<ceil_div(n, 128), 128, 0, st>>>(cur.as<XYZZ<F>>(), n, c);
+      CUDA_CHECK_LAUNCH();
+      msm_pre_affine_kernel<F><<<ceil_div(T, 128), 128, 0, st>>>(cur.as<XYZZ<F>>(), n, T, dst + (uint64_t)w * n);
+      CUDA_CHECK_LAUNCH();
+      launches += 2;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cur.release();
+    return launches;
+  }
+
+  // pre_stride != 0: `pts` is the base of a window-precomputed table [w][i] built with window width
+  // force_c; the MSM covers points [pre_offset, pre_offset + n) of it.
   int run(const Affine<F>* pts, const uint32_t* scalars, uint64_t n, cudaStream_t st, bool want_xyzz = false,
-          int force_c = 0) {
+          int force_c = 0, uint32_t pre_stride = 0, uint32_t pre_offset = 0) {
     int launches = 0;
     result.reserve(sizeof(XYZZ<F>) + sizeof(Affine<F>));
     flag.reserve(sizeof(int));
@@ -435,6 +550,8 @@ struct MsmEngine {
     MsmPlan pl = msm_plan(n, force_c);
     uint64_t total = (uint64_t)pl.W * n;
     if (total >= (1ull << 32)) throw std::runtime_error("msm: W*n must be < 2^32");
+    const uint32_t wstride = pre_stride ? 0u : pl.B;
+    if (pre_stride) pl.nbuckets = pl.B;  // precomputed windows: every digit of every window lands in one bucket set
     codes.reserve(total * 4);
     sorted.reserve(total * 4);
     hist.reserve((size_t)pl.nbuckets * 4);
@@ -446,7 +563,7 @@ struct MsmEngine {
 
     StageTrace tr(st);
     CUDA_CHECK(cudaMemsetAsync(hist.p, 0, (size_t)pl.nbuckets * 4, st));
-    msm_digits_kernel<<<ceil_div(n, 256), 256, 0, st>>>(scalars, n, pl.c, pl.W, pl.B, codes.as<uint32_t>(),
+    msm_digits_kernel<<<ceil_div(n, 256), 256, 0, st>>>(scalars, n, pl.c, pl.W, pl.B, wstride, codes.as<uint32_t>(),
                                                        hist.as<uint32_t>());
     CUDA_CHECK_LAUNCH();
     scan_tile_sums_kernel<<<ntiles, SCAN_BLOCK, 0, st>>>(hist.as<uint32_t>(), pl.nbuckets, tile_sums.as<uint32_t>());
@@ -458,8 +575,10 @@ struct MsmEngine {
     CUDA_CHECK_LAUNCH();
     tr.mark("digits+scan");
     CUDA_CHECK(cudaMemcpyAsync(cursor.p, offsets.p, ((size_t)pl.nbuckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    if (pre_stride && (uint64_t)pl.W * pre_stride >= (1ull << 31))
+      throw std::runtime_error("msm: precomputed table too large for 31-bit entry indices");
     msm_scatter_kernel<<<ceil_div(total, 256), 256, 0, st>>>(codes.as<uint32_t>(), total, n, cursor.as<uint32_t>(),
-                                                            sorted.as<uint32_t>());
+                                                            sorted.as<uint32_t>(), pre_stride, pre_offset);
     CUDA_CHECK_LAUNCH();
     tr.mark("scatter");
     // tasks: count per bucket -> scan -> length histogram -> emit sorted by length
@@ -502,10 +621,17 @@ struct MsmEngine {
                                                                         d_ntasks, partials.as<XYZZ<F>>());
     CUDA_CHECK_LAUNCH();
     tr.mark("accumulate");
+    heavy.reserve(((size_t)pl.nbuckets + 1) * 4);
+    CUDA_CHECK(cudaMemsetAsync(heavy.p, 0, 4, st));
     msm_bucket_fold_kernel<FC><<<ceil_div(pl.nbuckets, 128), 128, 0, st>>>(
-        partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(), pl.nbuckets, buckets.as<XYZZ<FC>>());
+        partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(), pl.nbuckets, buckets.as<XYZZ<FC>>(), heavy.as<uint32_t>(),
+        heavy.as<uint32_t>() + 1);
     CUDA_CHECK_LAUNCH();
-    launches += 15;
+    msm_bucket_fold_heavy_kernel<FC><<<296, 128, 0, st>>>(partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(),
+                                                          heavy.as<uint32_t>(), heavy.as<uint32_t>() + 1,
+                                                          buckets.as<XYZZ<FC>>());
+    CUDA_CHECK_LAUNCH();
+    launches += 16;
 
     // weighted-sum recursion down to one item per window
     uint32_t n_in = pl.B;
@@ -513,6 +639,7 @@ struct MsmEngine {
     const XYZZ<FC>* E = nullptr;
     int pp = 0;
     tr.mark("fold");
+    if (pre_stride) pl.W = 1;  // one shared bucket set: reduce a single "window", no Horner
     while (n_in > 1) {
       // wide levels (many items): radix reduce_L running sums, fewest group operations per bucket;
       // narrow levels: radix 2 on two threads, shortest dependency chain.

@@ -97,6 +97,33 @@ struct GroupApi {
     if (out_is_inf) *out_is_inf = flag;
   }
 
+  // plain table: the sub-range is just a pointer offset; precomputed table: stride/offset indexing
+  static int run_on_table(Context& c, Resource* t, uint64_t offset, const uint32_t* dscalars, uint64_t n, bool partial) {
+    if (t->pre_c)
+      return engine().run(t->buf.as<Affine<F>>(), dscalars, n, c.stream, partial, t->pre_c, (uint32_t)t->n,
+                          (uint32_t)offset);
+    return engine().run(t->buf.as<Affine<F>>() + offset, dscalars, n, c.stream, partial, g_force_window_bits);
+  }
+
+  static int table_precompute(uint64_t table, int window_bits) {
+    return guarded([&](Context& c) {
+      Resource* t = need(table, KIND, "table_precompute");
+      if (t->pre_c) throw InvalidArgument("table_precompute: table is already precomputed");
+      if (window_bits < 2 || window_bits > MSM_MAX_C) throw InvalidArgument("table_precompute: window_bits must be in [2,20]");
+      if (t->n == 0) return;
+      MsmPlan pl = msm_plan(t->n, window_bits);
+      if ((uint64_t)pl.W * t->n >= (1ull << 31)) throw InvalidArgument("table_precompute: W*n must be < 2^31");
+      DevBuf big;
+      big.reserve((size_t)pl.W * t->n * PT);
+      c.launches += engine().precompute(t->buf.as<Affine<F>>(), t->n, window_bits, big.as<Affine<F>>(), c.stream);
+      t->buf.release();
+      t->buf = big;
+      big.p = nullptr;
+      big.cap = 0;
+      t->pre_c = window_bits;
+    });
+  }
+
   static int table_load(const uint8_t* pts, uint64_t n, uint64_t* handle) {
     return guarded([&](Context& c) {
       if (!handle || (n && !pts)) throw InvalidArgument("table_load: null argument");
@@ -137,8 +164,7 @@ struct GroupApi {
         ds.reserve(n * 32);
         CUDA_CHECK(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
       }
-      c.launches += engine().run(t->buf.as<Affine<F>>() + offset, ds.as<uint32_t>(), n, c.stream, false,
-                                 g_force_window_bits);
+      c.launches += run_on_table(c, t, offset, ds.as<uint32_t>(), n, false);
       fetch_result(c, out_xy, out_is_inf);
     });
   }
@@ -151,8 +177,7 @@ struct GroupApi {
       if (!out) throw InvalidArgument("msm_dev: null output");
       if (offset + n > t->n || sc_offset + n > s->n) throw InvalidArgument("msm_dev: range out of bounds");
       MsmEngine<F>& e = engine();
-      c.launches += e.run(t->buf.as<Affine<F>>() + offset, s->buf.as<uint32_t>() + 8 * sc_offset, n, c.stream, partial,
-                          g_force_window_bits);
+      c.launches += run_on_table(c, t, offset, s->buf.as<uint32_t>() + 8 * sc_offset, n, partial);
       if (partial) {
         CUDA_CHECK(cudaMemcpyAsync(out, e.result.template as<char>() + PT, sizeof(XYZZ<F>), cudaMemcpyDeviceToHost,
                                    c.stream));

@@ -11,8 +11,8 @@ using Api = GroupApi<Fp>;
 extern "C" {
 
 int zkp_msm_set_window_bits(int c) {
-  if (c != 0 && (c < 2 || c > 16)) {
-    set_last_error("zkp_msm_set_window_bits: c must be 0 or in [2,16]");
+  if (c != 0 && (c < 2 || c > MSM_MAX_C)) {
+    set_last_error("zkp_msm_set_window_bits: c must be 0 or in [2,20]");
     return ZKP_ERR_INVALID_ARGUMENT;
   }
   g_force_window_bits = c;
@@ -44,6 +44,8 @@ int zkp_g1_fixed_base_mul(const uint8_t base_xy[64], const uint8_t* scalars, uin
 int zkp_g1_fixed_base_mul_dev(const uint8_t base_xy[64], uint64_t scalars, uint64_t n, uint64_t* out_table) {
   return Api::fixed_base_dev(base_xy, scalars, n, out_table);
 }
+
+int zkp_g1_table_precompute(uint64_t table, int window_bits) { return Api::table_precompute(table, window_bits); }
 
 // G1 or G2 table -> canonical affine points on the host
 int zkp_table_download(uint64_t table, uint64_t offset, uint64_t n, uint8_t* out_pts) {

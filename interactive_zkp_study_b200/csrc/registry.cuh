@@ -14,6 +14,7 @@ enum class HandleKind : int { G1Table = 1, G2Table = 2, Scalars = 3 };
 struct Resource {
   HandleKind kind;
   uint64_t n = 0;  // elements (points or scalars)
+  int pre_c = 0;   // point tables: window width of the precomputed layout [w][i] (0 = plain)
   DevBuf buf;
 };
 

@@ -179,6 +179,12 @@ def g2_table_load(pts_bytes, n):
     return _load("zkp_g2_table_load", pts_bytes, n, "g2")
 
 
+def table_precompute(handle, window_bits):
+    fn = _lib.lib().zkp_g1_table_precompute if handle.kind == "g1" else _lib.lib().zkp_g2_table_precompute
+    check(fn(handle.handle, int(window_bits)))
+    handle.pre_c = int(window_bits)
+
+
 def scalars_load(sc_bytes, n):
     return _load("zkp_scalars_load", sc_bytes, n, "fr")
 

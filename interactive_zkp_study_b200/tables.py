@@ -31,11 +31,22 @@ def _get(points, g2):
         handle = native.g2_table_load(native.g2_vec_bytes(points), n)
     else:
         handle = native.g1_table_load(native.g1_vec_bytes(points), n)
+    _maybe_precompute(handle, n)
     _cache[key] = (fp, handle)
     while len(_cache) > _MAX_ENTRIES:
         _, (_, old) = _cache.popitem(last=False)
         old.free()
     return handle
+
+
+PRECOMPUTE_MIN_POINTS = 1 << 14
+
+
+def _maybe_precompute(handle, n):
+    """Large static tables get the window-precomputed layout (no doubling chain per MSM); small ones
+    (toy SRS) stay plain: their MSMs are launch-latency bound either way."""
+    if n >= PRECOMPUTE_MIN_POINTS:
+        native.table_precompute(handle, max(4, min(20, n.bit_length() - 4)))
 
 
 def g1_table(points):
@@ -54,4 +65,5 @@ def clear():
 
 def adopt_g1(points, handle):
     """Register an already device-resident table (e.g. fresh from SRS.generate) for `points`."""
+    _maybe_precompute(handle, len(points))
     _cache[(id(points), False)] = (_fingerprint(points, False), handle)

@@ -34,7 +34,8 @@ def test_field_ops_bit_exact(native, field, mod):
     assert _unvec(native.dbg_field_op(field, 4, ab, None, n)) == [(x * x) % mod for x in a]
     m = 300
     got = _unvec(native.dbg_field_op(field, 3, _vec(a[:m]), None, m))
-    assert got == [bn254.inv(x, mod) for x in a[:m]]  # inv(0) == 0 as in py_ecc
+    assert got == [bn254.inv(x, mod) for x in a[:m]]  # inv(0) == 0 as in py_ecc (binary extended Euclid)
+    assert _unvec(native.dbg_field_op(field, 5, _vec(a[:m]), None, m)) == got  # Fermat chain agrees
 
 
 def test_g1_add_all_cases(native):

@@ -39,7 +39,7 @@ def test_g1_msm_empty_is_infinity(native):
     assert native.g1_msm(b"", b"", 0) is None
 
 
-@pytest.mark.parametrize("c", [2, 5, 9, 13, 16])
+@pytest.mark.parametrize("c", [2, 5, 9, 13, 14, 16, 18, 20])
 def test_g1_msm_every_window_width(native, c):
     rng = random.Random(200 + c)
     pts = _points_g1(rng, 300)
@@ -144,3 +144,58 @@ def test_g1_msm_full_size_known_dlog(native, log_n):
     got = native.g1_msm_dev(table, 0, k_h, 0, n)
     total = sum(a * b for a, b in zip(k, s)) % R
     assert got == bn254.g1_mul(bn254.G1, total)
+
+
+@pytest.mark.parametrize("c", [4, 7, 12, 14, 16, 19])
+def test_precomputed_table_matches_plain(native, c):
+    """Window-precomputed tables (zkp_g1_table_precompute) give the same affine point as the oracle,
+    for whole-table and sub-range MSMs, host and device scalars, incl. infinity entries."""
+    rng = random.Random(400 + c)
+    n = 300
+    pts = _points_g1(rng, n)
+    pts[17] = None
+    scalars = [rng.randrange(R) for _ in range(n)]
+    scalars[3] = 0
+    scalars[4] = R - 1
+    table = native.g1_table_load(native.g1_vec_bytes(pts), n)
+    native.table_precompute(table, c)
+    assert native.g1_msm_table(table, 0, native.fr_vec_bytes(scalars), n) == bn254.g1_msm(pts, scalars)
+    assert native.g1_msm_table(table, 50, native.fr_vec_bytes(scalars[:120]), 120) == bn254.g1_msm(pts[50:170], scalars[:120])
+    sc = native.scalars_load(native.fr_vec_bytes(scalars), n)
+    assert native.g1_msm_dev(table, 100, sc, 7, 150) == bn254.g1_msm(pts[100:250], scalars[7:157])
+    p0 = native.g1_msm_dev_partial(table, 0, sc, 0, 150)
+    p1 = native.g1_msm_dev_partial(table, 150, sc, 150, 150)
+    assert native.g1_combine_partials(p0 + p1, 2) == bn254.g1_msm(pts, scalars)
+    back = native.table_download(table, 0, n)     # window 0 is the plain table
+    assert [native.g1_from_bytes(back[64 * i:64 * i + 64]) for i in range(n)] == pts
+    assert native.g1_msm_table(table, 0, native.fr_vec_bytes([0] * n), n) is None
+
+
+def test_precomputed_g2_table(native):
+    rng = random.Random(55)
+    base = [bn254.g2_mul(bn254.G2, rng.randrange(1, 1 << 60)) for _ in range(3)]
+    pts, acc = [], base[0]
+    for i in range(40):
+        acc = bn254.g2_add(acc, base[i % 3])
+        pts.append(acc)
+    scalars = [rng.randrange(R) for _ in range(40)]
+    table = native.g2_table_load(native.g2_vec_bytes(pts), 40)
+    native.table_precompute(table, 8)
+    assert native.g2_msm_table(table, 0, native.fr_vec_bytes(scalars), 40) == bn254.g2_msm(pts, scalars)
+
+
+def test_precomputed_full_size_known_dlog(native):
+    n = 1 << 18
+    s_h = native.scalars_generate(0x5EED0002, n)
+    k_h = native.scalars_generate(0x5EED0001, n)
+    table = native.g1_fixed_base_mul_dev(native.g1_bytes(bn254.G1), s_h, n)
+    plain = native.g1_msm_dev(table, 0, k_h, 0, n)
+    native.table_precompute(table, 16)
+    s = synthetic.scalars(0x5EED0002, n)
+    k = synthetic.scalars(0x5EED0001, n)
+    want = bn254.g1_mul(bn254.G1, sum(a * b for a, b in zip(k, s)) % R)
+    assert plain == want
+    assert native.g1_msm_dev(table, 0, k_h, 0, n) == want
+    half = n // 2
+    want_half = bn254.g1_mul(bn254.G1, sum(a * b for a, b in zip(k[:half], s[half:])) % R)
+    assert native.g1_msm_dev(table, half, k_h, 0, half) == want_half
