@@ -99,6 +99,7 @@ int zkp_msm_set_window_bits(int c);
 int zkp_g1_fixed_base_mul(const uint8_t base_xy[64], const uint8_t* scalars, uint64_t n, uint64_t* out_table);
 int zkp_g2_fixed_base_mul(const uint8_t base_xy[128], const uint8_t* scalars, uint64_t n, uint64_t* out_table);
 int zkp_g1_fixed_base_mul_dev(const uint8_t base_xy[64], uint64_t scalars, uint64_t n, uint64_t* out_table);
+int zkp_g2_fixed_base_mul_dev(const uint8_t base_xy[128], uint64_t scalars, uint64_t n, uint64_t* out_table);
 int zkp_table_download(uint64_t table, uint64_t offset, uint64_t n, uint8_t* out_pts);
 int zkp_scalars_download(uint64_t scalars, uint64_t offset, uint64_t n, uint8_t* out);
 
@@ -141,6 +142,18 @@ int zkp_fr_vec_matrix(const uint8_t* vec, const uint8_t* mat, uint64_t rows, uin
  * rem_out: z_len - 1 elements. */
 int zkp_groth16_quotient(const uint8_t* a, const uint8_t* b, const uint8_t* c, uint64_t len, const uint8_t* z,
                          uint64_t z_len, uint8_t* h_out, uint8_t* rem_out);
+/* The same on device-resident coefficient vectors (the 2^20-constraint configuration cannot go through
+ * the reference's dense numWires x numGates lists: SURVEY F12).  Returns two new scalar handles
+ * (quotient: 2*len - z_len coefficients; remainder: z_len - 1).  The inverse power series of the
+ * reversed divisor is cached per z handle (Z(x) is fixed per circuit). */
+int zkp_groth16_quotient_dev(uint64_t a, uint64_t b, uint64_t c, uint64_t len, uint64_t z, uint64_t z_len,
+                             uint64_t* h_out, uint64_t* rem_out);
+/* Device-resident Fr vector utilities used to assemble MSM scalar vectors without leaving HBM. */
+int zkp_scalars_alloc(uint64_t n, uint64_t* handle);
+int zkp_scalars_copy(uint64_t dst, uint64_t dst_off, uint64_t src, uint64_t src_off, uint64_t n);
+int zkp_scalars_upload(uint64_t dst, uint64_t dst_off, const uint8_t* host, uint64_t n);
+int zkp_scalars_scale(uint64_t h, uint64_t off, uint64_t n, const uint8_t k[32]);
+int zkp_fr_poly_eval_dev(uint64_t h, uint64_t off, uint64_t n, const uint8_t x[32], uint8_t out[32]);
 /* General product and exact/long division over Fr in coefficient form
  * (Polynomial.__mul__ polynomial.py:144-159; poly_div polynomial.py:385-435). */
 int zkp_fr_poly_mul(const uint8_t* a, uint64_t a_len, const uint8_t* b, uint64_t b_len, uint8_t* out);

@@ -69,6 +69,13 @@ PROTOTYPES = {
     "zkp_fr_poly_eval": (c_int, [vp, u64, vp, vp]),
     "zkp_fr_vec_matrix": (c_int, [vp, vp, u64, u64, vp]),
     "zkp_groth16_quotient": (c_int, [vp, vp, vp, u64, vp, u64, vp, vp]),
+    "zkp_groth16_quotient_dev": (c_int, [u64, u64, u64, u64, u64, u64, u64p, u64p]),
+    "zkp_scalars_alloc": (c_int, [u64, u64p]),
+    "zkp_scalars_copy": (c_int, [u64, u64, u64, u64, u64]),
+    "zkp_scalars_upload": (c_int, [u64, u64, vp, u64]),
+    "zkp_scalars_scale": (c_int, [u64, u64, u64, vp]),
+    "zkp_fr_poly_eval_dev": (c_int, [u64, u64, u64, vp, vp]),
+    "zkp_g2_fixed_base_mul_dev": (c_int, [vp, u64, u64, u64p]),
     "zkp_fr_poly_mul": (c_int, [vp, u64, vp, u64, vp]),
     "zkp_fr_poly_divmod": (c_int, [vp, u64, vp, u64, vp, vp]),
     "zkp_msm_profile": (c_int, [c_int]),

@@ -365,7 +365,10 @@ static int series_inverse_dev(Context& c, const Fr* f, uint64_t lf, uint64_t m, 
 
 // a = b*q + r.  a (la), b (lb >= 1, b[lb-1] != 0), la >= lb.  q: la-lb+1 elements, r: lb-1 elements.
 // All device Montgomery.  vanishing: b is x^(lb-1) - 1 (fast path).
-static int poly_divmod_dev(Context& c, const Fr* a, uint64_t la, const Fr* b, uint64_t lb, Fr* q, Fr* r, bool vanishing) {
+// inv_cache: optional persistent buffer holding rev(b)^-1 mod x^m from an earlier call with the same
+// divisor (the Groth16 Z(x) is fixed per circuit); *inv_cached tells whether it is already filled.
+static int poly_divmod_dev(Context& c, const Fr* a, uint64_t la, const Fr* b, uint64_t lb, Fr* q, Fr* r, bool vanishing,
+                           Fr* inv_cache = nullptr, bool* inv_cached = nullptr) {
   int launches = 0;
   uint64_t m = la - lb + 1;
   if (vanishing && lb >= 2) {
@@ -377,14 +380,17 @@ static int poly_divmod_dev(Context& c, const Fr* a, uint64_t la, const Fr* b, ui
   Fr* ra = g_arena.alloc(m);
   uint64_t lrb = lb < m ? lb : m;
   Fr* rb = g_arena.alloc(lrb);
-  Fr* g = g_arena.alloc(m);
+  Fr* g = inv_cache ? inv_cache : g_arena.alloc(m);
   Fr* qr = g_arena.alloc(m);
   fr_reverse_kernel<<<GRID_1D(m)>>>(a, la, m, ra);
   CUDA_CHECK_LAUNCH();
   fr_reverse_kernel<<<GRID_1D(lrb)>>>(b, lb, lrb, rb);
   CUDA_CHECK_LAUNCH();
   launches += 2;
-  launches += series_inverse_dev(c, rb, lrb, m, g);
+  if (!(inv_cached && *inv_cached)) {
+    launches += series_inverse_dev(c, rb, lrb, m, g);
+    if (inv_cached) *inv_cached = true;
+  }
   launches += poly_mul_dev(c, ra, m, g, m, qr, m);
   fr_reverse_kernel<<<GRID_1D(m)>>>(qr, m, m, q);
   CUDA_CHECK_LAUNCH();
@@ -607,6 +613,154 @@ int zkp_fr_poly_divmod(const uint8_t* a, uint64_t a_len, const uint8_t* b, uint6
     download_canon(c, dr, b_len - 1, r_out, &launches);
     c.launches += launches;
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+// ------------------------------------------------------------------ device-resident Fr vectors (handles)
+struct DivisorCache {
+  uint64_t z_handle = 0, z_len = 0, m = 0;
+  DevBuf inv;
+  bool filled = false;
+};
+static DivisorCache g_div_cache;
+
+int zkp_scalars_alloc(uint64_t n, uint64_t* handle) {
+  return guarded([&](Context& c) {
+    if (!handle) throw InvalidArgument("zkp_scalars_alloc: null handle");
+    auto r = std::make_unique<Resource>();
+    r->kind = HandleKind::Scalars;
+    r->n = n;
+    r->buf.reserve(n ? n * 32 : 32);
+    CUDA_CHECK(cudaMemsetAsync(r->buf.p, 0, n ? n * 32 : 32, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    *handle = registry().put(std::move(r));
+  });
+}
+
+int zkp_scalars_copy(uint64_t dst, uint64_t dst_off, uint64_t src, uint64_t src_off, uint64_t n) {
+  return guarded([&](Context& c) {
+    Resource* d = need(dst, HandleKind::Scalars, "zkp_scalars_copy");
+    Resource* s = need(src, HandleKind::Scalars, "zkp_scalars_copy");
+    if (dst_off + n > d->n || src_off + n > s->n) throw InvalidArgument("zkp_scalars_copy: range out of bounds");
+    if (n) CUDA_CHECK(cudaMemcpyAsync(d->buf.as<Fr>() + dst_off, s->buf.as<Fr>() + src_off, n * 32,
+                                     cudaMemcpyDeviceToDevice, c.stream));
+  });
+}
+
+int zkp_scalars_upload(uint64_t dst, uint64_t dst_off, const uint8_t* host, uint64_t n) {
+  return guarded([&](Context& c) {
+    Resource* d = need(dst, HandleKind::Scalars, "zkp_scalars_upload");
+    if (dst_off + n > d->n || (n && !host)) throw InvalidArgument("zkp_scalars_upload: bad range or null source");
+    if (n) CUDA_CHECK(cudaMemcpyAsync(d->buf.as<Fr>() + dst_off, host, n * 32, cudaMemcpyHostToDevice, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int zkp_scalars_scale(uint64_t h, uint64_t off, uint64_t n, const uint8_t k[32]) {
+  return guarded([&](Context& c) {
+    Resource* d = need(h, HandleKind::Scalars, "zkp_scalars_scale");
+    if (off + n > d->n || !k) throw InvalidArgument("zkp_scalars_scale: bad range or null factor");
+    if (!n) return;
+    ArenaScope scope;
+    Fr* dk = g_arena.alloc(1);
+    CUDA_CHECK(cudaMemcpyAsync(dk, k, 32, cudaMemcpyHostToDevice, c.stream));
+    fr_vec_op_kernel<<<GRID_1D(n)>>>(3, d->buf.as<Fr>() + off, dk, n, d->buf.as<Fr>() + off);
+    CUDA_CHECK_LAUNCH();
+    c.launches++;
+  });
+}
+
+int zkp_fr_poly_eval_dev(uint64_t h, uint64_t off, uint64_t n, const uint8_t x[32], uint8_t out[32]) {
+  return guarded([&](Context& c) {
+    Resource* d = need(h, HandleKind::Scalars, "zkp_fr_poly_eval_dev");
+    if (off + n > d->n || !x || !out) throw InvalidArgument("zkp_fr_poly_eval_dev: bad argument");
+    if (!n) {
+      memset(out, 0, 32);
+      return;
+    }
+    ArenaScope scope;
+    uint64_t np = (n + HORNER_CHUNK - 1) / HORNER_CHUNK;
+    Fr* partial = g_arena.alloc(np);
+    Fr* tab = g_arena.alloc(41);
+    Fr* dx = tab + 40;
+    CUDA_CHECK(cudaMemcpyAsync(dx, x, 32, cudaMemcpyHostToDevice, c.stream));
+    fr_to_mont_kernel<<<1, 32, 0, c.stream>>>(dx, 1, dx);
+    CUDA_CHECK_LAUNCH();
+    Fr xm;
+    CUDA_CHECK(cudaMemcpyAsync(&xm, dx, 32, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    horner_pow_table_kernel<<<1, 32, 0, c.stream>>>(xm, tab);
+    CUDA_CHECK_LAUNCH();
+    horner_partial_kernel<<<GRID_1D(np)>>>(d->buf.as<Fr>() + off, n, xm, partial);
+    CUDA_CHECK_LAUNCH();
+    horner_combine_kernel<<<1, 256, 0, c.stream>>>(partial, np, tab, dx);
+    CUDA_CHECK_LAUNCH();
+    c.launches += 4;
+    CUDA_CHECK(cudaMemcpyAsync(out, dx, 32, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+// hxr on device-resident coefficient vectors (the 2^20 configuration needs
+// coefficient-level entry points).  a, b, c: `len` canonical coefficients each; z: z_len coefficients of
+// the (fixed) divisor.  Creates two new scalar handles: the quotient (2*len - z_len coefficients) and
+// the remainder (z_len - 1).  The power-series inverse of the reversed divisor is cached per z handle.
+int zkp_groth16_quotient_dev(uint64_t a, uint64_t b, uint64_t cc, uint64_t len, uint64_t z, uint64_t z_len,
+                             uint64_t* h_out, uint64_t* rem_out) {
+  return guarded([&](Context& c) {
+    Resource* ra = need(a, HandleKind::Scalars, "zkp_groth16_quotient_dev");
+    Resource* rb = need(b, HandleKind::Scalars, "zkp_groth16_quotient_dev");
+    Resource* rc = need(cc, HandleKind::Scalars, "zkp_groth16_quotient_dev");
+    Resource* rz = need(z, HandleKind::Scalars, "zkp_groth16_quotient_dev");
+    if (!h_out || !rem_out || !len || z_len < 2) throw InvalidArgument("zkp_groth16_quotient_dev: bad argument");
+    if (len > ra->n || len > rb->n || len > rc->n || z_len > rz->n) throw InvalidArgument("zkp_groth16_quotient_dev: length exceeds a vector");
+    uint64_t lp = 2 * len - 1;
+    if (lp < z_len) throw InvalidArgument("zkp_groth16_quotient_dev: divisor longer than the product");
+    ArenaScope scope;
+    int launches = 0;
+    auto to_mont_copy = [&](Resource* r, uint64_t n) {
+      Fr* d = g_arena.alloc(n);
+      fr_to_mont_kernel<<<GRID_1D(n)>>>(r->buf.as<Fr>(), n, d);
+      CUDA_CHECK_LAUNCH();
+      launches++;
+      return d;
+    };
+    Fr* da = to_mont_copy(ra, len);
+    Fr* db = to_mont_copy(rb, len);
+    Fr* dc = to_mont_copy(rc, len);
+    Fr* dz = to_mont_copy(rz, z_len);
+    Fr* dp = g_arena.alloc(lp);
+    launches += poly_mul_dev(c, da, len, db, len, dp, lp);
+    fr_sub_inplace_kernel<<<GRID_1D(len)>>>(dp, dc, len);
+    CUDA_CHECK_LAUNCH();
+    launches++;
+    uint64_t m = lp - z_len + 1;
+    if (g_div_cache.z_handle != z || g_div_cache.z_len != z_len || g_div_cache.m != m) {
+      g_div_cache.z_handle = z;
+      g_div_cache.z_len = z_len;
+      g_div_cache.m = m;
+      g_div_cache.filled = false;
+      g_div_cache.inv.reserve(m * sizeof(Fr));
+    }
+    auto hq = std::make_unique<Resource>();
+    hq->kind = HandleKind::Scalars;
+    hq->n = m;
+    hq->buf.reserve(m * 32);
+    auto hr = std::make_unique<Resource>();
+    hr->kind = HandleKind::Scalars;
+    hr->n = z_len - 1;
+    hr->buf.reserve(z_len * 32);
+    launches += poly_divmod_dev(c, dp, lp, dz, z_len, hq->buf.as<Fr>(), hr->buf.as<Fr>(), false,
+                                g_div_cache.inv.as<Fr>(), &g_div_cache.filled);
+    fr_from_mont_kernel<<<GRID_1D(m)>>>(hq->buf.as<Fr>(), m, hq->buf.as<Fr>());
+    CUDA_CHECK_LAUNCH();
+    fr_from_mont_kernel<<<GRID_1D(z_len - 1)>>>(hr->buf.as<Fr>(), z_len - 1, hr->buf.as<Fr>());
+    CUDA_CHECK_LAUNCH();
+    launches += 2;
+    c.launches += launches;
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    *h_out = registry().put(std::move(hq));
+    *rem_out = registry().put(std::move(hr));
   });
 }
 

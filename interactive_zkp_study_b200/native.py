@@ -220,6 +220,43 @@ def g2_fixed_base_mul(base_bytes, sc_bytes, n):
     return DeviceHandle(h.value, n, "g2")
 
 
+def g2_fixed_base_mul_dev(base_bytes, scalars, n):
+    h = ctypes.c_uint64()
+    check(_lib.lib().zkp_g2_fixed_base_mul_dev(buf(base_bytes), scalars.handle, n, ctypes.byref(h)))
+    return DeviceHandle(h.value, n, "g2")
+
+
+def scalars_alloc(n):
+    h = ctypes.c_uint64()
+    check(_lib.lib().zkp_scalars_alloc(n, ctypes.byref(h)))
+    return DeviceHandle(h.value, n, "fr")
+
+
+def scalars_copy(dst, dst_off, src, src_off, n):
+    check(_lib.lib().zkp_scalars_copy(dst.handle, dst_off, src.handle, src_off, n))
+
+
+def scalars_upload(dst, dst_off, data, n):
+    check(_lib.lib().zkp_scalars_upload(dst.handle, dst_off, buf(data), n))
+
+
+def scalars_scale(h, off, n, k):
+    check(_lib.lib().zkp_scalars_scale(h.handle, off, n, buf(fe_bytes(k))))
+
+
+def fr_poly_eval_dev(h, off, n, x):
+    out = bytearray(32)
+    check(_lib.lib().zkp_fr_poly_eval_dev(h.handle, off, n, buf(fe_bytes(x)), buf(out)))
+    return int.from_bytes(out, "little")
+
+
+def groth16_quotient_dev(a, b, c, length, z, z_len):
+    hq, hr = ctypes.c_uint64(), ctypes.c_uint64()
+    check(_lib.lib().zkp_groth16_quotient_dev(a.handle, b.handle, c.handle, length, z.handle, z_len,
+                                              ctypes.byref(hq), ctypes.byref(hr)))
+    return DeviceHandle(hq.value, 2 * length - z_len, "fr"), DeviceHandle(hr.value, z_len - 1, "fr")
+
+
 def g1_fixed_base_mul_dev(base_bytes, scalars, n):
     h = ctypes.c_uint64()
     check(_lib.lib().zkp_g1_fixed_base_mul_dev(buf(base_bytes), scalars.handle, n, ctypes.byref(h)))

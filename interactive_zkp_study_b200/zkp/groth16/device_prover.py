@@ -1,0 +1,86 @@
+"""Groth16 proving at scale: coefficient-vector entry points over device-resident keys.
+
+The reference's `proof_a/b/c(sigma..., Ax, Rx, ...)` signatures take the dense numWires x numGates QAP
+matrices, which cannot exist at 2^20 constraints (2^40 entries).  What the prover needs
+from them is only the three coefficient vectors uA = R.Ax, uB = R.Bx, uC = R.Cx (numGates entries
+each) -- this module is the same algebra as zkp/groth16/proving.py + poly_utils.hxr
+(/root/reference/zkp/groth16/proving.py:23-75, poly_utils.py:116-125) on those vectors, with the CRS
+resident on the GPU in three concatenated, window-precomputed tables so that each proof element is
+ONE multi-scalar multiplication:
+
+    TA  (G1) = [x^j]_1 (j < k) | alpha_1 | delta_1                  scalars  uA | 1 | r            -> A
+    TB2 (G2) = [x^j]_2 (j < k) | beta_2  | delta_2                  scalars  uB | 1 | s            -> B
+    TC  (G1) = [x^j]_1 (j < k) | beta_1 | sigma1_4[private] | sigma1_5 (k-1)
+                                                                     scalars  r*uB | r | Rx_priv | H -> X
+    C = s*A + X        (the s*r*delta terms of proving.py:64 cancel)
+"""
+from ... import native
+from ...compat import G1, G2, curve_order, g1_from_ints, g2_from_ints
+
+R = curve_order
+
+
+class DeviceKey:
+    def __init__(self, k, m_priv, TA, TB2, TC):
+        self.k, self.m_priv, self.TA, self.TB2, self.TC = k, m_priv, TA, TB2, TC
+
+
+def _powers(x, count):
+    return native.fr_prefix_product(native.fr_vec_bytes([x % R] * count), count)
+
+
+def setup_from_toxic(k, alpha, beta, delta, x_val, zx_val, priv_vals, precompute=True):
+    """CRS generation on the device (batched fixed-base multiplications; reference setup.py:15-69).
+    priv_vals[i] = (beta*A_i(x) + alpha*B_i(x) + C_i(x)) / delta for the private wires, in order."""
+    m_priv = len(priv_vals)
+    pw = _powers(x_val, k)
+    inv_delta = pow(delta % R, -1, R)
+    s15 = native.fr_vec_op(3, pw[:32 * (k - 1)], native.fe_bytes(zx_val % R * inv_delta % R), k - 1) if k > 1 else b""
+    enc = native.fr_vec_bytes
+    scA = pw + enc([alpha % R, delta % R])
+    scC = pw + enc([beta % R]) + enc([v % R for v in priv_vals]) + s15
+    TA = native.g1_fixed_base_mul(native.g1_bytes(G1), scA, k + 2)
+    TB2 = native.g2_fixed_base_mul(native.g2_bytes(G2), pw + enc([beta % R, delta % R]), k + 2)
+    TC = native.g1_fixed_base_mul(native.g1_bytes(G1), scC, k + 1 + m_priv + (k - 1))
+    if precompute:
+        for t in (TA, TB2, TC):
+            if t.n >= (1 << 12):
+                native.table_precompute(t, max(4, min(20, t.n.bit_length() - 4)))
+    return DeviceKey(k, m_priv, TA, TB2, TC)
+
+
+def prove(key, uA, uB, uC, Z, rx_priv, r, s, keep_quotient=False):
+    """uA, uB, uC: device scalar handles with k coefficients; Z: handle with k+1 coefficients (monic
+    divisor); rx_priv: handle with the private wires' witness values.  Returns (A, B, C) as the
+    reference's point types (and the quotient / remainder handles when keep_quotient)."""
+    k, mp = key.k, key.m_priv
+    r, s = int(r) % R, int(s) % R
+    hq, hr = native.groth16_quotient_dev(uA, uB, uC, k, Z, k + 1)     # H: k-1 coefficients, rem: k
+    one = native.fr_vec_bytes([1])
+    scA = native.scalars_alloc(k + 2)
+    native.scalars_copy(scA, 0, uA, 0, k)
+    native.scalars_upload(scA, k, one + native.fe_bytes(r), 2)
+    A = native.g1_msm_dev(key.TA, 0, scA, 0, k + 2)
+    scB = native.scalars_alloc(k + 2)
+    native.scalars_copy(scB, 0, uB, 0, k)
+    native.scalars_upload(scB, k, one + native.fe_bytes(s), 2)
+    B = native.g2_msm_dev(key.TB2, 0, scB, 0, k + 2)
+    nC = k + 1 + mp + (k - 1)
+    scC = native.scalars_alloc(nC)
+    native.scalars_copy(scC, 0, uB, 0, k)
+    native.scalars_scale(scC, 0, k, r)
+    native.scalars_upload(scC, k, native.fe_bytes(r), 1)
+    if mp:
+        native.scalars_copy(scC, k + 1, rx_priv, 0, mp)
+    if k > 1:
+        native.scalars_copy(scC, k + 1 + mp, hq, 0, k - 1)
+    X = native.g1_msm_dev(key.TC, 0, scC, 0, nC)
+    C = native.g1_msm(native.g1_bytes(A) + native.g1_bytes(X), native.fe_bytes(s) + one, 2)
+    for h in (scA, scB, scC):
+        h.free()
+    out = (g1_from_ints(A), g2_from_ints(B), g1_from_ints(C))
+    if keep_quotient:
+        return out + (hq, hr)
+    hq.free()
+    hr.free()
+    return out

@@ -105,3 +105,27 @@ def test_proofs_match_oracle_for_other_randomness(toy):
     Hx = ints(g["Hx"])
     C = proof_c(toy["sigma1_1"], toy["sigma1_2"], toy["sigma1_4"], toy["sigma1_5"], toy["Bx"], toy["Rx"], Hx, s, r, A)
     assert _g1i(C) == ref_path.proof_c(s11, s12, s14, s15, Bi, Rx, Hx, s, r, wantA)
+
+
+def test_setup_sigmas_bit_exact_with_reference(toy):
+    """CRS generation (reference zkp/groth16/setup.py:15-69; tests/groth16/test_setup.py) with the
+    conftest toxic waste: every sigma list equals the reference's, placeholders included."""
+    from interactive_zkp_study_b200.zkp.groth16 import setup as st
+    from interactive_zkp_study_b200.zkp.groth16 import poly_utils as pu
+    from interactive_zkp_study_b200.compat import FQ, FR
+    g = toy["g"]
+    t = {k: FR(int(v)) for k, v in g["toxic"].items()}
+    k, m, pub = g["numGates"], g["numWires"], g["pub_r_indexs"]
+    Axv, Bxv, Cxv = pu.ax_val(toy["Ax"], t["x_val"]), pu.bx_val(toy["Bx"], t["x_val"]), pu.cx_val(toy["Cx"], t["x_val"])
+    Zxv = pu.zx_val(toy["Zx"], t["x_val"])
+    assert [_g1i(p) for p in st.sigma11(t["alpha"], t["beta"], t["delta"])] == [g1(p) for p in g["sigma1_1"]]
+    assert [_g1i(p) for p in st.sigma12(k, t["x_val"])] == [g1(p) for p in g["sigma1_2"]]
+    s13, VAL = st.sigma13(m, t["alpha"], t["beta"], t["gamma"], Axv, Bxv, Cxv, pub_r_indexs=pub)
+    assert [_g1i(p) for p in s13] == [g1(p) for p in g["sigma1_3"]]
+    assert [int(v) for v in VAL] == ints(g["VAL"])
+    s14 = st.sigma14(m, t["alpha"], t["beta"], t["delta"], Axv, Bxv, Cxv, pub_r_indexs=pub)
+    assert [_g1i(p) for p in s14] == [g1(p) for p in g["sigma1_4"]]
+    assert _g1i(s14[0]) == (0, 0) and isinstance(s14[0][0], FQ)        # placeholder, setup.py:50
+    assert [_g1i(p) for p in st.sigma15(k, t["delta"], t["x_val"], Zxv)] == [g1(p) for p in g["sigma1_5"]]
+    assert [_g2i(p) for p in st.sigma21(t["beta"], t["delta"], t["gamma"])] == [g2(p) for p in g["sigma2_1"]]
+    assert [_g2i(p) for p in st.sigma22(k, t["x_val"])] == [g2(p) for p in g["sigma2_2"]]
