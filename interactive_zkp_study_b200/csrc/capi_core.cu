@@ -17,6 +17,42 @@ static StageProfile g_last_profile;
 int g_msm_profile_enabled = 0;
 StageProfile& last_msm_profile() { return g_last_profile; }
 
+// ------------------------------------------------------------------ device buffer pool
+static std::vector<DevBuf> g_pool;
+static size_t g_pool_bytes = 0;
+static constexpr size_t POOL_MAX_BYTES = size_t(8) << 30;
+
+void DevBuf::reserve_pooled(size_t bytes) {
+  if (bytes <= cap) return;
+  if (p) recycle();
+  int best = -1;
+  for (int i = 0; i < (int)g_pool.size(); i++)
+    if (g_pool[i].cap >= bytes && g_pool[i].cap <= 2 * bytes + 4096 && (best < 0 || g_pool[i].cap < g_pool[best].cap)) best = i;
+  if (best >= 0) {
+    p = g_pool[best].p;
+    cap = g_pool[best].cap;
+    g_pool_bytes -= cap;
+    g_pool.erase(g_pool.begin() + best);
+    return;
+  }
+  reserve(bytes);
+}
+
+void DevBuf::recycle() {
+  if (!p) return;
+  if (g_pool_bytes + cap > POOL_MAX_BYTES || cap > (size_t(2) << 30)) {
+    release();
+    return;
+  }
+  DevBuf b;
+  b.p = p;
+  b.cap = cap;
+  g_pool.push_back(b);
+  g_pool_bytes += cap;
+  p = nullptr;
+  cap = 0;
+}
+
 Context& ctx() {
   if (!g_ready) throw std::runtime_error("zkp_init has not been called successfully");
   return g_ctx;
@@ -255,7 +291,7 @@ int zkp_free(uint64_t handle) {
     auto it = registry().items.find(handle);
     if (it == registry().items.end()) throw BadHandle("zkp_free: unknown handle");
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
-    it->second->buf.release();
+    it->second->buf.recycle();
     registry().items.erase(it);
   });
 }
@@ -266,7 +302,7 @@ int zkp_scalars_load(const uint8_t* scalars, uint64_t n, uint64_t* handle) {
     auto r = std::make_unique<Resource>();
     r->kind = HandleKind::Scalars;
     r->n = n;
-    r->buf.reserve(n ? n * 32 : 32);
+    r->buf.reserve_pooled(n ? n * 32 : 32);
     if (n) CUDA_CHECK(cudaMemcpyAsync(r->buf.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
     *handle = registry().put(std::move(r));
@@ -279,7 +315,7 @@ int zkp_scalars_generate(uint64_t seed, uint64_t n, uint64_t* handle) {
     auto r = std::make_unique<Resource>();
     r->kind = HandleKind::Scalars;
     r->n = n;
-    r->buf.reserve(n ? n * 32 : 32);
+    r->buf.reserve_pooled(n ? n * 32 : 32);
     if (n) {
       scalars_generate_kernel<<<ceil_div(n, 256), 256, 0, c.stream>>>(seed, n, r->buf.as<uint32_t>());
       CUDA_CHECK_LAUNCH();

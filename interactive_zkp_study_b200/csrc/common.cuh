@@ -46,6 +46,11 @@ struct DevBuf {
     p = nullptr;
     cap = 0;
   }
+  // Handle-owned buffers come from / go back to a small size-matched pool: cudaMalloc / cudaFree of
+  // tens of MiB cost 0.1-1 ms each (cudaFree also synchronises the device), which would dominate a
+  // proof that assembles a handful of scalar vectors.
+  void reserve_pooled(size_t bytes);
+  void recycle();
 };
 
 struct Context {

@@ -7,6 +7,10 @@
 namespace zkp {
 
 struct __align__(16) Fp2 {
+  // Components use the out-of-line Fp product (arguments and result in registers): an inlined Fp2
+  // product is three calls plus a few adds, so the G2 kernels stay small (fast to compile, no stack
+  // traffic for operands) while the multiplier body is shared.
+  using Fp = FpC;
   Fp c0, c1;
 
   static ZKP_DEVINL Fp2 zero() { return {Fp::zero(), Fp::zero()}; }
@@ -18,17 +22,15 @@ struct __align__(16) Fp2 {
   friend ZKP_DEVINL Fp2 operator-(const Fp2& a, const Fp2& b) { return {a.c0 - b.c0, a.c1 - b.c1}; }
   ZKP_DEVINL Fp2 neg() const { return {c0.neg(), c1.neg()}; }
   ZKP_DEVINL Fp2 dbl() const { return {c0.dbl(), c1.dbl()}; }
-  // Karatsuba: 3 Fp multiplications.  Deliberately not inlined: an Fp2 product is ~450 SASS
-  // instructions, the call overhead is <5% of it, and inlining every product of the XYZZ formulas
-  // pushes the G2 kernels past 255 registers and minutes of ptxas time.
-  friend __device__ __noinline__ Fp2 operator*(const Fp2& a, const Fp2& b) {
+  // Karatsuba: 3 Fp multiplications
+  friend ZKP_DEVINL Fp2 operator*(const Fp2& a, const Fp2& b) {
     Fp t0 = a.c0 * b.c0;
     Fp t1 = a.c1 * b.c1;
     Fp t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
     return {t0 - t1, t2 - t0 - t1};
   }
   // (c0 + c1 u)^2 = (c0 + c1)(c0 - c1) + 2 c0 c1 u : 2 Fp multiplications
-  __device__ __noinline__ Fp2 sqr() const {
+  ZKP_DEVINL Fp2 sqr() const {
     Fp s = (c0 + c1) * (c0 - c1);
     Fp m = c0 * c1;
     return {s, m.dbl()};

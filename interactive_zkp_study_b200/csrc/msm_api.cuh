@@ -130,7 +130,7 @@ struct GroupApi {
       auto r = std::make_unique<Resource>();
       r->kind = KIND;
       r->n = n;
-      r->buf.reserve(n ? n * PT : PT);
+      r->buf.reserve_pooled(n ? n * PT : PT);
       if (n) upload_points(c, pts, n, r->buf.p);
       CUDA_CHECK(cudaStreamSynchronize(c.stream));
       *handle = registry().put(std::move(r));
@@ -214,7 +214,7 @@ struct GroupApi {
     auto r = std::make_unique<Resource>();
     r->kind = KIND;
     r->n = n;
-    r->buf.reserve(n ? n * PT : PT);
+    r->buf.reserve_pooled(n ? n * PT : PT);
     if (n) {
       fixed_base_mul_kernel<F><<<ceil_div(n, 128), 128, 0, c.stream>>>(base, dscalars, n, r->buf.as<Affine<F>>());
       CUDA_CHECK_LAUNCH();

@@ -630,7 +630,7 @@ int zkp_scalars_alloc(uint64_t n, uint64_t* handle) {
     auto r = std::make_unique<Resource>();
     r->kind = HandleKind::Scalars;
     r->n = n;
-    r->buf.reserve(n ? n * 32 : 32);
+    r->buf.reserve_pooled(n ? n * 32 : 32);
     CUDA_CHECK(cudaMemsetAsync(r->buf.p, 0, n ? n * 32 : 32, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
     *handle = registry().put(std::move(r));
@@ -745,11 +745,11 @@ int zkp_groth16_quotient_dev(uint64_t a, uint64_t b, uint64_t cc, uint64_t len, 
     auto hq = std::make_unique<Resource>();
     hq->kind = HandleKind::Scalars;
     hq->n = m;
-    hq->buf.reserve(m * 32);
+    hq->buf.reserve_pooled(m * 32);
     auto hr = std::make_unique<Resource>();
     hr->kind = HandleKind::Scalars;
     hr->n = z_len - 1;
-    hr->buf.reserve(z_len * 32);
+    hr->buf.reserve_pooled(z_len * 32);
     launches += poly_divmod_dev(c, dp, lp, dz, z_len, hq->buf.as<Fr>(), hr->buf.as<Fr>(), false,
                                 g_div_cache.inv.as<Fr>(), &g_div_cache.filled);
     fr_from_mont_kernel<<<GRID_1D(m)>>>(hq->buf.as<Fr>(), m, hq->buf.as<Fr>());
