@@ -305,11 +305,11 @@ template <class F>
 __global__ void __launch_bounds__(128) msm_bucket_fold_kernel(const XYZZ<F>* __restrict__ partials,
                                                                const uint32_t* __restrict__ task_base, uint32_t nbuckets,
                                                                XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ heavy_count,
-                                                               uint32_t* __restrict__ heavy_list) {
+                                                               uint32_t* __restrict__ heavy_list, uint32_t serial_limit) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbuckets) return;
   uint32_t t0 = task_base[b], t1 = task_base[b + 1];
-  if (t1 - t0 > MSM_FOLD_SERIAL) {
+  if (t1 - t0 > serial_limit) {
     heavy_list[atomicAdd(heavy_count, 1u)] = b;
     return;
   }
@@ -625,7 +625,10 @@ struct MsmEngine {
     CUDA_CHECK(cudaMemsetAsync(heavy.p, 0, 4, st));
     msm_bucket_fold_kernel<FC><<<ceil_div(pl.nbuckets, 128), 128, 0, st>>>(
         partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(), pl.nbuckets, buckets.as<XYZZ<FC>>(), heavy.as<uint32_t>(),
-        heavy.as<uint32_t>() + 1);
+        heavy.as<uint32_t>() + 1,
+        // "heavy" is relative to the average bucket: every bucket of a dense MSM (many entries per
+        // bucket) folds serially in parallel with the others; only outliers get a whole block
+        MSM_FOLD_SERIAL + 3 * (uint32_t)(total / pl.nbuckets / MSM_TASK_LEN));
     CUDA_CHECK_LAUNCH();
     msm_bucket_fold_heavy_kernel<FC><<<296, 128, 0, st>>>(partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(),
                                                           heavy.as<uint32_t>(), heavy.as<uint32_t>() + 1,

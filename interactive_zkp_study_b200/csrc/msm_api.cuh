@@ -46,6 +46,52 @@ __global__ void __launch_bounds__(128) fixed_base_mul_kernel(Affine<F> base_cano
   out[i] = acc.to_affine();  // Montgomery affine, (0,0) for infinity
 }
 
+// Windowed fixed-base multiplication for large batches: tab[j*256 + d] = d * 2^(8j) * base (affine
+// Montgomery, j < 32, d < 256; built once per call with the kernel above on 8192 small scalars), then
+// out[i] = sum_j tab[j][byte_j(s_i)]: at most 32 mixed additions per scalar instead of 254 doublings
+// + ~127 additions (11x less work), one inversion per point.
+static __global__ void fixed_base_table_scalars_kernel(uint32_t* __restrict__ out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // t = j*256 + d
+  if (t >= 8192) return;
+  uint32_t j = t >> 8, d = t & 255;
+  uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  v[j >> 2] = d << ((j & 3) * 8);
+#pragma unroll
+  for (int k = 0; k < 8; k++) out[8 * t + k] = v[k];
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) fixed_base_windowed_kernel(const Affine<F>* __restrict__ tab,
+                                                                   const uint32_t* __restrict__ scalars, uint64_t n,
+                                                                   Affine<F>* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[8];
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * i);
+  uint4 lo = sp[0], hi = sp[1];
+  s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
+  s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+  for (int it = 0; it < 6; it++) {
+    uint32_t t[8], borrow = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint64_t d = (uint64_t)s[k] - FrParams::MOD_(k) - borrow;
+      t[k] = (uint32_t)d;
+      borrow = (uint32_t)(d >> 63);
+    }
+    if (borrow) break;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = t[k];
+  }
+  XYZZ<F> acc = XYZZ<F>::inf();
+#pragma unroll 1
+  for (int j = 0; j < 32; j++) {
+    uint32_t d = (s[j >> 2] >> ((j & 3) * 8)) & 255u;
+    if (d) acc.madd(tab[j * 256 + d]);
+  }
+  out[i] = acc.to_affine();
+}
+
 template <class F>
 __global__ void combine_partials_kernel(const XYZZ<F>* __restrict__ parts, uint32_t count, Affine<F>* __restrict__ out,
                                         int* __restrict__ inf_flag) {
@@ -215,7 +261,22 @@ struct GroupApi {
     r->kind = KIND;
     r->n = n;
     r->buf.reserve_pooled(n ? n * PT : PT);
-    if (n) {
+    if (n >= 4096) {
+      DevBuf tsc, tab;
+      tsc.reserve_pooled(8192 * 32);
+      tab.reserve_pooled(8192 * PT);
+      fixed_base_table_scalars_kernel<<<32, 256, 0, c.stream>>>(tsc.as<uint32_t>());
+      CUDA_CHECK_LAUNCH();
+      fixed_base_mul_kernel<F><<<64, 128, 0, c.stream>>>(base, tsc.as<uint32_t>(), 8192, tab.as<Affine<F>>());
+      CUDA_CHECK_LAUNCH();
+      fixed_base_windowed_kernel<F><<<ceil_div(n, 128), 128, 0, c.stream>>>(tab.as<Affine<F>>(), dscalars, n,
+                                                                           r->buf.as<Affine<F>>());
+      CUDA_CHECK_LAUNCH();
+      c.launches += 3;
+      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      tsc.recycle();
+      tab.recycle();
+    } else if (n) {
       fixed_base_mul_kernel<F><<<ceil_div(n, 128), 128, 0, c.stream>>>(base, dscalars, n, r->buf.as<Affine<F>>());
       CUDA_CHECK_LAUNCH();
       c.launches++;
