@@ -110,3 +110,27 @@ def test_synthetic_stream_is_reduced_and_deterministic():
     assert all(0 <= x < R for x in v)
     assert v[:3] == [synthetic.scalar(0x5EED0001, i) for i in range(3)]
     assert v != synthetic.scalars(0x5EED0002, 2000)
+
+
+def _golden_proof(f):
+    proof = {k: (g1(v) if k.endswith("_comm") else int(v)) for k, v in f["proof"].items()}
+    pre = {k: g1(v) for k, v in f["pre_comm"].items()}
+    return proof, pre
+
+
+def test_oracle_plonk_verifier_accepts_golden_and_rejects_tampering():
+    """The restated verifier (oracle/plonk_verifier.py) on the reference-minted proofs: accepts each,
+    rejects a tampered evaluation and a tampered commitment (reference tests/plonk/test_e2e.py:198-250)."""
+    from oracle import plonk_verifier
+    for name in ("plonk_n1.json", "plonk_x3.json", "plonk_chain16.json"):
+        f = load(name)
+        proof, pre = _golden_proof(f)
+        g2p = [g2(p) for p in f["g2_powers"]]
+        assert plonk_verifier.verify(proof, pre, f["n"], int(f["omega"]), g2p) is True
+        if name == "plonk_x3.json":
+            bad = dict(proof)
+            bad["a_eval"] = (bad["a_eval"] + 1) % R
+            assert plonk_verifier.verify(bad, pre, f["n"], int(f["omega"]), g2p) is False
+            bad = dict(proof)
+            bad["z_comm"] = bn254.g1_add(bad["z_comm"], bn254.G1)
+            assert plonk_verifier.verify(bad, pre, f["n"], int(f["omega"]), g2p) is False
