@@ -154,6 +154,32 @@ int zkp_scalars_copy(uint64_t dst, uint64_t dst_off, uint64_t src, uint64_t src_
 int zkp_scalars_upload(uint64_t dst, uint64_t dst_off, const uint8_t* host, uint64_t n);
 int zkp_scalars_scale(uint64_t h, uint64_t off, uint64_t n, const uint8_t k[32]);
 int zkp_fr_poly_eval_dev(uint64_t h, uint64_t off, uint64_t n, const uint8_t x[32], uint8_t out[32]);
+/* ---- device-resident vector ops and the PLONK rounds at scale -------------------------------------
+ * All on scalar handles, canonical values unless stated.  They are the device form of the Polynomial
+ * arithmetic of zkp/plonk/polynomial.py:108-159 used by the prover rounds (round1..5.py). */
+int zkp_fr_vec_op_dev(int op, uint64_t dst, uint64_t dst_off, uint64_t a, uint64_t a_off, uint64_t b, uint64_t b_off,
+                      uint64_t n);                              /* 0 add, 1 sub, 2 mul */
+int zkp_fr_axpy_dev(uint64_t dst, uint64_t dst_off, const uint8_t k[32], uint64_t src, uint64_t src_off, uint64_t n);
+int zkp_scalars_add_const(uint64_t h, uint64_t off, uint64_t n, const uint8_t k[32]);
+int zkp_scalars_fill_powers(uint64_t h, uint64_t off, uint64_t n, const uint8_t first[32], const uint8_t base[32]);
+int zkp_scalars_convert(uint64_t h, uint64_t off, uint64_t n, int to_montgomery);
+int zkp_scalars_is_zero(uint64_t h, uint64_t off, uint64_t n, int* out_all_zero);
+int zkp_fr_batch_inverse_dev(uint64_t h, uint64_t off, uint64_t n, int montgomery);
+int zkp_fr_scan_dev(int op, uint64_t dst, uint64_t dst_off, uint64_t src, uint64_t src_off, uint64_t n); /* 0 product, 1 sum */
+/* (p(x) - p(zeta)) / (x - zeta): poly_div by a linear factor (round5.py:165-171, kzg.py:95-104) */
+int zkp_fr_div_linear_dev(uint64_t src, uint64_t src_off, uint64_t n, const uint8_t zeta[32], uint64_t dst,
+                          uint64_t dst_off);
+/* numerators / denominators of the grand-product accumulator (permutation.py:120-135) */
+int zkp_plonk_perm_terms_dev(uint64_t a, uint64_t b, uint64_t c, uint64_t s1, uint64_t s2, uint64_t s3, uint64_t n,
+                             const uint8_t omega[32], const uint8_t beta[32], const uint8_t gamma[32], uint64_t num,
+                             uint64_t den);
+/* round 3 on the coset g*<w_N>, N = ext*n >= 3n+6 (round3.py:114-147 evaluated pointwise):
+ * ext = 4 for n >= 8, 8 for n = 2, 4 and 16 for n = 1. */
+int zkp_plonk_coset_setup_dev(uint64_t n, uint32_t ext, const uint8_t g[32], const uint8_t w8[32],
+                              const uint8_t g_pow_n[32], const uint8_t w8_pow_n[32], uint64_t x_out, uint64_t l1f_out,
+                              uint64_t zh8_out);
+int zkp_plonk_quotient_dev(const uint64_t evals[12], uint64_t n, uint32_t ext, uint64_t x, uint64_t l1f, uint64_t zh8,
+                           const uint8_t beta[32], const uint8_t gamma[32], const uint8_t alpha[32], uint64_t t_out);
 /* General product and exact/long division over Fr in coefficient form
  * (Polynomial.__mul__ polynomial.py:144-159; poly_div polynomial.py:385-435). */
 int zkp_fr_poly_mul(const uint8_t* a, uint64_t a_len, const uint8_t* b, uint64_t b_len, uint8_t* out);

@@ -76,6 +76,18 @@ PROTOTYPES = {
     "zkp_scalars_scale": (c_int, [u64, u64, u64, vp]),
     "zkp_fr_poly_eval_dev": (c_int, [u64, u64, u64, vp, vp]),
     "zkp_g2_fixed_base_mul_dev": (c_int, [vp, u64, u64, u64p]),
+    "zkp_fr_vec_op_dev": (c_int, [c_int, u64, u64, u64, u64, u64, u64, u64]),
+    "zkp_fr_axpy_dev": (c_int, [u64, u64, vp, u64, u64, u64]),
+    "zkp_scalars_add_const": (c_int, [u64, u64, u64, vp]),
+    "zkp_scalars_fill_powers": (c_int, [u64, u64, u64, vp, vp]),
+    "zkp_scalars_convert": (c_int, [u64, u64, u64, c_int]),
+    "zkp_scalars_is_zero": (c_int, [u64, u64, u64, intp]),
+    "zkp_fr_batch_inverse_dev": (c_int, [u64, u64, u64, c_int]),
+    "zkp_fr_scan_dev": (c_int, [c_int, u64, u64, u64, u64, u64]),
+    "zkp_fr_div_linear_dev": (c_int, [u64, u64, u64, vp, u64, u64]),
+    "zkp_plonk_perm_terms_dev": (c_int, [u64, u64, u64, u64, u64, u64, u64, vp, vp, vp, u64, u64]),
+    "zkp_plonk_coset_setup_dev": (c_int, [u64, u32, vp, vp, vp, vp, u64, u64, u64]),
+    "zkp_plonk_quotient_dev": (c_int, [u64p, u64, u32, u64, u64, u64, vp, vp, vp, u64]),
     "zkp_fr_poly_mul": (c_int, [vp, u64, vp, u64, vp]),
     "zkp_fr_poly_divmod": (c_int, [vp, u64, vp, u64, vp, vp]),
     "zkp_msm_profile": (c_int, [c_int]),

@@ -241,13 +241,34 @@ __global__ void fr_div_vanishing_kernel(const Fr* __restrict__ a, uint64_t la, u
 // products such as tau^i (srs.py:78-82) and the accumulator z (permutation.py:120-135).
 static constexpr int PP_THREADS = 256, PP_ITEMS = 4, PP_TILE = PP_THREADS * PP_ITEMS;
 
-// inclusive block scan (Hillis-Steele in shared memory) of one Montgomery value per thread
-__device__ __forceinline__ Fr block_inclusive_product(Fr v, Fr* sm) {
+// The scans are generic over the monoid: SUM == false -> products (canonical in/out, Montgomery
+// inside), SUM == true -> sums (form-agnostic).
+template <bool SUM>
+__device__ __forceinline__ Fr scan_op(const Fr& a, const Fr& b) {
+  if (SUM) return a + b;
+  return a * b;
+}
+template <bool SUM>
+__device__ __forceinline__ Fr scan_id() {
+  return SUM ? Fr::zero() : Fr::one();
+}
+template <bool SUM>
+__device__ __forceinline__ Fr scan_in(const Fr& a) {
+  return SUM ? a : a.to_mont();
+}
+template <bool SUM>
+__device__ __forceinline__ Fr scan_out(const Fr& a) {
+  return SUM ? a : a.from_mont();
+}
+
+// inclusive block scan (Hillis-Steele in shared memory) of one value per thread
+template <bool SUM>
+__device__ __forceinline__ Fr block_inclusive_scan(Fr v, Fr* sm) {
   sm[threadIdx.x] = v;
   __syncthreads();
   for (int o = 1; o < PP_THREADS; o <<= 1) {
     Fr t = v;
-    if ((int)threadIdx.x >= o) t = sm[threadIdx.x - o] * v;
+    if ((int)threadIdx.x >= o) t = scan_op<SUM>(sm[threadIdx.x - o], v);
     __syncthreads();
     v = t;
     sm[threadIdx.x] = v;
@@ -256,56 +277,183 @@ __device__ __forceinline__ Fr block_inclusive_product(Fr v, Fr* sm) {
   return v;
 }
 
+template <bool SUM>
 __global__ void __launch_bounds__(PP_THREADS) pp_tile_products_kernel(const Fr* __restrict__ in, uint64_t n,
                                                                        Fr* __restrict__ tile_prod) {
   __shared__ Fr sm[PP_THREADS];
   uint64_t base = (uint64_t)blockIdx.x * PP_TILE + (uint64_t)threadIdx.x * PP_ITEMS;
-  Fr p = Fr::one();
+  Fr p = scan_id<SUM>();
 #pragma unroll
   for (int k = 0; k < PP_ITEMS; k++)
-    if (base + k < n) p = p * in[base + k].to_mont();
-  Fr inc = block_inclusive_product(p, sm);
+    if (base + k < n) p = scan_op<SUM>(p, scan_in<SUM>(in[base + k]));
+  Fr inc = block_inclusive_scan<SUM>(p, sm);
   if (threadIdx.x == PP_THREADS - 1) tile_prod[blockIdx.x] = inc;
 }
 
-// single block: tile_prod[i] <- exclusive prefix product (Montgomery)
-__global__ void __launch_bounds__(PP_THREADS) pp_tile_scan_kernel(Fr* __restrict__ tile_prod, uint64_t ntiles) {
+// single block: tile_prod[i] <- exclusive prefix; *total (optional) <- the grand total
+template <bool SUM>
+__global__ void __launch_bounds__(PP_THREADS) pp_tile_scan_kernel(Fr* __restrict__ tile_prod, uint64_t ntiles,
+                                                                   Fr* __restrict__ total) {
   __shared__ Fr sm[PP_THREADS];
   __shared__ Fr carry;
-  if (threadIdx.x == 0) carry = Fr::one();
+  if (threadIdx.x == 0) carry = scan_id<SUM>();
   __syncthreads();
   for (uint64_t base = 0; base < ntiles; base += PP_THREADS) {
     uint64_t i = base + threadIdx.x;
-    Fr v = i < ntiles ? tile_prod[i] : Fr::one();
-    Fr inc = block_inclusive_product(v, sm);
+    Fr v = i < ntiles ? tile_prod[i] : scan_id<SUM>();
+    Fr inc = block_inclusive_scan<SUM>(v, sm);
     Fr c = carry;
-    Fr prev = threadIdx.x ? sm[threadIdx.x - 1] : Fr::one();
+    Fr prev = threadIdx.x ? sm[threadIdx.x - 1] : scan_id<SUM>();
     __syncthreads();
-    if (i < ntiles) tile_prod[i] = c * prev;
-    if (threadIdx.x == PP_THREADS - 1) carry = c * inc;
+    if (i < ntiles) tile_prod[i] = scan_op<SUM>(c, prev);
+    if (threadIdx.x == PP_THREADS - 1) carry = scan_op<SUM>(c, inc);
     __syncthreads();
   }
+  if (total && threadIdx.x == 0) *total = scan_out<SUM>(carry);
 }
 
+template <bool SUM>
 __global__ void __launch_bounds__(PP_THREADS) pp_apply_kernel(const Fr* __restrict__ in, uint64_t n,
                                                                const Fr* __restrict__ tile_off, Fr* __restrict__ out) {
   __shared__ Fr sm[PP_THREADS];
   uint64_t base = (uint64_t)blockIdx.x * PP_TILE + (uint64_t)threadIdx.x * PP_ITEMS;
   Fr x[PP_ITEMS];
-  Fr p = Fr::one();
+  Fr p = scan_id<SUM>();
 #pragma unroll
   for (int k = 0; k < PP_ITEMS; k++) {
-    x[k] = (base + k < n) ? in[base + k].to_mont() : Fr::one();
-    p = p * x[k];
+    x[k] = (base + k < n) ? scan_in<SUM>(in[base + k]) : scan_id<SUM>();
+    p = scan_op<SUM>(p, x[k]);
   }
-  block_inclusive_product(p, sm);
+  block_inclusive_scan<SUM>(p, sm);
   Fr run = tile_off[blockIdx.x];
-  if (threadIdx.x) run = run * sm[threadIdx.x - 1];
+  if (threadIdx.x) run = scan_op<SUM>(run, sm[threadIdx.x - 1]);
 #pragma unroll
   for (int k = 0; k < PP_ITEMS; k++) {
-    if (base + k < n) out[base + k] = run.from_mont();
-    run = run * x[k];
+    if (base + k < n) out[base + k] = scan_out<SUM>(run);
+    run = scan_op<SUM>(run, x[k]);
   }
+}
+
+// exclusive scan of n device elements: out[i] = op(in[0..i)); optional grand total.  in != out.
+template <bool SUM>
+static int scan_dev(Context& c, const Fr* in, uint64_t n, Fr* out, Fr* total) {
+  uint64_t ntiles = (n + PP_TILE - 1) / PP_TILE;
+  Fr* tiles = g_arena.alloc(ntiles);
+  pp_tile_products_kernel<SUM><<<(unsigned)ntiles, PP_THREADS, 0, c.stream>>>(in, n, tiles);
+  CUDA_CHECK_LAUNCH();
+  pp_tile_scan_kernel<SUM><<<1, PP_THREADS, 0, c.stream>>>(tiles, ntiles, total);
+  CUDA_CHECK_LAUNCH();
+  pp_apply_kernel<SUM><<<(unsigned)ntiles, PP_THREADS, 0, c.stream>>>(in, n, tiles, out);
+  CUDA_CHECK_LAUNCH();
+  return 3;
+}
+
+
+// ------------------------------------------------------------------ device-handle vector kernels
+__global__ void fr_axpy_kernel(Fr* __restrict__ dst, Fr k_mont, const Fr* __restrict__ src, uint64_t n) {
+  uint64_t i = IDX64;
+  if (i < n) dst[i] = dst[i] + src[i] * k_mont;  // canonical * Montgomery constant -> canonical
+}
+__global__ void fr_add_const_kernel(Fr* __restrict__ v, Fr k, uint64_t n) {
+  uint64_t i = IDX64;
+  if (i < n) v[i] = v[i] + k;
+}
+// v[i] = first * base^i (canonical out); pow2tab: base^(2^k) Montgomery
+__global__ void fr_fill_powers_kernel(Fr* __restrict__ v, uint64_t n, Fr first, const Fr* __restrict__ pow2tab) {
+  uint64_t i = IDX64;
+  if (i >= n) return;
+  Fr r = first;
+  uint64_t e = i;
+  for (int k = 0; e; k++, e >>= 1)
+    if (e & 1) r = r * pow2tab[k];
+  v[i] = r;
+}
+__global__ void fr_is_zero_kernel(const Fr* __restrict__ v, uint64_t n, int* __restrict__ flag) {
+  uint64_t i = IDX64;
+  if (i < n && !v[i].is_zero()) *flag = 0;
+}
+// q_k = zeta^-(k+1) * (T - P_k - d_k), d_j = c_j zeta^j, P = exclusive prefix sums of d, T = sum d.
+// zinv_pow2: (zeta^-1)^(2^k) Montgomery.  All values canonical.
+__global__ void fr_div_linear_finish_kernel(const Fr* __restrict__ d, const Fr* __restrict__ P, const Fr* __restrict__ T,
+                                            const Fr* __restrict__ zinv_pow2, uint64_t n_out, Fr* __restrict__ q) {
+  uint64_t k = IDX64;
+  if (k >= n_out) return;
+  Fr s = *T - P[k] - d[k];
+  uint64_t e = k + 1;
+  for (int b = 0; e; b++, e >>= 1)
+    if (e & 1) s = s * zinv_pow2[b];
+  q[k] = s;
+}
+
+// PLONK grand-product factors (permutation.py:120-135), canonical in/out:
+//   num_i = (a_i + beta w^i + gamma)(b_i + beta K1 w^i + gamma)(c_i + beta K2 w^i + gamma)
+//   den_i = (a_i + beta s1_i + gamma)(b_i + beta s2_i + gamma)(c_i + beta s3_i + gamma)
+__global__ void plonk_perm_terms_kernel(const Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ c,
+                                        const Fr* __restrict__ s1, const Fr* __restrict__ s2, const Fr* __restrict__ s3,
+                                        uint64_t n, const Fr* __restrict__ omega_pow2, Fr beta_c, Fr gamma_c,
+                                        Fr* __restrict__ num, Fr* __restrict__ den) {
+  uint64_t i = IDX64;
+  if (i >= n) return;
+  Fr beta = beta_c.to_mont(), gamma = gamma_c.to_mont();
+  Fr w = Fr::one();
+  uint64_t e = i;
+  for (int k = 0; e; k++, e >>= 1)
+    if (e & 1) w = w * omega_pow2[k];
+  Fr bw = beta * w;
+  Fr am = a[i].to_mont() + gamma, bm = b[i].to_mont() + gamma, cm = c[i].to_mont() + gamma;
+  Fr nu = (am + bw) * (bm + bw.dbl()) * (cm + bw.dbl() + bw);
+  Fr de = (am + beta * s1[i].to_mont()) * (bm + beta * s2[i].to_mont()) * (cm + beta * s3[i].to_mont());
+  num[i] = nu.from_mont();
+  den[i] = de.from_mont();
+}
+
+// zh_inv[j] = 1 / (g^n * (w8^n)^j - 1), j < 8 (Montgomery): Z_H on the 8n coset takes 8 values.
+__global__ void plonk_zh_inv_kernel(Fr g_n_canon, Fr w8n_canon, uint32_t ext, Fr* __restrict__ out) {
+  uint32_t j = threadIdx.x;
+  if (j >= ext) return;
+  Fr v = g_n_canon.to_mont(), w = w8n_canon.to_mont();
+  for (uint32_t k = 0; k < j; k++) v = v * w;
+  out[j] = (v - Fr::one()).inv();
+}
+
+struct PlonkQuotArgs {
+  const Fr *a, *b, *c, *z, *ql, *qr, *qo, *qm, *qc, *s1, *s2, *s3;  // 8n coset evaluations, Montgomery
+  const Fr *x;        // coset points x_i = g w8^i, Montgomery
+  const Fr *l1f;      // 1 / (n (x_i - 1)), Montgomery
+  const Fr *zh_inv;   // 8 values
+  Fr beta, gamma, alpha;  // canonical
+  uint64_t N;         // ext * n
+  uint32_t ext;       // coset size / n: 4 (n >= 8), 8 (n = 2, 4), 16 (n = 1); N >= 3n + 6
+  Fr* t;              // out: quotient evaluations, Montgomery
+};
+// t(x) = [gate + alpha*(perm_num - perm_den)] / Z_H(x) + alpha^2 (z(x) - 1) / (n (x - 1))
+// (round3.py:114-147 evaluated pointwise on a coset where Z_H != 0; the L1 term's Z_H cancels).
+__global__ void __launch_bounds__(128) plonk_quotient_kernel(PlonkQuotArgs q) {
+  uint64_t i = IDX64;
+  if (i >= q.N) return;
+  Fr beta = q.beta.to_mont(), gamma = q.gamma.to_mont(), alpha = q.alpha.to_mont();
+  Fr a = q.a[i], b = q.b[i], c = q.c[i], z = q.z[i];
+  Fr zw = q.z[(i + q.ext) & (q.N - 1)];  // z(w x): w = w_N^ext
+  Fr gate = q.ql[i] * a + q.qr[i] * b + q.qo[i] * c + q.qm[i] * (a * b) + q.qc[i];
+  Fr bx = beta * q.x[i];
+  Fr ag = a + gamma, bg = b + gamma, cg = c + gamma;
+  Fr num = (ag + bx) * (bg + bx.dbl()) * (cg + bx.dbl() + bx) * z;
+  Fr den = (ag + beta * q.s1[i]) * (bg + beta * q.s2[i]) * (cg + beta * q.s3[i]) * zw;
+  Fr main = (gate + alpha * (num - den)) * q.zh_inv[i & (q.ext - 1)];
+  Fr l1 = alpha * alpha * ((z - Fr::one()) * q.l1f[i]);
+  q.t[i] = main + l1;
+}
+// x_i = g * w8^i and l1f_i = 1/(n (x_i - 1)) before inversion: writes x (Montgomery) and n(x_i-1) (Montgomery)
+__global__ void plonk_coset_points_kernel(uint64_t N, Fr g_canon, const Fr* __restrict__ w8_pow2, Fr n_canon,
+                                          Fr* __restrict__ x, Fr* __restrict__ l1den) {
+  uint64_t i = IDX64;
+  if (i >= N) return;
+  Fr r = g_canon.to_mont();
+  uint64_t e = i;
+  for (int k = 0; e; k++, e >>= 1)
+    if (e & 1) r = r * w8_pow2[k];
+  x[i] = r;
+  l1den[i] = n_canon.to_mont() * (r - Fr::one());
 }
 
 // ------------------------------------------------------------------ device-level polynomial ops (Montgomery)
@@ -508,18 +656,10 @@ int zkp_fr_prefix_product(const uint8_t* a, uint64_t n, uint8_t* out) {
     if (n && (!a || !out)) throw InvalidArgument("zkp_fr_prefix_product: null argument");
     if (!n) return;
     ArenaScope scope;
-    uint64_t ntiles = (n + PP_TILE - 1) / PP_TILE;
     Fr* da = g_arena.alloc(n);
     Fr* dout = g_arena.alloc(n);
-    Fr* tiles = g_arena.alloc(ntiles);
     CUDA_CHECK(cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, c.stream));
-    pp_tile_products_kernel<<<(unsigned)ntiles, PP_THREADS, 0, c.stream>>>(da, n, tiles);
-    CUDA_CHECK_LAUNCH();
-    pp_tile_scan_kernel<<<1, PP_THREADS, 0, c.stream>>>(tiles, ntiles);
-    CUDA_CHECK_LAUNCH();
-    pp_apply_kernel<<<(unsigned)ntiles, PP_THREADS, 0, c.stream>>>(da, n, tiles, dout);
-    CUDA_CHECK_LAUNCH();
-    c.launches += 3;
+    c.launches += scan_dev<false>(c, da, n, dout, nullptr);
     CUDA_CHECK(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
   });
@@ -761,6 +901,252 @@ int zkp_groth16_quotient_dev(uint64_t a, uint64_t b, uint64_t cc, uint64_t len, 
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
     *h_out = registry().put(std::move(hq));
     *rem_out = registry().put(std::move(hr));
+  });
+}
+
+// ------------------------------------------------------------------ handle-based vector API (PLONK at scale)
+static Fr fr_from_bytes(const uint8_t* b) {
+  Fr x;
+  memcpy(x.v, b, 32);
+  return x;
+}
+static Fr* hptr(uint64_t h, uint64_t off, uint64_t n, const char* what) {
+  Resource* r = need(h, HandleKind::Scalars, what);
+  if (off + n > r->n) throw InvalidArgument(std::string(what) + ": range out of bounds");
+  return r->buf.as<Fr>() + off;
+}
+// canonical constant -> Montgomery on the device (one tiny kernel + 32-byte read back)
+static Fr host_to_mont(Context& c, const uint8_t* k) {
+  Fr* d = g_arena.alloc(1);
+  CUDA_CHECK(cudaMemcpyAsync(d, k, 32, cudaMemcpyHostToDevice, c.stream));
+  fr_to_mont_kernel<<<1, 32, 0, c.stream>>>(d, 1, d);
+  CUDA_CHECK_LAUNCH();
+  Fr out;
+  CUDA_CHECK(cudaMemcpyAsync(&out, d, 32, cudaMemcpyDeviceToHost, c.stream));
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  c.launches++;
+  return out;
+}
+
+int zkp_fr_vec_op_dev(int op, uint64_t dst, uint64_t dst_off, uint64_t a, uint64_t a_off, uint64_t b, uint64_t b_off,
+                      uint64_t n) {
+  return guarded([&](Context& c) {
+    if (op < 0 || op > 2) throw InvalidArgument("zkp_fr_vec_op_dev: op must be 0 (add), 1 (sub) or 2 (mul)");
+    if (!n) return;
+    Fr* d = hptr(dst, dst_off, n, "zkp_fr_vec_op_dev");
+    Fr* pa = hptr(a, a_off, n, "zkp_fr_vec_op_dev");
+    Fr* pb = hptr(b, b_off, n, "zkp_fr_vec_op_dev");
+    fr_vec_op_kernel<<<GRID_1D(n)>>>(op, pa, pb, n, d);
+    CUDA_CHECK_LAUNCH();
+    c.launches++;
+  });
+}
+
+int zkp_fr_axpy_dev(uint64_t dst, uint64_t dst_off, const uint8_t k[32], uint64_t src, uint64_t src_off, uint64_t n) {
+  return guarded([&](Context& c) {
+    if (!k) throw InvalidArgument("zkp_fr_axpy_dev: null factor");
+    if (!n) return;
+    ArenaScope scope;
+    Fr* d = hptr(dst, dst_off, n, "zkp_fr_axpy_dev");
+    Fr* s = hptr(src, src_off, n, "zkp_fr_axpy_dev");
+    Fr km = host_to_mont(c, k);
+    fr_axpy_kernel<<<GRID_1D(n)>>>(d, km, s, n);
+    CUDA_CHECK_LAUNCH();
+    c.launches++;
+  });
+}
+
+int zkp_scalars_add_const(uint64_t h, uint64_t off, uint64_t n, const uint8_t k[32]) {
+  return guarded([&](Context& c) {
+    if (!k) throw InvalidArgument("zkp_scalars_add_const: null constant");
+    if (!n) return;
+    Fr* d = hptr(h, off, n, "zkp_scalars_add_const");
+    fr_add_const_kernel<<<GRID_1D(n)>>>(d, fr_from_bytes(k), n);
+    CUDA_CHECK_LAUNCH();
+    c.launches++;
+  });
+}
+
+int zkp_scalars_fill_powers(uint64_t h, uint64_t off, uint64_t n, const uint8_t first[32], const uint8_t base[32]) {
+  return guarded([&](Context& c) {
+    if (!first || !base) throw InvalidArgument("zkp_scalars_fill_powers: null argument");
+    if (!n) return;
+    Fr* d = hptr(h, off, n, "zkp_scalars_fill_powers");
+    FrBytes bb;
+    memcpy(bb.b, base, 32);
+    int launches = 0;
+    const Fr* tab = pow2_table(c, bb, false, &launches);
+    fr_fill_powers_kernel<<<GRID_1D(n)>>>(d, n, fr_from_bytes(first), tab);
+    CUDA_CHECK_LAUNCH();
+    c.launches += launches + 1;
+  });
+}
+
+int zkp_scalars_convert(uint64_t h, uint64_t off, uint64_t n, int to_montgomery) {
+  return guarded([&](Context& c) {
+    if (!n) return;
+    Fr* d = hptr(h, off, n, "zkp_scalars_convert");
+    if (to_montgomery) fr_to_mont_kernel<<<GRID_1D(n)>>>(d, n, d);
+    else fr_from_mont_kernel<<<GRID_1D(n)>>>(d, n, d);
+    CUDA_CHECK_LAUNCH();
+    c.launches++;
+  });
+}
+
+int zkp_scalars_is_zero(uint64_t h, uint64_t off, uint64_t n, int* out_all_zero) {
+  return guarded([&](Context& c) {
+    if (!out_all_zero) throw InvalidArgument("zkp_scalars_is_zero: null output");
+    *out_all_zero = 1;
+    if (!n) return;
+    ArenaScope scope;
+    Fr* d = hptr(h, off, n, "zkp_scalars_is_zero");
+    int* flag = reinterpret_cast<int*>(g_arena.alloc(1));
+    int one = 1;
+    CUDA_CHECK(cudaMemcpyAsync(flag, &one, 4, cudaMemcpyHostToDevice, c.stream));
+    fr_is_zero_kernel<<<GRID_1D(n)>>>(d, n, flag);
+    CUDA_CHECK_LAUNCH();
+    c.launches++;
+    CUDA_CHECK(cudaMemcpyAsync(out_all_zero, flag, 4, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int zkp_fr_batch_inverse_dev(uint64_t h, uint64_t off, uint64_t n, int montgomery) {
+  return guarded([&](Context& c) {
+    if (!n) return;
+    ArenaScope scope;
+    Fr* d = hptr(h, off, n, "zkp_fr_batch_inverse_dev");
+    Fr* tmp = g_arena.alloc(n);
+    uint64_t T = (n + BATCH_INV_CHUNK - 1) / BATCH_INV_CHUNK;
+    fr_batch_inverse_kernel<<<ceil_div(T, 128), 128, 0, c.stream>>>(d, n, T, montgomery ? 1 : 0, tmp);
+    CUDA_CHECK_LAUNCH();
+    CUDA_CHECK(cudaMemcpyAsync(d, tmp, n * 32, cudaMemcpyDeviceToDevice, c.stream));
+    c.launches++;
+  });
+}
+
+// exclusive scan: op 0 product (dst[0] = 1), 1 sum (dst[0] = 0); canonical values; dst must not overlap src
+int zkp_fr_scan_dev(int op, uint64_t dst, uint64_t dst_off, uint64_t src, uint64_t src_off, uint64_t n) {
+  return guarded([&](Context& c) {
+    if (op != 0 && op != 1) throw InvalidArgument("zkp_fr_scan_dev: op must be 0 (product) or 1 (sum)");
+    if (!n) return;
+    ArenaScope scope;
+    Fr* d = hptr(dst, dst_off, n, "zkp_fr_scan_dev");
+    Fr* s = hptr(src, src_off, n, "zkp_fr_scan_dev");
+    c.launches += op == 0 ? scan_dev<false>(c, s, n, d, nullptr) : scan_dev<true>(c, s, n, d, nullptr);
+  });
+}
+
+// dst[0..n-1) = coefficients of (p(x) - p(zeta)) / (x - zeta) for p = src[0..n)   (poly_div by a linear
+// factor, round5.py:165-171 / kzg.py:95-104), as scale-by-powers + one sum scan.  zeta != 0.
+int zkp_fr_div_linear_dev(uint64_t src, uint64_t src_off, uint64_t n, const uint8_t zeta[32], uint64_t dst,
+                          uint64_t dst_off) {
+  return guarded([&](Context& c) {
+    if (!zeta) throw InvalidArgument("zkp_fr_div_linear_dev: null zeta");
+    if (n < 2) return;
+    ArenaScope scope;
+    Fr* p = hptr(src, src_off, n, "zkp_fr_div_linear_dev");
+    Fr* q = hptr(dst, dst_off, n - 1, "zkp_fr_div_linear_dev");
+    if (host_is_zero32(zeta)) {
+      CUDA_CHECK(cudaMemcpyAsync(q, p + 1, (n - 1) * 32, cudaMemcpyDeviceToDevice, c.stream));
+      return;
+    }
+    FrBytes zb;
+    memcpy(zb.b, zeta, 32);
+    int launches = 0;
+    const Fr* zp = pow2_table(c, zb, false, &launches);
+    const Fr* zip = pow2_table(c, zb, true, &launches);
+    Fr* d = g_arena.alloc(n);
+    Fr* P = g_arena.alloc(n);
+    Fr* T = g_arena.alloc(1);
+    CUDA_CHECK(cudaMemcpyAsync(d, p, n * 32, cudaMemcpyDeviceToDevice, c.stream));
+    launches += scale_by_powers(c, d, n, zp);
+    launches += scan_dev<true>(c, d, n, P, T);
+    fr_div_linear_finish_kernel<<<GRID_1D(n - 1)>>>(d, P, T, zip, n - 1, q);
+    CUDA_CHECK_LAUNCH();
+    c.launches += launches + 1;
+  });
+}
+
+int zkp_plonk_perm_terms_dev(uint64_t a, uint64_t b, uint64_t cc, uint64_t s1, uint64_t s2, uint64_t s3, uint64_t n,
+                             const uint8_t omega[32], const uint8_t beta[32], const uint8_t gamma[32], uint64_t num,
+                             uint64_t den) {
+  return guarded([&](Context& c) {
+    if (!omega || !beta || !gamma) throw InvalidArgument("zkp_plonk_perm_terms_dev: null scalar");
+    if (!n) return;
+    const char* w = "zkp_plonk_perm_terms_dev";
+    FrBytes ob;
+    memcpy(ob.b, omega, 32);
+    int launches = 0;
+    const Fr* tab = pow2_table(c, ob, false, &launches);
+    plonk_perm_terms_kernel<<<GRID_1D(n)>>>(hptr(a, 0, n, w), hptr(b, 0, n, w), hptr(cc, 0, n, w), hptr(s1, 0, n, w),
+                                            hptr(s2, 0, n, w), hptr(s3, 0, n, w), n, tab, fr_from_bytes(beta),
+                                            fr_from_bytes(gamma), hptr(num, 0, n, w), hptr(den, 0, n, w));
+    CUDA_CHECK_LAUNCH();
+    c.launches += launches + 1;
+  });
+}
+
+// Static per-domain data of the quotient kernel: x (N = 8n coset points, Montgomery), l1f = 1/(n (x_i-1))
+// (Montgomery), zh_inv (8 values at zh8[0..8)).  g = coset shift, w8 = primitive 8n-th root.
+int zkp_plonk_coset_setup_dev(uint64_t n, uint32_t ext, const uint8_t g[32], const uint8_t w8[32],
+                              const uint8_t g_pow_n[32], const uint8_t w8_pow_n[32], uint64_t x_out, uint64_t l1f_out,
+                              uint64_t zh8_out) {
+  return guarded([&](Context& c) {
+    if (!g || !w8 || !g_pow_n || !w8_pow_n) throw InvalidArgument("zkp_plonk_coset_setup_dev: null scalar");
+    const char* w = "zkp_plonk_coset_setup_dev";
+    if (ext != 4 && ext != 8 && ext != 16) throw InvalidArgument("zkp_plonk_coset_setup_dev: ext must be 4, 8 or 16");
+    uint64_t N = (uint64_t)ext * n;
+    ArenaScope scope;
+    Fr* x = hptr(x_out, 0, N, w);
+    Fr* l1 = hptr(l1f_out, 0, N, w);
+    Fr* zh = hptr(zh8_out, 0, ext, w);
+    FrBytes wb;
+    memcpy(wb.b, w8, 32);
+    int launches = 0;
+    const Fr* tab = pow2_table(c, wb, false, &launches);
+    uint8_t nb[32] = {0};
+    for (int i = 0; i < 8; i++) nb[i] = (uint8_t)(n >> (8 * i));
+    plonk_coset_points_kernel<<<GRID_1D(N)>>>(N, fr_from_bytes(g), tab, fr_from_bytes(nb), x, l1);
+    CUDA_CHECK_LAUNCH();
+    Fr* tmp = g_arena.alloc(N);
+    uint64_t T = (N + BATCH_INV_CHUNK - 1) / BATCH_INV_CHUNK;
+    fr_batch_inverse_kernel<<<ceil_div(T, 128), 128, 0, c.stream>>>(l1, N, T, 1, tmp);
+    CUDA_CHECK_LAUNCH();
+    CUDA_CHECK(cudaMemcpyAsync(l1, tmp, N * 32, cudaMemcpyDeviceToDevice, c.stream));
+    plonk_zh_inv_kernel<<<1, 32, 0, c.stream>>>(fr_from_bytes(g_pow_n), fr_from_bytes(w8_pow_n), ext, zh);
+    CUDA_CHECK_LAUNCH();
+    c.launches += launches + 3;
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+// evals: 12 handles in the order a, b, c, z, q_l, q_r, q_o, q_m, q_c, s_sigma1, s_sigma2, s_sigma3 (8n
+// Montgomery coset evaluations each); writes the quotient's coset evaluations (Montgomery) to t_out.
+int zkp_plonk_quotient_dev(const uint64_t evals[12], uint64_t n, uint32_t ext, uint64_t x, uint64_t l1f, uint64_t zh8,
+                           const uint8_t beta[32], const uint8_t gamma[32], const uint8_t alpha[32], uint64_t t_out) {
+  return guarded([&](Context& c) {
+    if (!evals || !beta || !gamma || !alpha) throw InvalidArgument("zkp_plonk_quotient_dev: null argument");
+    const char* w = "zkp_plonk_quotient_dev";
+    if (ext != 4 && ext != 8 && ext != 16) throw InvalidArgument("zkp_plonk_quotient_dev: ext must be 4, 8 or 16");
+    uint64_t N = (uint64_t)ext * n;
+    if (N & (N - 1)) throw InvalidArgument("zkp_plonk_quotient_dev: n must be a power of two");
+    if (N < 3 * n + 6) throw InvalidArgument("zkp_plonk_quotient_dev: coset too small for the quotient degree");
+    PlonkQuotArgs q;
+    const Fr** slots[12] = {&q.a, &q.b, &q.c, &q.z, &q.ql, &q.qr, &q.qo, &q.qm, &q.qc, &q.s1, &q.s2, &q.s3};
+    for (int k = 0; k < 12; k++) *slots[k] = hptr(evals[k], 0, N, w);
+    q.x = hptr(x, 0, N, w);
+    q.l1f = hptr(l1f, 0, N, w);
+    q.zh_inv = hptr(zh8, 0, ext, w);
+    q.ext = ext;
+    q.beta = fr_from_bytes(beta);
+    q.gamma = fr_from_bytes(gamma);
+    q.alpha = fr_from_bytes(alpha);
+    q.N = N;
+    q.t = hptr(t_out, 0, N, w);
+    plonk_quotient_kernel<<<ceil_div(N, 128), 128, 0, c.stream>>>(q);
+    CUDA_CHECK_LAUNCH();
+    c.launches++;
   });
 }
 

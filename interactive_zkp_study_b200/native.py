@@ -387,3 +387,65 @@ def dbg_point_add(group, a_bytes, b_bytes, n):
     out = bytearray(sz * n)
     check(_lib.lib().zkp_dbg_point_add(group, buf(a_bytes), buf(b_bytes), n, buf(out)))
     return bytes(out)
+
+
+# ------------------------------------------------------------------ device-resident vector ops (handles)
+def vec_op_dev(op, dst, dst_off, a, a_off, b, b_off, n):
+    check(_lib.lib().zkp_fr_vec_op_dev(op, dst.handle, dst_off, a.handle, a_off, b.handle, b_off, n))
+
+
+def axpy_dev(dst, dst_off, k, src, src_off, n):
+    check(_lib.lib().zkp_fr_axpy_dev(dst.handle, dst_off, buf(fe_bytes(k)), src.handle, src_off, n))
+
+
+def scalars_add_const(h, off, n, k):
+    check(_lib.lib().zkp_scalars_add_const(h.handle, off, n, buf(fe_bytes(k))))
+
+
+def scalars_fill_powers(h, off, n, first, base):
+    check(_lib.lib().zkp_scalars_fill_powers(h.handle, off, n, buf(fe_bytes(first)), buf(fe_bytes(base))))
+
+
+def scalars_convert(h, off, n, to_montgomery):
+    check(_lib.lib().zkp_scalars_convert(h.handle, off, n, 1 if to_montgomery else 0))
+
+
+def scalars_is_zero(h, off, n):
+    flag = ctypes.c_int()
+    check(_lib.lib().zkp_scalars_is_zero(h.handle, off, n, ctypes.byref(flag)))
+    return bool(flag.value)
+
+
+def batch_inverse_dev(h, off, n, montgomery=False):
+    check(_lib.lib().zkp_fr_batch_inverse_dev(h.handle, off, n, 1 if montgomery else 0))
+
+
+def scan_dev(op, dst, dst_off, src, src_off, n):
+    check(_lib.lib().zkp_fr_scan_dev(op, dst.handle, dst_off, src.handle, src_off, n))
+
+
+def div_linear_dev(src, src_off, n, zeta, dst, dst_off):
+    check(_lib.lib().zkp_fr_div_linear_dev(src.handle, src_off, n, buf(fe_bytes(zeta)), dst.handle, dst_off))
+
+
+def ntt_dev(h, off, log_n, omega, inverse=False, coset_shift=None):
+    cs = fe_bytes(coset_shift) if coset_shift is not None else None
+    check(_lib.lib().zkp_fr_ntt_dev(h.handle, off, log_n, buf(fe_bytes(omega)), 1 if inverse else 0, buf(cs)))
+
+
+def plonk_perm_terms_dev(a, b, c, s1, s2, s3, n, omega, beta, gamma, num, den):
+    check(_lib.lib().zkp_plonk_perm_terms_dev(a.handle, b.handle, c.handle, s1.handle, s2.handle, s3.handle, n,
+                                              buf(fe_bytes(omega)), buf(fe_bytes(beta)), buf(fe_bytes(gamma)),
+                                              num.handle, den.handle))
+
+
+def plonk_coset_setup_dev(n, ext, g, w8, x_out, l1f_out, zh8_out):
+    check(_lib.lib().zkp_plonk_coset_setup_dev(n, ext, buf(fe_bytes(g)), buf(fe_bytes(w8)), buf(fe_bytes(pow(g, n, R_MOD))),
+                                               buf(fe_bytes(pow(w8, n, R_MOD))), x_out.handle, l1f_out.handle,
+                                               zh8_out.handle))
+
+
+def plonk_quotient_dev(evals12, n, ext, x, l1f, zh8, beta, gamma, alpha, t_out):
+    arr = (ctypes.c_uint64 * 12)(*[h.handle for h in evals12])
+    check(_lib.lib().zkp_plonk_quotient_dev(arr, n, ext, x.handle, l1f.handle, zh8.handle, buf(fe_bytes(beta)),
+                                            buf(fe_bytes(gamma)), buf(fe_bytes(alpha)), t_out.handle))
