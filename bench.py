@@ -412,6 +412,11 @@ def run_ours(args):
         except Exception as e:  # never lose the headline line
             extras["groth16_prove_error"] = repr(e)
         try:
+            import plonk_large
+            extras["plonk_prove_2^%d" % args.log_n] = plonk_large.run(args.log_n, 3, verify=True, quiet=True)
+        except Exception as e:
+            extras["plonk_prove_error"] = repr(e)
+        try:
             extras["fr_ntt"] = ntt_extra(nat, args.log_n)
         except Exception as e:
             extras["fr_ntt_error"] = repr(e)
