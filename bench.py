@@ -264,15 +264,22 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    gbuf = {}
+    if world > 1:
+        import torch
+        gbuf = {"host": torch.empty(128, dtype=torch.uint8).pin_memory(),
+                "send": torch.empty(128, dtype=torch.uint8, device="cuda"),
+                "recv": torch.empty(128 * world, dtype=torch.uint8, device="cuda"),
+                "host_all": torch.empty(128 * world, dtype=torch.uint8).pin_memory()}
+
     def gather_and_fold(partial):
         """The one exchange step: 128 B per rank over NCCL (NVLink), folded on rank 0."""
-        import torch
-        t = torch.frombuffer(bytearray(partial), dtype=torch.uint8).cuda()
-        out = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(out, t)
+        gbuf["host"].copy_(torch.frombuffer(bytearray(partial), dtype=torch.uint8))
+        gbuf["send"].copy_(gbuf["host"], non_blocking=True)
+        dist.all_gather_into_tensor(gbuf["recv"], gbuf["send"])
         if rank == 0:
-            blob = b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
-            return nat.g1_combine_partials(blob, world)
+            gbuf["host_all"].copy_(gbuf["recv"])            # one D2H of world*128 bytes (synchronises)
+            return nat.g1_combine_partials(gbuf["host_all"].numpy().tobytes(), world)
         return None
 
     def step_resident(i):

@@ -179,6 +179,11 @@ const Fr* pow2_table(Context& c, const FrBytes& x, bool inverted, int* launches)
   key.push_back(inverted ? 1 : 0);
   auto it = g_pow2_cache.find(key);
   if (it != g_pow2_cache.end()) return it->second.as<Fr>();
+  if (g_pow2_cache.size() >= 512) {  // per-proof challenges (zeta, ...) would otherwise accumulate
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    for (auto& kv : g_pow2_cache) kv.second.release();
+    g_pow2_cache.clear();
+  }
   DevBuf& buf = g_pow2_cache[key];
   buf.reserve(32 * sizeof(Fr));
   Fr xv;
@@ -290,13 +295,15 @@ int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes&
     a.S = S;
     a.log_g = NTT_LOG_TILE - S;  // >= NTT_Q and <= s0 (s0 >= 10)
     if (a.log_g > a.s0) a.log_g = a.s0;
+    if (done + S == log_n) a.dst = data;  // the last pass lands in the caller's buffer (no extra copy)
     uint32_t tile = 1u << (a.S + a.log_g);
     ntt_pass_kernel<<<n / tile, tile / 2, tile * 32, c.stream>>>(a);
     CUDA_CHECK_LAUNCH();
     launches++;
     done += S;
   }
-  CUDA_CHECK(cudaMemcpyAsync(data, scratch, (size_t)n * sizeof(Fr), cudaMemcpyDeviceToDevice, c.stream));
+  if (S1 == log_n)  // single pass: the bit-reversed gather could not be done in place
+    CUDA_CHECK(cudaMemcpyAsync(data, scratch, (size_t)n * sizeof(Fr), cudaMemcpyDeviceToDevice, c.stream));
   return launches;
 }
 

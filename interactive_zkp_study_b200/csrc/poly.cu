@@ -159,53 +159,54 @@ __global__ void __launch_bounds__(128) fr_batch_inverse_kernel(const Fr* __restr
   }
 }
 
-// Horner in two levels: thread j evaluates its chunk of HORNER_CHUNK coefficients at x, then a
-// single block combines the partials with x^(HORNER_CHUNK*j).  coeffs canonical, x Montgomery.
+// Horner evaluation in levels of HORNER_CHUNK: thread j evaluates its chunk of 64 coefficients at x
+// (level 0), the n/64 partial values are the coefficients of a polynomial in x^64 (level 1), and so
+// on until one value is left: log_64(n) launches, each 64 sequential multiply-adds deep.
+// coeffs canonical, powers Montgomery (xs[l] = x^(64^l)), results canonical.
 static constexpr int HORNER_CHUNK = 64;
-__global__ void horner_partial_kernel(const Fr* __restrict__ coeffs, uint64_t n, Fr x, Fr* __restrict__ partial) {
+__global__ void horner_powers_kernel(const Fr* __restrict__ x_canon, Fr* __restrict__ xs, int levels) {
+  if (IDX64 != 0) return;
+  Fr x = x_canon->to_mont();
+  for (int l = 0; l < levels; l++) {
+    xs[l] = x;
+    for (int k = 1; k < HORNER_CHUNK; k <<= 1) x = x.sqr();
+  }
+}
+__global__ void horner_partial_kernel(const Fr* __restrict__ coeffs, uint64_t n, const Fr* __restrict__ xp,
+                                      Fr* __restrict__ partial) {
   uint64_t j = IDX64;
   uint64_t beg = j * HORNER_CHUNK;
   if (beg >= n) return;
   uint64_t end = beg + HORNER_CHUNK < n ? beg + HORNER_CHUNK : n;
+  Fr x = *xp;
   Fr acc = Fr::zero();
   for (uint64_t i = end; i > beg; i--) acc = acc * x + coeffs[i - 1];  // canonical coeffs: acc stays canonical
   partial[j] = acc;
 }
-// single block of 256 threads: out = sum_j partial[j] * xc^j, xc = x^HORNER_CHUNK given as pow2 table
-__global__ void horner_combine_kernel(const Fr* __restrict__ partial, uint64_t np, const Fr* __restrict__ xc_pow2,
-                                      Fr* __restrict__ out) {
-  __shared__ Fr sm[256];
-  Fr acc = Fr::zero();
-  for (uint64_t j = threadIdx.x; j < np; j += 256) {
-    Fr p = partial[j];
-    // xc^j from the table
-    Fr w = Fr::one();
-    bool first = true;
-    uint64_t e = j;
-    for (int k = 0; e; k++, e >>= 1)
-      if (e & 1) {
-        if (first) { w = xc_pow2[k]; first = false; }
-        else w = w * xc_pow2[k];
-      }
-    acc = acc + (first ? p : p * w);  // p canonical, w Montgomery -> canonical
+
+// p(x) for n device coefficients (canonical); x: 32 canonical bytes on the host; result left in *out_dev
+static int poly_eval_dev_impl(Context& c, const Fr* coeffs, uint64_t n, const uint8_t* x, Fr* out_dev) {
+  int levels = 0;
+  for (uint64_t m = n; m > 1; m = (m + HORNER_CHUNK - 1) / HORNER_CHUNK) levels++;
+  if (levels == 0) levels = 1;
+  Fr* xs = g_arena.alloc(levels + 1);
+  Fr* xc = xs + levels;
+  CUDA_CHECK(cudaMemcpyAsync(xc, x, 32, cudaMemcpyHostToDevice, c.stream));
+  horner_powers_kernel<<<1, 32, 0, c.stream>>>(xc, xs, levels);
+  CUDA_CHECK_LAUNCH();
+  int launches = 1;
+  const Fr* cur = coeffs;
+  uint64_t m = n;
+  for (int l = 0; l < levels; l++) {
+    uint64_t np = (m + HORNER_CHUNK - 1) / HORNER_CHUNK;
+    Fr* part = np == 1 ? out_dev : g_arena.alloc(np);
+    horner_partial_kernel<<<GRID_1D(np)>>>(cur, m, xs + l, part);
+    CUDA_CHECK_LAUNCH();
+    launches++;
+    cur = part;
+    m = np;
   }
-  sm[threadIdx.x] = acc;
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) sm[threadIdx.x] = sm[threadIdx.x] + sm[threadIdx.x + s];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *out = sm[0];
-}
-// tab[k] = x^(HORNER_CHUNK * 2^k), k < 40
-__global__ void horner_pow_table_kernel(Fr x, Fr* __restrict__ tab) {
-  if (IDX64 != 0) return;
-  Fr xc = x;
-  for (int k = 1; k < HORNER_CHUNK; k <<= 1) xc = xc.sqr();
-  for (int k = 0; k < 40; k++) {
-    tab[k] = xc;
-    xc = xc.sqr();
-  }
+  return launches;
 }
 
 // out[j] = sum_i vec[i] * mat[i*cols + j]   (canonical in/out)
@@ -674,28 +675,10 @@ int zkp_fr_poly_eval(const uint8_t* coeffs, uint64_t n, const uint8_t x[32], uin
     }
     ArenaScope scope;
     Fr* dc = g_arena.alloc(n);
-    uint64_t np = (n + HORNER_CHUNK - 1) / HORNER_CHUNK;
-    Fr* partial = g_arena.alloc(np);
-    Fr* tab = g_arena.alloc(41);
+    Fr* res = g_arena.alloc(1);
     CUDA_CHECK(cudaMemcpyAsync(dc, coeffs, n * 32, cudaMemcpyHostToDevice, c.stream));
-    // x -> Montgomery on the host side of the launch: pass canonical, convert in a tiny kernel
-    Fr xc;
-    memcpy(xc.v, x, 32);
-    Fr* dx = tab + 40;
-    CUDA_CHECK(cudaMemcpyAsync(dx, &xc, 32, cudaMemcpyHostToDevice, c.stream));
-    fr_to_mont_kernel<<<1, 32, 0, c.stream>>>(dx, 1, dx);
-    CUDA_CHECK_LAUNCH();
-    Fr xm;
-    CUDA_CHECK(cudaMemcpyAsync(&xm, dx, 32, cudaMemcpyDeviceToHost, c.stream));
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
-    horner_pow_table_kernel<<<1, 32, 0, c.stream>>>(xm, tab);
-    CUDA_CHECK_LAUNCH();
-    horner_partial_kernel<<<GRID_1D(np)>>>(dc, n, xm, partial);
-    CUDA_CHECK_LAUNCH();
-    horner_combine_kernel<<<1, 256, 0, c.stream>>>(partial, np, tab, dx);
-    CUDA_CHECK_LAUNCH();
-    c.launches += 4;
-    CUDA_CHECK(cudaMemcpyAsync(out, dx, 32, cudaMemcpyDeviceToHost, c.stream));
+    c.launches += poly_eval_dev_impl(c, dc, n, x, res);
+    CUDA_CHECK(cudaMemcpyAsync(out, res, 32, cudaMemcpyDeviceToHost, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
   });
 }
@@ -819,24 +802,9 @@ int zkp_fr_poly_eval_dev(uint64_t h, uint64_t off, uint64_t n, const uint8_t x[3
       return;
     }
     ArenaScope scope;
-    uint64_t np = (n + HORNER_CHUNK - 1) / HORNER_CHUNK;
-    Fr* partial = g_arena.alloc(np);
-    Fr* tab = g_arena.alloc(41);
-    Fr* dx = tab + 40;
-    CUDA_CHECK(cudaMemcpyAsync(dx, x, 32, cudaMemcpyHostToDevice, c.stream));
-    fr_to_mont_kernel<<<1, 32, 0, c.stream>>>(dx, 1, dx);
-    CUDA_CHECK_LAUNCH();
-    Fr xm;
-    CUDA_CHECK(cudaMemcpyAsync(&xm, dx, 32, cudaMemcpyDeviceToHost, c.stream));
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
-    horner_pow_table_kernel<<<1, 32, 0, c.stream>>>(xm, tab);
-    CUDA_CHECK_LAUNCH();
-    horner_partial_kernel<<<GRID_1D(np)>>>(d->buf.as<Fr>() + off, n, xm, partial);
-    CUDA_CHECK_LAUNCH();
-    horner_combine_kernel<<<1, 256, 0, c.stream>>>(partial, np, tab, dx);
-    CUDA_CHECK_LAUNCH();
-    c.launches += 4;
-    CUDA_CHECK(cudaMemcpyAsync(out, dx, 32, cudaMemcpyDeviceToHost, c.stream));
+    Fr* res = g_arena.alloc(1);
+    c.launches += poly_eval_dev_impl(c, d->buf.as<Fr>() + off, n, x, res);
+    CUDA_CHECK(cudaMemcpyAsync(out, res, 32, cudaMemcpyDeviceToHost, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
   });
 }
