@@ -180,8 +180,12 @@ const Fr* pow2_table(Context& c, const FrBytes& x, bool inverted, int* launches)
   auto it = g_pow2_cache.find(key);
   if (it != g_pow2_cache.end()) return it->second.as<Fr>();
   if (g_pow2_cache.size() >= 512) {  // per-proof challenges (zeta, ...) would otherwise accumulate
+    // two generations: tables handed out earlier in the current call stay valid until the next purge
+    static std::vector<DevBuf> graveyard;
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
-    for (auto& kv : g_pow2_cache) kv.second.release();
+    for (auto& b : graveyard) b.release();
+    graveyard.clear();
+    for (auto& kv : g_pow2_cache) graveyard.push_back(kv.second);
     g_pow2_cache.clear();
   }
   DevBuf& buf = g_pow2_cache[key];
