@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-diag-suppress", "128",
     "-I", os.path.join(ROOT, "include"),
-]
+] + os.environ.get("ZKP_B200_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

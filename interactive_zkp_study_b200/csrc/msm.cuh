@@ -208,6 +208,15 @@ static __global__ void msm_scatter_kernel(const uint32_t* __restrict__ codes, ui
 // structured inputs: a few huge buckets).  One thread per task; buckets with several tasks are
 // folded afterwards.
 static constexpr uint32_t MSM_TASK_LEN = 64;
+#ifndef MSM_ACC_MIN_BLOCKS
+#define MSM_ACC_MIN_BLOCKS 4  // resident 128-thread blocks per SM the G1 accumulate kernel is compiled for
+#endif
+// 32-byte coordinates (G1): 104 registers, 4 blocks/SM (5 or 6 blocks measured no faster: the kernel is bound by the IMAD pipe, not by latency); 64-byte coordinates (G2)
+// need ~230 registers and stay at 2 blocks per SM.
+template <class F>
+struct AccMinBlocks {
+  static constexpr int value = sizeof(F) == 32 ? MSM_ACC_MIN_BLOCKS : 2;
+};
 
 static __global__ void msm_task_count_kernel(const uint32_t* __restrict__ offsets, uint32_t nbuckets,
                                              uint32_t* __restrict__ ntasks) {
@@ -278,7 +287,7 @@ static __global__ void msm_task_emit_kernel(const uint32_t* __restrict__ offsets
 }
 
 template <class F>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<F>* __restrict__ pts,
+__global__ void __launch_bounds__(128, AccMinBlocks<F>::value) msm_accumulate_kernel(const Affine<F>* __restrict__ pts,
                                                               const uint32_t* __restrict__ sorted,
                                                               const uint4* __restrict__ tasks,
                                                               const uint32_t* __restrict__ ntasks_ptr,
