@@ -85,7 +85,7 @@ __device__ __forceinline__ void sts_elem(uint32_t* sm, uint32_t tile, uint32_t i
   for (int l = 0; l < 8; l++) sm[l * tile + idx] = x.v[l];
 }
 
-__global__ void __launch_bounds__(512) ntt_pass_kernel(NttPassArgs a) {
+__global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassArgs a) {
   extern __shared__ uint32_t sm[];
   const uint32_t log_tile = a.S + a.log_g;
   const uint32_t tile = 1u << log_tile;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPassArgs a) {
   const uint32_t n = 1u << a.log_n;
   const bool first = a.s0 == 0;
   const uint32_t tid = threadIdx.x;
-  const uint32_t nthreads = blockDim.x;  // tile / 2 (or 1 when tile == 1)
+  const uint32_t nthreads = blockDim.x;  // tile / 4 (or 1 for tiles of fewer than 4 elements)
 
   // ---- global index of local slot l
   // first pass : contiguous tile, l = g * 2^S + mid, global = blockIdx * tile + l
@@ -129,18 +129,50 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPassArgs a) {
   }
   __syncthreads();
 
-  // ---- S butterfly stages
-  for (uint32_t u = 1; u <= a.S; u++) {
-    const uint32_t h = 1u << (u - 1);  // half size in `mid` units
+  // ---- S butterfly stages, two at a time (radix 4 in registers): a thread owns the four elements whose
+  // `mid` differs in bits u-1 and u, runs stage u on the pairs (00,01),(10,11) and stage u+1 on the
+  // pairs (00,10),(01,11) without going back to shared memory.  Half the barriers and half the
+  // shared-memory traffic of one-stage-at-a-time, two independent butterflies per step, and the three
+  // twiddles of a quad (w1; w2; w2 * omega^(n/4)) are requested together before any arithmetic.
+  auto decode = [&](uint32_t t, uint32_t per_sub_log, uint32_t& idx, uint32_t& g) {
+    if (first) { g = t >> per_sub_log; idx = t & ((1u << per_sub_log) - 1); }
+    else { idx = t >> a.log_g; g = t & (G - 1); }
+  };
+  auto slot = [&](uint32_t mid, uint32_t g) -> uint32_t { return first ? ((g << a.S) + mid) : ((mid << a.log_g) + g); };
+  uint32_t u = 1;
+  for (; u + 1 <= a.S; u += 2) {
+    const uint32_t h = 1u << (u - 1);
+    const uint32_t s = a.s0 + u;  // global index of the first of the two stages
+    for (uint32_t q = tid; q < tile / 4; q += nthreads) {
+      uint32_t qi, g;
+      decode(q, a.S - 2, qi, g);
+      uint32_t mid = ((qi >> (u - 1)) << (u + 1)) | (qi & (h - 1));
+      uint32_t imod = first ? (mid & (h - 1)) : (((mid & (h - 1)) << a.s0) + lo_base + g);
+      uint32_t e1 = imod << (a.log_n - s);
+      uint32_t e2 = imod << (a.log_n - s - 1);
+      uint32_t l00 = slot(mid, g), l01 = slot(mid + h, g), l10 = slot(mid + 2 * h, g), l11 = slot(mid + 3 * h, g);
+      Fr w1 = a.tw[e1], w2a = a.tw[e2], w2b = a.tw[e2 + (n >> 2)];
+      Fr x00 = lds_elem(sm, tile, l00), x01 = lds_elem(sm, tile, l01);
+      Fr x10 = lds_elem(sm, tile, l10), x11 = lds_elem(sm, tile, l11);
+      if (e1) { x01 = x01 * w1; x11 = x11 * w1; }
+      Fr a0 = x00 + x01, a1 = x00 - x01, b0 = x10 + x11, b1 = x10 - x11;
+      if (e2) b0 = b0 * w2a;
+      b1 = b1 * w2b;
+      sts_elem(sm, tile, l00, a0 + b0);
+      sts_elem(sm, tile, l10, a0 - b0);
+      sts_elem(sm, tile, l01, a1 + b1);
+      sts_elem(sm, tile, l11, a1 - b1);
+    }
+    __syncthreads();
+  }
+  if (u <= a.S) {  // odd stage count: one plain radix-2 stage
+    const uint32_t h = 1u << (u - 1);
+    const uint32_t s = a.s0 + u;
     for (uint32_t t = tid; t < tile / 2; t += nthreads) {
       uint32_t bf, g;
-      if (first) { g = t >> (a.S - 1); bf = t & ((1u << (a.S - 1)) - 1); }
-      else { bf = t >> a.log_g; g = t & (G - 1); }
+      decode(t, a.S - 1, bf, g);
       uint32_t mid = ((bf >> (u - 1)) << u) | (bf & (h - 1));
-      uint32_t l0 = first ? ((g << a.S) + mid) : ((mid << a.log_g) + g);
-      uint32_t l1 = first ? (l0 + h) : (l0 + (h << a.log_g));
-      // global stage s = s0 + u, half m = 2^(s-1); exponent = (i mod m) * n / (2m)
-      uint32_t s = a.s0 + u;
+      uint32_t l0 = slot(mid, g), l1 = slot(mid + h, g);
       uint32_t imod = first ? (mid & (h - 1)) : (((mid & (h - 1)) << a.s0) + lo_base + g);
       uint32_t e = imod << (a.log_n - s);
       Fr x0 = lds_elem(sm, tile, l0);
@@ -282,7 +314,7 @@ int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes&
   a.bitrev_in = 1;
   {
     uint32_t tile = 1u << (a.S + a.log_g);
-    uint32_t threads = tile >= 2 ? tile / 2 : 1;
+    uint32_t threads = tile >= 4 ? tile / 4 : 1;
     ntt_pass_kernel<<<n / tile, threads, tile * 32, c.stream>>>(a);
     CUDA_CHECK_LAUNCH();
     launches++;
@@ -301,7 +333,7 @@ int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes&
     if (a.log_g > a.s0) a.log_g = a.s0;
     if (done + S == log_n) a.dst = data;  // the last pass lands in the caller's buffer (no extra copy)
     uint32_t tile = 1u << (a.S + a.log_g);
-    ntt_pass_kernel<<<n / tile, tile / 2, tile * 32, c.stream>>>(a);
+    ntt_pass_kernel<<<n / tile, tile / 4, tile * 32, c.stream>>>(a);
     CUDA_CHECK_LAUNCH();
     launches++;
     done += S;
