@@ -43,6 +43,7 @@ int zkp_init(int device);
 int zkp_shutdown(void);
 const char* zkp_last_error(void);
 int zkp_device_info(char* name, int name_cap, int* sm_count, int* cc_major, int* cc_minor, int* sm_clock_khz);
+int zkp_device_mem_info(uint64_t* free_bytes, uint64_t* total_bytes);
 /* number of kernels this library has launched since zkp_init (bench.py "gpu_launches") */
 uint64_t zkp_launch_count(void);
 /* CUDA-event timer on the library's stream (the stream every kernel is launched on) */

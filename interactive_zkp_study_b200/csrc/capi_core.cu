@@ -270,6 +270,15 @@ int zkp_device_info(char* name, int name_cap, int* sm_count, int* cc_major, int*
   });
 }
 
+int zkp_device_mem_info(uint64_t* free_bytes, uint64_t* total_bytes) {
+  return guarded([&](Context&) {
+    size_t f = 0, t = 0;
+    CUDA_CHECK(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+  });
+}
+
 uint64_t zkp_launch_count(void) { return g_ready ? g_ctx.launches : 0; }
 
 int zkp_timer_start(void) {

@@ -77,6 +77,12 @@ def device_info():
             "sm_clock_khz": khz.value}
 
 
+def device_mem_info():
+    f, t = ctypes.c_uint64(), ctypes.c_uint64()
+    check(_lib.lib().zkp_device_mem_info(ctypes.byref(f), ctypes.byref(t)))
+    return f.value, t.value
+
+
 def launch_count():
     return int(_lib.lib().zkp_launch_count())
 
