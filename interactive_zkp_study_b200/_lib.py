@@ -113,6 +113,14 @@ def load_library():
     with _lock:
         if _lib is not None:
             return _lib
+        if not os.path.exists(LIB_PATH) and os.environ.get("ZKP_B200_AUTOBUILD", "1") != "0":
+            # a fresh checkout: compile the CUDA sources in-tree (this is the build, not a fallback --
+            # without nvcc or without the sources it still fails loudly below)
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception as e:
+                raise ZkpB200Error("libzkp_b200.so is missing and building it failed: %s" % e) from e
         if not os.path.exists(LIB_PATH):
             raise ZkpB200Error(
                 "libzkp_b200.so not found at %s: build it with "
