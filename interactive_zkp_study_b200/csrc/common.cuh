@@ -73,7 +73,13 @@ extern int g_msm_profile_enabled;
 struct StageTrace {
   bool on, print;
   cudaStream_t st;
-  std::vector<std::pair<std::string, cudaEvent_t>> ev;
+  std::vector<std::pair<const char*, cudaEvent_t>> ev;
+  // events are created once and reused: creating/destroying ~20 events per MSM costs more than
+  // recording them, and the profile is taken inside bench.py's timed region
+  static std::vector<cudaEvent_t>& pool() {
+    static std::vector<cudaEvent_t> p;
+    return p;
+  }
   explicit StageTrace(cudaStream_t s) : st(s) {
     static const bool env = getenv("ZKP_B200_TRACE") && atoi(getenv("ZKP_B200_TRACE"));
     print = env;
@@ -82,8 +88,13 @@ struct StageTrace {
   }
   void mark(const char* name) {
     if (!on) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
+    std::vector<cudaEvent_t>& p = pool();
+    if (ev.size() >= p.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      p.push_back(e);
+    }
+    cudaEvent_t e = p[ev.size()];
     cudaEventRecord(e, st);
     ev.emplace_back(name, e);
   }
@@ -96,13 +107,12 @@ struct StageTrace {
       float ms = 0;
       cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
       prof.stages.emplace_back(ev[i].first, ms * 1e3f);
-      if (print) fprintf(stderr, "[zkp trace] %-18s %8.1f us\n", ev[i].first.c_str(), ms * 1e3);
+      if (print) fprintf(stderr, "[zkp trace] %-18s %8.1f us\n", ev[i].first, ms * 1e3);
     }
     float tot = 0;
     cudaEventElapsedTime(&tot, ev.front().second, ev.back().second);
     prof.total_us = tot * 1e3f;
     if (print) fprintf(stderr, "[zkp trace] %-18s %8.1f us\n", "TOTAL", tot * 1e3);
-    for (auto& kv : ev) cudaEventDestroy(kv.second);
   }
 };
 

@@ -211,11 +211,14 @@ static constexpr uint32_t MSM_TASK_LEN = 64;
 #ifndef MSM_ACC_MIN_BLOCKS
 #define MSM_ACC_MIN_BLOCKS 4  // resident 128-thread blocks per SM the G1 accumulate kernel is compiled for
 #endif
+#ifndef MSM_ACC_MIN_BLOCKS_G2
+#define MSM_ACC_MIN_BLOCKS_G2 2
+#endif
 // 32-byte coordinates (G1): 104 registers, 4 blocks/SM (5 or 6 blocks measured no faster: the kernel is bound by the IMAD pipe, not by latency); 64-byte coordinates (G2)
 // need ~230 registers and stay at 2 blocks per SM.
 template <class F>
 struct AccMinBlocks {
-  static constexpr int value = sizeof(F) == 32 ? MSM_ACC_MIN_BLOCKS : 2;
+  static constexpr int value = sizeof(F) == 32 ? MSM_ACC_MIN_BLOCKS : MSM_ACC_MIN_BLOCKS_G2;
 };
 
 static __global__ void msm_task_count_kernel(const uint32_t* __restrict__ offsets, uint32_t nbuckets,
