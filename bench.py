@@ -297,7 +297,7 @@ def run_ours(args):
         if step_resident(0) != want:
             raise SystemExit("PARITY FAILURE: 2^%d MSM != (sum k_i s_i) * G" % args.log_n)
 
-    if world > 1 and args.verify and n * world <= (1 << 22):
+    if world > 1 and args.verify and n * world <= (1 << 23):
         # sharded MSM == (sum over ALL ranks' ranges of k_i s_i) * G, checked on rank 0
         got = step_resident(0)
         if rank == 0:
