@@ -227,3 +227,42 @@ def test_prove_is_randomised_but_consistent(native):
     p1, p2 = prover.prove(None, *args), prover.prove(None, *args)
     assert _pt(p1.a_comm) != _pt(p2.a_comm)
     assert bn254.g1_is_on_curve(_pt(p1.W_zeta_comm)) and bn254.g1_is_on_curve(_pt(p2.W_zeta_omega_comm))
+
+
+def test_kzg_openings_verify_with_pairing(native, monkeypatch):
+    """create_witness / verify_opening (reference kzg.py:70-160; tests/plonk/test_crypto.py:201-301): the
+    opening proof is computed on the GPU; the two pairings of the check are verifier-side work and are
+    supplied here by the oracle's py_ecc restatement (in a deployment: the real py_ecc)."""
+    import os
+    import sys
+    from oracle import plonk_verifier
+    bn = plonk_verifier._pairing()
+    from interactive_zkp_study_b200.zkp.plonk import kzg, field
+    from interactive_zkp_study_b200.zkp.plonk.field import FR
+    from interactive_zkp_study_b200.zkp.plonk.polynomial import Polynomial
+    from interactive_zkp_study_b200.zkp.plonk.srs import SRS
+
+    def pairing(q, p):
+        q2 = (bn.FQ2([int(q[0].coeffs[0]), int(q[0].coeffs[1])]), bn.FQ2([int(q[1].coeffs[0]), int(q[1].coeffs[1])]))
+        p1 = None if p is None else (bn.FQ(int(p[0])), bn.FQ(int(p[1])))
+        return bn.pairing(q2, p1)
+
+    monkeypatch.setattr(kzg, "ec_pairing", pairing)
+    srs = SRS.generate(8, seed=1234)
+    p = Polynomial([FR(1), FR(2), FR(3), FR(0), FR(7)])
+    C = kzg.commit(p, srs)
+    z = FR(11)
+    y = p.evaluate(z)
+    assert int(y) == (1 + 2 * 11 + 3 * 121 + 7 * 11 ** 4) % R
+    pi = kzg.create_witness(p, z, srs)
+    assert kzg.verify_opening(C, pi, z, y, srs) is True
+    assert kzg.verify_opening(C, pi, z, y + FR(1), srs) is False        # wrong evaluation
+    assert kzg.verify_opening(C, pi, FR(12), y, srs) is False           # wrong point
+    other = kzg.commit(p + Polynomial([FR(1)]), srs)
+    assert kzg.verify_opening(other, pi, z, y, srs) is False            # wrong commitment
+    # constant polynomial: quotient is zero, the proof is the point at infinity
+    c = Polynomial([FR(5)])
+    assert kzg.create_witness(c, z, srs) is None
+    assert kzg.verify_opening(kzg.commit(c, srs), None, z, FR(5), srs) is True
+    with pytest.raises(NotImplementedError):
+        field.ec_pairing(srs.g2_powers[0], C)                             # no py_ecc in this image: loud, no fallback
