@@ -84,6 +84,12 @@ int zkp_g1_msm_dev(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t s
                    uint8_t out_xy[64], int* out_is_inf);
 int zkp_g2_msm_dev(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n,
                    uint8_t out_xy[128], int* out_is_inf);
+/* `count` independent MSMs on one table in one call: MSM k uses points [offsets[k], +lens[k]) and scalars
+ * [sc_offsets[k], +lens[k]) of handle scalars[k]; out_xy holds count x 64 bytes.  The MSMs alternate between
+ * two streams so the latency-bound tail of one overlaps the accumulation of the next (a prover issues its
+ * commitments in groups: kzg.commit x3 in round1.py:80-82, round3.py:178-180, x2 in round5.py:174-175). */
+int zkp_g1_msm_dev_batch(uint64_t table, uint32_t count, const uint64_t* scalars, const uint64_t* sc_offsets,
+                         const uint64_t* offsets, const uint64_t* lens, uint8_t* out_xy, int* out_is_inf);
 /* Shard form for the multi-GPU path: the un-normalised XYZZ partial sum of this rank's
  * point range, 4 coordinates x 32 B Montgomery for G1 (128 B); combine folds `count` partials
  * (gathered from all ranks) into the affine result. */

@@ -53,6 +53,7 @@ PROTOTYPES = {
     "zkp_g2_msm_table": (c_int, [u64, u64, vp, u64, vp, intp]),
     "zkp_g1_msm_dev": (c_int, [u64, u64, u64, u64, u64, vp, intp]),
     "zkp_g2_msm_dev": (c_int, [u64, u64, u64, u64, u64, vp, intp]),
+    "zkp_g1_msm_dev_batch": (c_int, [u64, u32, u64p, u64p, u64p, u64p, vp, intp]),
     "zkp_g1_msm_dev_partial": (c_int, [u64, u64, u64, u64, u64, vp]),
     "zkp_g1_combine_partials": (c_int, [vp, u32, vp, intp]),
     "zkp_msm_set_window_bits": (c_int, [c_int]),

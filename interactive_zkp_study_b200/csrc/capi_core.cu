@@ -224,6 +224,9 @@ int zkp_init(int device) {
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.stream2, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_ctx.ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_ctx.ev_join, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreate(&g_ev0));
     CUDA_CHECK(cudaEventCreate(&g_ev1));
     g_ready = true;

@@ -57,6 +57,8 @@ struct Context {
   int device = -1;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;                 // second lane of the batched-MSM pipeline
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::mutex mu;  // serialises entry points (Flask's dev server is threaded, ctypes drops the GIL)
   unsigned long long launches = 0;  // kernels launched by this library (bench.py "gpu_launches")
 };

@@ -111,11 +111,12 @@ struct GroupApi {
   static constexpr uint64_t FE_PER_PT = PT / 32;
   static constexpr HandleKind KIND = sizeof(F) == 32 ? HandleKind::G1Table : HandleKind::G2Table;
 
-  static MsmEngine<F>& engine() {
-    static MsmEngine<F> e;
+  // slot 0: the library stream; slot 1: the second lane used by the batched pipeline
+  static MsmEngine<F>& engine(int slot = 0) {
+    static MsmEngine<F> e[2];
     static const int env_compact = getenv("ZKP_B200_COMPACT_ACC") ? atoi(getenv("ZKP_B200_COMPACT_ACC")) : 0;
-    e.compact_accumulate = (g_compact_accumulate | env_compact) != 0;
-    return e;
+    e[slot].compact_accumulate = (g_compact_accumulate | env_compact) != 0;
+    return e[slot];
   }
   static DevBuf& scratch_pts() {
     static DevBuf b;
@@ -144,11 +145,56 @@ struct GroupApi {
   }
 
   // plain table: the sub-range is just a pointer offset; precomputed table: stride/offset indexing
-  static int run_on_table(Context& c, Resource* t, uint64_t offset, const uint32_t* dscalars, uint64_t n, bool partial) {
+  static int run_on_table(Context& c, Resource* t, uint64_t offset, const uint32_t* dscalars, uint64_t n, bool partial,
+                          int slot = 0) {
+    cudaStream_t st = slot ? c.stream2 : c.stream;
     if (t->pre_c)
-      return engine().run(t->buf.as<Affine<F>>(), dscalars, n, c.stream, partial, t->pre_c, (uint32_t)t->n,
-                          (uint32_t)offset);
-    return engine().run(t->buf.as<Affine<F>>() + offset, dscalars, n, c.stream, partial, g_force_window_bits);
+      return engine(slot).run(t->buf.as<Affine<F>>(), dscalars, n, st, partial, t->pre_c, (uint32_t)t->n,
+                              (uint32_t)offset);
+    return engine(slot).run(t->buf.as<Affine<F>>() + offset, dscalars, n, st, partial, g_force_window_bits);
+  }
+
+  // `count` independent MSMs on one table, alternating between two streams (each with its own
+  // workspace): the latency-bound tail of MSM k (bucket fold, reduction levels, inversion: a handful of
+  // warps) runs while the integer-bound accumulation of MSM k+1 fills the machine.  A prover issues its
+  // commitments in groups (PLONK rounds 1, 3, 5; Groth16 A and C), so this is its natural call shape.
+  static int msm_batch(uint64_t table, uint32_t count, const uint64_t* scalars, const uint64_t* sc_off,
+                       const uint64_t* offsets, const uint64_t* lens, uint8_t* out_xy, int* out_is_inf) {
+    return guarded([&](Context& c) {
+      Resource* t = need(table, KIND, "msm_batch");
+      if (count && (!scalars || !sc_off || !offsets || !lens || !out_xy)) throw InvalidArgument("msm_batch: null argument");
+      std::vector<Resource*> sv(count);
+      for (uint32_t k = 0; k < count; k++) {
+        sv[k] = need(scalars[k], HandleKind::Scalars, "msm_batch");
+        if (offsets[k] + lens[k] > t->n || sc_off[k] + lens[k] > sv[k]->n) throw InvalidArgument("msm_batch: range out of bounds");
+      }
+      if (!count) return;
+      static DevBuf res;
+      const size_t stride = PT + 16;
+      res.reserve((size_t)count * stride);
+      CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
+      CUDA_CHECK(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
+      for (uint32_t k = 0; k < count; k++) {
+        int slot = k & 1;
+        cudaStream_t st = slot ? c.stream2 : c.stream;
+        c.launches += run_on_table(c, t, offsets[k], sv[k]->buf.template as<uint32_t>() + 8 * sc_off[k], lens[k], false, slot);
+        MsmEngine<F>& e = engine(slot);
+        CUDA_CHECK(cudaMemcpyAsync(res.as<char>() + k * stride, e.result.p, PT, cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(res.as<char>() + k * stride + PT, e.flag.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
+      }
+      CUDA_CHECK(cudaEventRecord(c.ev_join, c.stream2));
+      CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
+      std::vector<uint8_t> host((size_t)count * stride);
+      CUDA_CHECK(cudaMemcpyAsync(host.data(), res.p, host.size(), cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      for (uint32_t k = 0; k < count; k++) {
+        int flag;
+        memcpy(&flag, host.data() + k * stride + PT, sizeof(int));
+        if (flag) memset(out_xy + (size_t)k * PT, 0, PT);
+        else memcpy(out_xy + (size_t)k * PT, host.data() + k * stride, PT);
+        if (out_is_inf) out_is_inf[k] = flag;
+      }
+    });
   }
 
   static int table_precompute(uint64_t table, int window_bits) {

@@ -45,6 +45,10 @@ int zkp_g1_fixed_base_mul_dev(const uint8_t base_xy[64], uint64_t scalars, uint6
   return Api::fixed_base_dev(base_xy, scalars, n, out_table);
 }
 
+int zkp_g1_msm_dev_batch(uint64_t table, uint32_t count, const uint64_t* scalars, const uint64_t* sc_offsets,
+                         const uint64_t* offsets, const uint64_t* lens, uint8_t* out_xy, int* out_is_inf) {
+  return Api::msm_batch(table, count, scalars, sc_offsets, offsets, lens, out_xy, out_is_inf);
+}
 int zkp_g1_table_precompute(uint64_t table, int window_bits) { return Api::table_precompute(table, window_bits); }
 
 // G1 or G2 table -> canonical affine points on the host

@@ -310,6 +310,19 @@ def g2_msm_dev(table, offset, scalars, sc_offset, n):
     return g2_from_bytes(bytes(out), bool(inf.value))
 
 
+def g1_msm_dev_batch(table, items):
+    """items: list of (scalars_handle, sc_offset, point_offset, n) -> list of points (pipelined on two streams)."""
+    k = len(items)
+    if k == 0:
+        return []
+    arr = lambda vals: (ctypes.c_uint64 * k)(*vals)
+    out = bytearray(64 * k)
+    inf = (ctypes.c_int * k)()
+    check(_lib.lib().zkp_g1_msm_dev_batch(table.handle, k, arr([it[0].handle for it in items]), arr([it[1] for it in items]),
+                                          arr([it[2] for it in items]), arr([it[3] for it in items]), buf(out), inf))
+    return [g1_from_bytes(bytes(out[64 * i:64 * i + 64]), bool(inf[i])) for i in range(k)]
+
+
 def g1_msm_dev_partial(table, offset, scalars, sc_offset, n):
     out = bytearray(128)
     check(_lib.lib().zkp_g1_msm_dev_partial(table.handle, offset, scalars.handle, sc_offset, n, buf(out)))

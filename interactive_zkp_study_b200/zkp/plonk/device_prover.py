@@ -46,6 +46,11 @@ def _commit(key, h, off, length):
     return native.g1_msm_dev(key.srs_table, 0, h, off, length)
 
 
+def _commit_many(key, items):
+    """Several commitments against the SRS in one pipelined call: items = [(handle, offset, length)]."""
+    return native.g1_msm_dev_batch(key.srs_table, [(h, off, 0, length) for h, off, length in items])
+
+
 def preprocess(n, selector_evals, sigma_evals, srs_table, srs_size):
     """selector_evals: 5 handles (q_l, q_r, q_o, q_m, q_c evaluations on H, n each); sigma_evals: 3
     handles with the evaluations of S_sigma1..3 (permutation.py:44-86).  Mirrors
@@ -102,8 +107,8 @@ def prove(key, a_vals, b_vals, c_vals, blinds=None, keep=False):
         native.ntt_dev(h, 0, log_n, w, inverse=True)
         _blind(h, n, blinds[2 * i:2 * i + 2])
         wires[name] = h
-    for name in "abc":
-        setattr(proof, name + "_comm", g1_from_ints(_commit(key, wires[name], 0, n + 2)))
+    for name, pt in zip("abc", _commit_many(key, [(wires[k], 0, n + 2) for k in "abc"])):
+        setattr(proof, name + "_comm", g1_from_ints(pt))
     for name in "abc":
         tr.append_point(name.encode() + b"_comm", getattr(proof, name + "_comm"))
     # ---- round 2
@@ -143,9 +148,8 @@ def prove(key, a_vals, b_vals, c_vals, blinds=None, keep=False):
             "제약 다항식이 Z_H(x)로 나누어 떨어지지 않습니다. "
             "회로 또는 witness에 오류가 있습니다."
         )
-    proof.t_lo_comm = g1_from_ints(_commit(key, t, 0, n))
-    proof.t_mid_comm = g1_from_ints(_commit(key, t, n, n))
-    proof.t_hi_comm = g1_from_ints(_commit(key, t, 2 * n, n + 6))
+    t_pts = _commit_many(key, [(t, 0, n), (t, n, n), (t, 2 * n, n + 6)])
+    proof.t_lo_comm, proof.t_mid_comm, proof.t_hi_comm = (g1_from_ints(p) for p in t_pts)
     for part in ("t_lo", "t_mid", "t_hi"):
         tr.append_point(part.encode() + b"_comm", getattr(proof, part + "_comm"))
     # ---- round 4
@@ -190,8 +194,8 @@ def prove(key, a_vals, b_vals, c_vals, blinds=None, keep=False):
     native.div_linear_dev(P, 0, n + 6, zeta, W, 0)
     Ww = native.scalars_alloc(n + 2)
     native.div_linear_dev(z, 0, n + 3, zeta * w % R, Ww, 0)
-    proof.W_zeta_comm = g1_from_ints(_commit(key, W, 0, n + 5))
-    proof.W_zeta_omega_comm = g1_from_ints(_commit(key, Ww, 0, n + 2))
+    w_pts = _commit_many(key, [(W, 0, n + 5), (Ww, 0, n + 2)])
+    proof.W_zeta_comm, proof.W_zeta_omega_comm = (g1_from_ints(p) for p in w_pts)
     state = {"a": wires["a"], "b": wires["b"], "c": wires["c"], "z": z, "t": t, "r": r, "W": W, "Ww": Ww, "P": P,
              "challenges": {"beta": beta, "gamma": gamma, "alpha": alpha, "zeta": zeta, "v": v}}
     if keep:

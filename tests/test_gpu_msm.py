@@ -199,3 +199,22 @@ def test_precomputed_full_size_known_dlog(native):
     half = n // 2
     want_half = bn254.g1_mul(bn254.G1, sum(a * b for a, b in zip(k[:half], s[half:])) % R)
     assert native.g1_msm_dev(table, half, k_h, 0, half) == want_half
+
+
+def test_batched_msm_matches_individual_calls(native):
+    """zkp_g1_msm_dev_batch (two-stream pipeline) == the same MSMs issued one by one, for plain and
+    window-precomputed tables, mixed sizes, offsets, an empty MSM and an all-zero scalar vector."""
+    rng = random.Random(808)
+    n = 700
+    pts = _points_g1(rng, n)
+    table = native.g1_table_load(native.g1_vec_bytes(pts), n)
+    vecs = [[rng.randrange(R) for _ in range(n)] for _ in range(3)] + [[0] * n]
+    hs = [native.scalars_load(native.fr_vec_bytes(v), n) for v in vecs]
+    items = [(hs[0], 0, 0, n), (hs[1], 5, 100, 300), (hs[2], 0, 699, 1), (hs[3], 0, 0, n), (hs[0], 10, 20, 0),
+             (hs[1], 0, 0, 650), (hs[2], 100, 0, 600)]
+    want = [bn254.g1_msm(pts[off:off + m], vecs[hs.index(h)][so:so + m]) for h, so, off, m in items]
+    assert native.g1_msm_dev_batch(table, items) == want
+    native.table_precompute(table, 7)
+    assert native.g1_msm_dev_batch(table, items) == want
+    assert native.g1_msm_dev_batch(table, []) == []
+    assert native.g1_msm_dev(table, 0, hs[0], 0, n) == want[0]          # single-call path still fine afterwards
