@@ -218,3 +218,23 @@ def test_batched_msm_matches_individual_calls(native):
     assert native.g1_msm_dev_batch(table, items) == want
     assert native.g1_msm_dev_batch(table, []) == []
     assert native.g1_msm_dev(table, 0, hs[0], 0, n) == want[0]          # single-call path still fine afterwards
+
+
+@pytest.mark.parametrize("precompute", [0, 11])
+def test_g2_msm_known_dlog_2_14(native, precompute):
+    """G2 at 2^14 points (Q_i = s_i * G2 generated on the device): result == (sum k_i s_i) * G2."""
+    n = 1 << 14
+    s_h = native.scalars_generate(0x5EED0003, n)
+    k_h = native.scalars_generate(0x5EED0001, n)
+    table = native.g2_fixed_base_mul_dev(native.g2_bytes(bn254.G2), s_h, n)
+    s = synthetic.scalars(0x5EED0003, n)
+    k = synthetic.scalars(0x5EED0001, n)
+    for i in (0, 4097, n - 1):
+        assert native.g2_from_bytes(native.table_download(table, i, 1)) == bn254.g2_mul(bn254.G2, s[i])
+    if precompute:
+        native.table_precompute(table, precompute)
+    want = bn254.g2_mul(bn254.G2, sum(a * b for a, b in zip(k, s)) % R)
+    assert native.g2_msm_dev(table, 0, k_h, 0, n) == want
+    half = n // 2
+    want_half = bn254.g2_mul(bn254.G2, sum(a * b for a, b in zip(k[:half], s[half:])) % R)
+    assert native.g2_msm_dev(table, half, k_h, 0, half) == want_half

@@ -64,3 +64,31 @@ def test_ntt_large_horner_and_round_trip(native, log_n):
     k = rng.randrange(n)
     assert int.from_bytes(cev[32 * k:32 * k + 32], "little") == ref_path.poly_eval(vals, 5 * pow(w, k, R) % R)
     assert native.fr_ntt(cev, log_n, w, True, 5) == data
+
+
+@pytest.mark.parametrize("log_n", [13, 15, 16, 18, 19, 21, 22, 23, 24])
+def test_ntt_every_pass_shape_device_resident(native, log_n):
+    """Every decomposition of log_n into shared-memory passes (10 + up to two passes of <= 7 stages),
+    on device-resident data: NTT output element k == p(w^k) by the (oracle-checked) device Horner, the
+    coset variant == p(5 w^k), and inverse(forward(x)) == x bit for bit."""
+    n = 1 << log_n
+    w = ref_path.get_root_of_unity(n)
+    h = native.scalars_generate(0x5EED0004 + log_n, n)
+    orig = native.scalars_alloc(n)
+    native.scalars_copy(orig, 0, h, 0, n)
+    native.ntt_dev(h, 0, log_n, w)
+    rng = random.Random(log_n)
+    for k in [0, 1, n // 2, n - 1, rng.randrange(n), rng.randrange(n)]:
+        got = int.from_bytes(native.scalars_download(h, k, 1), "little")
+        assert got == native.fr_poly_eval_dev(orig, 0, n, pow(w, k, R)), (log_n, k)
+    native.ntt_dev(h, 0, log_n, w, inverse=True)
+    diff = native.scalars_alloc(n)
+    native.vec_op_dev(1, diff, 0, h, 0, orig, 0, n)
+    assert native.scalars_is_zero(diff, 0, n)
+    native.ntt_dev(h, 0, log_n, w, coset_shift=5)
+    k = rng.randrange(n)
+    assert int.from_bytes(native.scalars_download(h, k, 1), "little") == \
+        native.fr_poly_eval_dev(orig, 0, n, 5 * pow(w, k, R) % R)
+    native.ntt_dev(h, 0, log_n, w, inverse=True, coset_shift=5)
+    native.vec_op_dev(1, diff, 0, h, 0, orig, 0, n)
+    assert native.scalars_is_zero(diff, 0, n)
