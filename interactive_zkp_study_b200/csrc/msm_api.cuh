@@ -6,8 +6,7 @@
 
 namespace zkp {
 
-extern int g_force_window_bits;     // defined in msm_g1.cu
-extern int g_compact_accumulate;    // experiment switch: out-of-line products in the accumulate kernel
+extern int g_force_window_bits;  // defined in msm_g1.cu
 
 // out[i] = scalars[i] * base: MSB-first double-and-add in XYZZ with mixed additions, one thread per
 // scalar, then one inversion per point.  Replaces the n sequential Python scalar-muls of
@@ -114,8 +113,6 @@ struct GroupApi {
   // slot 0: the library stream; slot 1: the second lane used by the batched pipeline
   static MsmEngine<F>& engine(int slot = 0) {
     static MsmEngine<F> e[2];
-    static const int env_compact = getenv("ZKP_B200_COMPACT_ACC") ? atoi(getenv("ZKP_B200_COMPACT_ACC")) : 0;
-    e[slot].compact_accumulate = (g_compact_accumulate | env_compact) != 0;
     return e[slot];
   }
   static DevBuf& scratch_pts() {

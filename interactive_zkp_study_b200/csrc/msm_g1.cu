@@ -3,7 +3,6 @@
 
 namespace zkp {
 int g_force_window_bits = 0;
-int g_compact_accumulate = 0;
 }
 using namespace zkp;
 using Api = GroupApi<Fp>;

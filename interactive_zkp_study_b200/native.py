@@ -12,8 +12,6 @@ from ._lib import ZkpB200Error, NotDivisibleError, buf, check  # noqa: F401
 R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 P_MOD = 21888242871839275222246405745257275088696311157297823662689037894645226208583
 
-_ZERO32 = bytes(32)
-
 
 # ------------------------------------------------------------------ encoders / decoders
 def fe_bytes(x):
