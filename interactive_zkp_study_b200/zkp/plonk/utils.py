@@ -1,67 +1,65 @@
-"""Drop-in for /root/reference/zkp/plonk/utils.py (coset FFTs :145-205 on the GPU; the scalar
-helpers :25-116 keep their formulas)."""
+"""Drop-in for /root/reference/zkp/plonk/utils.py: same callables, same values.
+
+The vector work (coset transforms :145-205, the public-input interpolation :84-116) runs on the GPU;
+the closed-form scalar helpers (:25-81, :119-142, :208-246) are single field expressions evaluated on
+the host, as in the reference.
+"""
 from .field import FR
 from .polynomial import Polynomial, fft, ifft, _ntt  # noqa: F401
 
+DEFAULT_COSET_SHIFT = 5  # the reference's conventional generator (utils.py:166-167)
+
+
+def _fr(x):
+    return x if isinstance(x, FR) else FR(x)
+
 
 def vanishing_poly_eval(n, zeta):
+    """Z_H(zeta) = zeta^n - 1."""
     return zeta ** n - FR(1)
 
 
 def lagrange_basis_eval(i, n, omega, zeta):
-    if not isinstance(zeta, FR):
-        zeta = FR(zeta)
-    omega_i = omega ** i
-    zh_zeta = vanishing_poly_eval(n, zeta)
-    denominator = zeta - omega_i
-    if denominator == FR(0):
+    """L_i(zeta) = w^i (zeta^n - 1) / (n (zeta - w^i)); 1 when zeta is the i-th domain point."""
+    zeta = _fr(zeta)
+    w_i = omega ** i
+    gap = zeta - w_i
+    if gap == FR(0):
         return FR(1)
-    n_inv = FR(1) / FR(n)
-    return n_inv * zh_zeta * omega_i / denominator
+    return (FR(1) / FR(n)) * vanishing_poly_eval(n, zeta) * w_i / gap
 
 
 def public_input_polynomial(pub_inputs, n, omega):
+    """PI(x): the polynomial whose first len(pub_inputs) evaluations on H are the public inputs and the
+    rest zero -- one device iNTT."""
     if not pub_inputs:
         return Polynomial.zero()
-    evals = [FR(0)] * n
-    for i, val in enumerate(pub_inputs):
-        evals[i] = val if isinstance(val, FR) else FR(val)
-    return Polynomial.from_evaluations(evals, omega)
+    values = [_fr(v) for v in pub_inputs]
+    return Polynomial.from_evaluations(values + [FR(0)] * (n - len(values)), omega)
 
 
 def public_input_poly_eval(pub_inputs, n, omega, zeta):
-    result = FR(0)
-    for i, val in enumerate(pub_inputs):
-        if not isinstance(val, FR):
-            val = FR(val)
-        result = result + val * lagrange_basis_eval(i, n, omega, zeta)
-    return result
+    """PI(zeta) = sum_i w_i L_i(zeta) without building the polynomial."""
+    total = FR(0)
+    for i, value in enumerate(pub_inputs):
+        total = total + _fr(value) * lagrange_basis_eval(i, n, omega, zeta)
+    return total
 
 
 def coset_fft(coeffs, omega, k=None):
-    """Evaluate on the coset k*H: c_i <- c_i k^i fused into the transform's first pass."""
-    if k is None:
-        k = FR(5)
-    return _ntt(coeffs, omega, False, shift=k)
+    """Evaluations on the coset k*H: the scaling c_i <- c_i k^i is fused into the transform's first pass."""
+    return _ntt(coeffs, omega, False, shift=FR(DEFAULT_COSET_SHIFT) if k is None else k)
 
 
 def coset_ifft(evals, omega, k=None):
     """Inverse of coset_fft: inverse transform with c_i <- c_i k^-i fused into its last pass."""
-    if k is None:
-        k = FR(5)
-    return _ntt(evals, omega, True, shift=k)
-
-
-def pad_to_power_of_2(lst, fill=None):
-    if fill is None:
-        fill = FR(0)
-    return list(lst) + [fill] * (next_power_of_2(len(lst)) - len(lst))
+    return _ntt(evals, omega, True, shift=FR(DEFAULT_COSET_SHIFT) if k is None else k)
 
 
 def next_power_of_2(n):
-    if n <= 1:
-        return 1
-    p = 1
-    while p < n:
-        p <<= 1
-    return p
+    return 1 if n <= 1 else 1 << (n - 1).bit_length()
+
+
+def pad_to_power_of_2(lst, fill=None):
+    filler = FR(0) if fill is None else fill
+    return list(lst) + [filler] * (next_power_of_2(len(lst)) - len(lst))

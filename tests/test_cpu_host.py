@@ -126,3 +126,32 @@ def test_sharded_msm_partition_and_combine_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert ok is True
+
+
+def test_plonk_scalar_helpers_match_reference_formulas():
+    """utils.py scalar helpers (reference zkp/plonk/utils.py:25-81,208-246): closed forms on the host."""
+    from interactive_zkp_study_b200.zkp.plonk import utils
+    from interactive_zkp_study_b200.zkp.plonk.field import get_root_of_unity
+    from oracle import ref_path
+    R = curve_order
+    assert [utils.next_power_of_2(n) for n in (0, 1, 2, 3, 4, 5, 8, 9, 1000)] == [1, 1, 2, 4, 4, 8, 8, 16, 1024]
+    assert utils.pad_to_power_of_2([FR(1), FR(2), FR(3)]) == [FR(1), FR(2), FR(3), FR(0)]
+    assert utils.pad_to_power_of_2([1, 2, 3, 4, 5], fill=7) == [1, 2, 3, 4, 5, 7, 7, 7]
+    n = 8
+    w = get_root_of_unity(n)
+    zeta = FR(123456789)
+    assert int(utils.vanishing_poly_eval(n, zeta)) == (pow(123456789, n, R) - 1) % R
+    dom = ref_path.get_roots_of_unity(n)
+    for i in range(n):
+        # L_i(zeta) by direct Lagrange product
+        num = den = 1
+        for j in range(n):
+            if j != i:
+                num = num * (123456789 - dom[j]) % R
+                den = den * (dom[i] - dom[j]) % R
+        assert int(utils.lagrange_basis_eval(i, n, w, zeta)) == num * pow(den, -1, R) % R
+        assert utils.lagrange_basis_eval(i, n, w, FR(dom[i])) == FR(1)
+    pub = [FR(5), FR(7)]
+    want = sum(int(v) * int(utils.lagrange_basis_eval(i, n, w, zeta)) for i, v in enumerate(pub)) % R
+    assert int(utils.public_input_poly_eval(pub, n, w, zeta)) == want
+    assert utils.public_input_polynomial([], n, w).is_zero()
