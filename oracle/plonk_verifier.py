@@ -5,21 +5,17 @@ produced on the GPU at sizes where no golden proof exists.  Pinned in tests/test
 every reference-minted golden proof and rejects tampered ones (as the reference's test_e2e.py does).
 """
 import hashlib
-import os
-import sys
 
 from . import bn254
 
 R = bn254.R
 K1, K2 = 2, 3
 
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
-
 
 def _pairing():
-    if _SHIM not in sys.path:
-        sys.path.insert(0, _SHIM)
-    from py_ecc import bn128  # the oracle's shim (see oracle/shim/py_ecc/__init__.py)
+    """The oracle's py_ecc restatement, imported under its own package path: it is never put on
+    sys.path as `py_ecc`, so the product's `import py_ecc` probe (compat.py) cannot pick it up."""
+    from .shim.py_ecc import bn128
     return bn128
 
 

@@ -56,3 +56,18 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
                 assert "oracle." not in text.replace("oracle/", ""), os.path.join(dirpath, f)
+
+
+def test_oracle_shim_never_masquerades_as_py_ecc():
+    """The oracle's py_ecc restatement is importable only as oracle.shim.py_ecc; loading it must not
+    make `import py_ecc` succeed for the product (compat.py probes for the real package)."""
+    import sys
+    from oracle import plonk_verifier
+    bn = plonk_verifier._pairing()
+    assert bn.__name__ == "oracle.shim.py_ecc.bn128"
+    import importlib
+    if "py_ecc" not in sys.modules:          # nothing named py_ecc is importable in this image
+        with pytest.raises(ImportError):
+            importlib.import_module("py_ecc")
+    from interactive_zkp_study_b200 import compat
+    assert compat.HAVE_PY_ECC is False or "site-packages" in sys.modules["py_ecc"].__file__
