@@ -11,14 +11,22 @@
 //   2. sort       : counting sort of (bucket, point index | sign) pairs: exclusive scan of the
 //                   histogram + atomic-cursor scatter.  Order inside a bucket is irrelevant
 //                   (the group is commutative and the final affine point is unique).
-//   3. accumulate : one thread per bucket walks its run of point indices and sums the points
-//                   with XYZZ mixed additions (negating y for negative digits).
-//   4. reduce     : per window sum_b (b+1)*B_b by a radix-L weighted-sum recursion
-//                   (V = sum_i i*A_i + sum_i E_i is preserved level to level), then Horner over
-//                   the windows, one inversion, out of Montgomery form.
+//   3. accumulate : each bucket's run of point indices is cut into tasks of <= 64 entries, the tasks
+//                   are counting-sorted by length so a warp walks runs of equal length, one thread
+//                   per task sums its points with XYZZ mixed additions (negating y for negative
+//                   digits); buckets with several tasks are folded (block-per-bucket if very many).
+//   4. reduce     : per window sum_b (b+1)*B_b by a weighted-sum recursion (V = sum_i i*A_i +
+//                   sum_i E_i is preserved level to level: radix 8 while wide, radix 2 on two warps
+//                   when narrow), then Horner over the windows, one binary-Euclid inversion, out of
+//                   Montgomery form.
+//
+// Static tables (SRS / CRS) can be window-precomputed: T[w][i] = 2^(c*w) * P_i.  Then every window's
+// digits weigh the same, all windows share ONE bucket set (stage 4 reduces a single window) and the
+// 254-step doubling chain of the Horner disappears; the digits kernel just maps (w, i) to entry
+// w*n + i of the big table.
 //
 // HBM layout: points AoS affine Montgomery (64 B G1 / 128 B G2, 16-byte aligned -> LDG.128),
-// scalars canonical 8xu32, codes/sorted W*n u32, buckets W*2^(c-1) XYZZ.
+// scalars canonical 8xu32, codes/sorted W*n u32, task records uint4, partials / buckets XYZZ.
 #pragma once
 #include "common.cuh"
 #include "ec.cuh"
