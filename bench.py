@@ -264,29 +264,21 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    gbuf = {}
+    exchange = None
     if world > 1:
-        import torch
-        gbuf = {"host": torch.empty(128, dtype=torch.uint8).pin_memory(),
-                "send": torch.empty(128, dtype=torch.uint8, device="cuda"),
-                "recv": torch.empty(128 * world, dtype=torch.uint8, device="cuda"),
-                "host_all": torch.empty(128 * world, dtype=torch.uint8).pin_memory()}
+        from interactive_zkp_study_b200 import sharded
+        exchange = sharded.PartialExchange()   # CUDA send/recv buffers of the one 128 B-per-rank gather
 
-    def gather_and_fold(partial):
-        """The one exchange step: 128 B per rank over NCCL (NVLink), folded on rank 0."""
-        gbuf["host"].copy_(torch.frombuffer(bytearray(partial), dtype=torch.uint8))
-        gbuf["send"].copy_(gbuf["host"], non_blocking=True)
-        dist.all_gather_into_tensor(gbuf["recv"], gbuf["send"])
-        if rank == 0:
-            gbuf["host_all"].copy_(gbuf["recv"])            # one D2H of world*128 bytes (synchronises)
-            return nat.g1_combine_partials(gbuf["host_all"].numpy().tobytes(), world)
-        return None
+    def sharded_step(k):
+        """Local Pippenger -> XYZZ partial written into the NCCL send buffer -> all-gather over NVLink ->
+        rank 0 folds straight out of the receive buffer (interactive_zkp_study_b200/sharded.py)."""
+        return sharded.g1_msm_sharded(exchange, table, k, n)
 
     def step_resident(i):
         k = k_h[i % n_vec]
         if world == 1:
             return nat.g1_msm_dev(table, 0, k, 0, n)
-        return gather_and_fold(nat.g1_msm_dev_partial(table, 0, k, 0, n))
+        return sharded_step(k)
 
     # ---- correctness of the exact workload before timing (size-independent check, SURVEY 8d)
     if rank == 0 and world == 1 and args.verify and args.log_n <= 22:
@@ -368,7 +360,7 @@ def run_ours(args):
         if world == 1:
             return nat.g1_msm_table(table, 0, pinned.addr, n)
         sc = nat.scalars_load(pinned.addr, n)          # H2D of this rank's scalar shard
-        r = gather_and_fold(nat.g1_msm_dev_partial(table, 0, sc, 0, n))
+        r = sharded_step(sc)
         sc.free()
         return r
 
@@ -460,7 +452,7 @@ def run_ours(args):
             "device": info["name"],
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / steps,
-                "h2d_bytes_per_step": 32 * n * world, "d2h_bytes_per_step": 64 + (128 * world if world > 1 else 0),
+                "h2d_bytes_per_step": 32 * n * world, "d2h_bytes_per_step": 64,
                 "path": "zkp_g1_msm_table: device-resident point table (static SRS), scalars from pinned host memory"},
         "gpu_launches": launches,
         "clocks": clocks,

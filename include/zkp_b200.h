@@ -92,7 +92,10 @@ int zkp_g1_msm_dev_batch(uint64_t table, uint32_t count, const uint64_t* scalars
                          const uint64_t* offsets, const uint64_t* lens, uint8_t* out_xy, int* out_is_inf);
 /* Shard form for the multi-GPU path: the un-normalised XYZZ partial sum of this rank's
  * point range, 4 coordinates x 32 B Montgomery for G1 (128 B); combine folds `count` partials
- * (gathered from all ranks) into the affine result. */
+ * (gathered from all ranks) into the affine result.  `out_xyzz` and `partials` may be host memory or
+ * device memory of this GPU (unified addressing), so the partial can be written straight into the
+ * send buffer of the NCCL gather and folded straight out of its receive buffer; both calls return
+ * after the library stream has drained. */
 int zkp_g1_msm_dev_partial(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n,
                            uint8_t out_xyzz[128]);
 int zkp_g1_combine_partials(const uint8_t* partials, uint32_t count, uint8_t out_xy[64], int* out_is_inf);

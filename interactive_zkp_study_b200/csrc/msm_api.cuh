@@ -268,7 +268,9 @@ struct GroupApi {
       MsmEngine<F>& e = engine();
       c.launches += run_on_table(c, t, offset, s->buf.as<uint32_t>() + 8 * sc_offset, n, partial);
       if (partial) {
-        CUDA_CHECK(cudaMemcpyAsync(out, e.result.template as<char>() + PT, sizeof(XYZZ<F>), cudaMemcpyDeviceToHost,
+        // cudaMemcpyDefault: `out` may be host memory or a device buffer of this GPU (e.g. the send
+        // buffer of the NCCL gather), resolved by unified addressing
+        CUDA_CHECK(cudaMemcpyAsync(out, e.result.template as<char>() + PT, sizeof(XYZZ<F>), cudaMemcpyDefault,
                                    c.stream));
         CUDA_CHECK(cudaStreamSynchronize(c.stream));
       } else {
@@ -286,7 +288,7 @@ struct GroupApi {
       DevBuf& dp = scratch_pts();
       dp.reserve((size_t)(count ? count : 1) * sizeof(XYZZ<F>));
       if (count)
-        CUDA_CHECK(cudaMemcpyAsync(dp.p, partials, (size_t)count * sizeof(XYZZ<F>), cudaMemcpyHostToDevice, c.stream));
+        CUDA_CHECK(cudaMemcpyAsync(dp.p, partials, (size_t)count * sizeof(XYZZ<F>), cudaMemcpyDefault, c.stream));
       using FC = typename CompactOf<F>::type;
       combine_partials_kernel<FC><<<1, 32, 0, c.stream>>>(dp.as<XYZZ<FC>>(), count, e.result.template as<Affine<FC>>(),
                                                         e.flag.template as<int>());

@@ -321,7 +321,12 @@ def g1_msm_dev_batch(table, items):
     return [g1_from_bytes(bytes(out[64 * i:64 * i + 64]), bool(inf[i])) for i in range(k)]
 
 
-def g1_msm_dev_partial(table, offset, scalars, sc_offset, n):
+def g1_msm_dev_partial(table, offset, scalars, sc_offset, n, out_addr=None):
+    """XYZZ partial sum (128 B, Montgomery) of one rank's point range.  With `out_addr` (a host or
+    device address, e.g. a torch tensor's data_ptr()) the partial is written there and None returned."""
+    if out_addr is not None:
+        check(_lib.lib().zkp_g1_msm_dev_partial(table.handle, offset, scalars.handle, sc_offset, n, buf(int(out_addr))))
+        return None
     out = bytearray(128)
     check(_lib.lib().zkp_g1_msm_dev_partial(table.handle, offset, scalars.handle, sc_offset, n, buf(out)))
     return bytes(out)

@@ -82,39 +82,78 @@ def _free_port():
     return port
 
 
+_R256 = 1 << 256
+
+
+def _encode_partial(pt, scale=1):
+    """Oracle-side encoder of the 128-byte shard partial (sharded.py wire format): XYZZ Montgomery,
+    un-normalised on purpose (zz = scale^2, zzz = scale^3) like a real GPU partial."""
+    from oracle import bn254
+    P = bn254.P
+    if pt is None:
+        return bytes(128)
+    zz, zzz = pow(scale, 2, P), pow(scale, 3, P)
+    coords = (pt[0] * zz % P, pt[1] * zzz % P, zz, zzz)
+    return b"".join((c * _R256 % P).to_bytes(32, "little") for c in coords)
+
+
+def _decode_partial(b):
+    from oracle import bn254
+    P = bn254.P
+    rinv = pow(_R256, -1, P)
+    x, y, zz, zzz = (int.from_bytes(b[32 * i:32 * i + 32], "little") * rinv % P for i in range(4))
+    if zz == 0:
+        return None
+    return (x * pow(zz, -1, P) % P, y * pow(zzz, -1, P) % P)
+
+
 def _gloo_worker(rank, world, port, q):
-    import torch
     import torch.distributed as dist
     from oracle import bn254, synthetic
+    from interactive_zkp_study_b200 import sharded
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    n = 24                                   # points per rank
-    # same partition bench.py uses: rank r owns global indices [r*n, (r+1)*n)
-    s = synthetic.scalars(0x5EED0002, n * world)[rank * n:(rank + 1) * n]
-    k = synthetic.scalars(0x5EED0001, n * world)[rank * n:(rank + 1) * n]
+    total = 49                               # odd on purpose: ranks own 25 and 24 points
+    start, count = sharded.shard_range(total, rank, world)
+    s = synthetic.scalars(0x5EED0002, total)[start:start + count]
+    k = synthetic.scalars(0x5EED0001, total)[start:start + count]
     pts = [bn254.g1_mul(bn254.G1, x) for x in s]
     part = bn254.g1_msm(pts, k)             # the per-rank partial sum (CPU stand-in for the GPU shard)
-    enc = (b"\x00" * 64) if part is None else part[0].to_bytes(32, "little") + part[1].to_bytes(32, "little")
-    t = torch.frombuffer(bytearray(enc), dtype=torch.uint8)
-    out = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(out, t)                  # the one exchange step of the sharded MSM
+    ex = sharded.PartialExchange()          # the product's exchange step, on the gloo backend
+    assert (ex.rank, ex.world, ex.on_device) == (rank, world, False)
+    ex.write_partial(_encode_partial(part, scale=7 + rank))
+    ex.all_gather()
+    blob = ex.gathered_bytes()
     if rank == 0:
         acc = None
-        for o in out:
-            b = bytes(o.numpy().tobytes())
-            p = None if b == bytes(64) else (int.from_bytes(b[:32], "little"), int.from_bytes(b[32:], "little"))
-            acc = bn254.g1_add(acc, p)
-        s_all = synthetic.scalars(0x5EED0002, n * world)
-        k_all = synthetic.scalars(0x5EED0001, n * world)
+        for r in range(world):
+            acc = bn254.g1_add(acc, _decode_partial(blob[128 * r:128 * r + 128]))
+        s_all = synthetic.scalars(0x5EED0002, total)
+        k_all = synthetic.scalars(0x5EED0001, total)
         want = bn254.g1_mul(bn254.G1, sum(a * b for a, b in zip(s_all, k_all)) % bn254.R)
         q.put(acc == want)
     dist.barrier()
     dist.destroy_process_group()
 
 
+def test_shard_range_tiles_the_index_space():
+    from interactive_zkp_study_b200.sharded import shard_range
+    for total in (0, 1, 7, 8, 49, 1 << 20, (1 << 26) + 3):
+        for world in (1, 2, 3, 4, 8):
+            nxt = 0
+            for r in range(world):
+                start, count = shard_range(total, r, world)
+                assert start == nxt and count in (total // world, total // world + 1)
+                nxt = start + count
+            assert nxt == total
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
+
+
 def test_sharded_msm_partition_and_combine_world2_gloo():
-    """N>1 path on CPU (gloo, world_size 2): contiguous point ranges, one gathered partial per rank,
-    fold on rank 0 == the unsharded MSM."""
+    """N>1 path on CPU (gloo, world_size 2): the product's shard_range + PartialExchange (the one
+    exchange step of the sharded MSM) with oracle-made partials in the 128-byte wire format; the fold
+    on rank 0 == the unsharded MSM."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -238,3 +238,50 @@ def test_g2_msm_known_dlog_2_14(native, precompute):
     half = n // 2
     want_half = bn254.g2_mul(bn254.G2, sum(a * b for a, b in zip(k[:half], s[half:])) % R)
     assert native.g2_msm_dev(table, half, k_h, 0, half) == want_half
+
+
+def test_partial_wire_format_and_device_pointer_exchange(native):
+    """The 128-byte shard partial decodes (x/zz, y/zzz out of Montgomery form) to the oracle's partial sum,
+    and the sharded-MSM entry point of the package (NCCL group of this one rank: partial written into
+    a CUDA send buffer, folded out of the CUDA receive buffer) returns the oracle's affine point."""
+    import os
+    import socket
+    import torch
+    import torch.distributed as dist
+    from interactive_zkp_study_b200 import sharded
+    rng = random.Random(77)
+    n = 200
+    pts = _points_g1(rng, n)
+    scalars = [rng.randrange(R) for _ in range(n)]
+    want = bn254.g1_msm(pts, scalars)
+    table = native.g1_table_load(native.g1_vec_bytes(pts), n)
+    sc = native.scalars_load(native.fr_vec_bytes(scalars), n)
+    raw = native.g1_msm_dev_partial(table, 0, sc, 0, n)
+    rinv = pow(1 << 256, -1, bn254.P)
+    x, y, zz, zzz = (int.from_bytes(raw[32 * i:32 * i + 32], "little") * rinv % bn254.P for i in range(4))
+    assert (x * pow(zz, -1, bn254.P) % bn254.P, y * pow(zzz, -1, bn254.P) % bn254.P) == want
+    assert pow(zz, 3, bn254.P) == pow(zzz, 2, bn254.P)
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    created = not dist.is_initialized()
+    if created:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.cuda.set_device(0)
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        ex = sharded.PartialExchange()
+        assert ex.on_device and ex.world == 1
+        assert sharded.g1_msm_sharded(ex, table, sc, n) == want
+        start, count = sharded.shard_range(n, 0, 1)
+        assert sharded.g1_msm_sharded(ex, table, sc, count // 2, offset=start, sc_offset=0) == bn254.g1_msm(pts[:100], scalars[:100])
+        # device-resident partials of two half ranges folded from a CUDA buffer
+        two = torch.zeros(256, dtype=torch.uint8, device="cuda")
+        native.g1_msm_dev_partial(table, 0, sc, 0, 100, out_addr=two.data_ptr())
+        native.g1_msm_dev_partial(table, 100, sc, 100, 100, out_addr=two.data_ptr() + 128)
+        assert native.g1_combine_partials(two.data_ptr(), 2) == want
+    finally:
+        if created:
+            dist.destroy_process_group()
