@@ -196,6 +196,27 @@ int zkp_fr_poly_mul(const uint8_t* a, uint64_t a_len, const uint8_t* b, uint64_t
 int zkp_fr_poly_divmod(const uint8_t* a, uint64_t a_len, const uint8_t* b, uint64_t b_len, uint8_t* q_out,
                        uint8_t* r_out);
 
+/* ---- QAP construction at scale over the reference's domain {1..k} ------------------
+ * The reference interpolates every wire's R1CS column through x = 1..k in floating point, scaled by
+ * the Vandermonde determinant (qap_creator_lcm.py:50-78 mk_singleton/lagrange_interp, :114-135
+ * r1cs_to_qap_times_lcm), and contracts the dense numWires x numGates result with the witness
+ * (poly_utils.py:52-59 _multiply_vec_matrix inside hxr :116-125).  By linearity R.Ax = interp(A.w):
+ * one sparse matrix-vector product and one exact interpolation per matrix.
+ * zkp_sparse_load: CSR matrix (row_ptr[rows+1], col_idx[nnz], values nnz x 32 B canonical) -> handle
+ * (release with zkp_free).  zkp_sparse_matvec_dev: out[row] = sum val * vec[col] on scalar handles.
+ * zkp_fr_ap_interpolate_dev: coefficients (k, degree < k) of the polynomial with p(j+1) = values[j],
+ * optionally times `scale` (the reference's determinant factor; NULL = 1).
+ * zkp_fr_ap_vanishing_dev: the k+1 coefficients of Z(x) = (x-1)(x-2)...(x-k) (qap_creator_lcm.py:128-135).
+ * zkp_fr_ap_lagrange_dev: the Lagrange basis of {1..k} evaluated at x (k values), for the CRS terms
+ * A_i(x), B_i(x), C_i(x) of setup.py:26-57 without the coefficient matrices. */
+int zkp_sparse_load(const uint32_t* row_ptr, const uint32_t* col_idx, const uint8_t* values, uint64_t rows, uint64_t cols,
+                    uint64_t nnz, uint64_t* handle);
+int zkp_sparse_matvec_dev(uint64_t matrix, uint64_t vec, uint64_t vec_off, uint64_t out, uint64_t out_off);
+int zkp_fr_ap_interpolate_dev(uint64_t values, uint64_t off, uint64_t k, const uint8_t* scale, uint64_t out,
+                              uint64_t out_off);
+int zkp_fr_ap_vanishing_dev(uint64_t k, uint64_t out, uint64_t out_off);
+int zkp_fr_ap_lagrange_dev(uint64_t k, const uint8_t x[32], uint64_t out, uint64_t out_off);
+
 /* ---- measurement helpers (bench.py) -----------------------------------------------------------
  * Per-stage CUDA-event profile of the most recent MSM (events recorded on the library stream).
  * zkp_msm_last_profile sums the stages whose name contains `stage` ("accumulate", "ws", "horner",

@@ -90,6 +90,11 @@ PROTOTYPES = {
     "zkp_plonk_perm_terms_dev": (c_int, [u64, u64, u64, u64, u64, u64, u64, vp, vp, vp, u64, u64]),
     "zkp_plonk_coset_setup_dev": (c_int, [u64, u32, vp, vp, vp, vp, u64, u64, u64]),
     "zkp_plonk_quotient_dev": (c_int, [u64p, u64, u32, u64, u64, u64, vp, vp, vp, u64]),
+    "zkp_sparse_load": (c_int, [vp, vp, vp, u64, u64, u64, u64p]),
+    "zkp_sparse_matvec_dev": (c_int, [u64, u64, u64, u64, u64]),
+    "zkp_fr_ap_interpolate_dev": (c_int, [u64, u64, u64, vp, u64, u64]),
+    "zkp_fr_ap_vanishing_dev": (c_int, [u64, u64, u64]),
+    "zkp_fr_ap_lagrange_dev": (c_int, [u64, vp, u64, u64]),
     "zkp_fr_poly_mul": (c_int, [vp, u64, vp, u64, vp]),
     "zkp_fr_poly_divmod": (c_int, [vp, u64, vp, u64, vp, vp]),
     "zkp_msm_profile": (c_int, [c_int]),

@@ -242,7 +242,10 @@ int zkp_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_ctx.mu);
   cudaSetDevice(g_ctx.device);
   cudaStreamSynchronize(g_ctx.stream);
-  for (auto& kv : g_registry.items) kv.second->buf.release();
+  for (auto& kv : g_registry.items) {
+    kv.second->buf.release();
+    for (DevBuf& b : kv.second->aux) b.release();
+  }
   g_registry.items.clear();
   return ZKP_OK;  // the context (stream, engines' workspaces) stays usable; nothing else to tear down
 }
@@ -304,6 +307,7 @@ int zkp_free(uint64_t handle) {
     if (it == registry().items.end()) throw BadHandle("zkp_free: unknown handle");
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
     it->second->buf.recycle();
+    for (DevBuf& b : it->second->aux) b.recycle();
     registry().items.erase(it);
   });
 }

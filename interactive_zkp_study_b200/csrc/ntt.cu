@@ -121,8 +121,9 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassArgs a) {
     uint64_t gi = global_of(l);
     Fr x;
     if (a.bitrev_in) {
-      uint32_t src_i = a.log_n ? (__brev((uint32_t)gi) >> (32 - a.log_n)) : 0;
-      x = a.src[src_i];
+      // batched transforms: the permutation acts on the index inside one transform (low log_n bits)
+      uint32_t src_i = a.log_n ? (__brev((uint32_t)gi & (n - 1)) >> (32 - a.log_n)) : 0;
+      x = a.src[(gi & ~(uint64_t)(n - 1)) | src_i];
       if (a.pre_pow2 && src_i) x = x * pow_from_table(a.pre_pow2, src_i);
     } else {
       x = a.src[gi];
@@ -193,11 +194,11 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassArgs a) {
     Fr x = lds_elem(sm, tile, l);
     if (last) {
       if (a.scale_n_inv) x = x * a.n_inv;
-      if (a.post_pow2 && gi) x = x * pow_from_table(a.post_pow2, (uint32_t)gi);
+      uint32_t li = (uint32_t)gi & (n - 1);
+      if (a.post_pow2 && li) x = x * pow_from_table(a.post_pow2, li);
     }
     a.dst[gi] = x;
   }
-  (void)n;
 }
 
 // ------------------------------------------------------------------ caches
@@ -284,10 +285,13 @@ static void host_n_inv_mont(uint32_t log_n, Fr* out) {
 }
 
 int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes& omega, bool inverse,
-               const FrBytes* coset_shift) {
+               const FrBytes* coset_shift, uint32_t log_batch) {
   if (log_n > FrParams::TWO_ADICITY) throw InvalidArgument("ntt: log_n exceeds the 2-adicity of Fr (28)");
+  if (log_n + log_batch > 31) throw InvalidArgument("ntt: batch * n must be < 2^32");
   int launches = 0;
-  const uint32_t n = 1u << log_n;
+  // 2^log_batch independent transforms of 2^log_n contiguous elements: the same passes over a longer
+  // array (tile indices simply run on into the next transform; twiddles depend on the position inside one)
+  const uint32_t n = 1u << (log_n + log_batch);
   const Fr* tw = twiddle_table(c, omega, inverse, log_n, &launches);
   const Fr* pre = nullptr;
   const Fr* post = nullptr;
@@ -309,8 +313,16 @@ int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes&
   a.dst = scratch;
   a.s0 = 0;
   a.S = S1;
-  a.log_g = log_n < (uint32_t)NTT_LOG_TILE ? 0 : 0;
+  // small batched transforms: several of them share one 1024-element tile
+  a.log_g = 0;
+  if (log_n < (uint32_t)NTT_LOG_TILE) {
+    a.log_g = (uint32_t)NTT_LOG_TILE - log_n;
+    if (a.log_g > log_batch) a.log_g = log_batch;
+  }
   a.bitrev_in = 1;
+  // a single-pass transform lives entirely inside one tile, which is read completely before it is
+  // written: the permuting gather can then run in place
+  if (S1 == log_n) a.dst = data;
   {
     uint32_t tile = 1u << (a.S + a.log_g);
     uint32_t threads = tile >= 4 ? tile / 4 : 1;
@@ -337,8 +349,6 @@ int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes&
     launches++;
     done += S;
   }
-  if (S1 == log_n)  // single pass: the bit-reversed gather could not be done in place
-    CUDA_CHECK(cudaMemcpyAsync(data, scratch, (size_t)n * sizeof(Fr), cudaMemcpyDeviceToDevice, c.stream));
   return launches;
 }
 

@@ -16,9 +16,10 @@ struct FrBytes {
 // Montgomery constants, so the form is preserved).
 //   forward:  out[k] = sum_j in[j] * omega^(jk), optionally pre-scaled in[j] *= shift^j
 //   inverse:  same with omega^-1, scaled by n^-1, optionally post-scaled out[j] *= shift^-j
-// `scratch` must hold n elements.  Returns the number of kernels launched.
+// `scratch` must hold as many elements as `data`.  Returns the number of kernels launched.
+// log_batch: transform 2^log_batch contiguous vectors of n elements each in the same launches.
 int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes& omega, bool inverse,
-               const FrBytes* coset_shift);
+               const FrBytes* coset_shift, uint32_t log_batch = 0);
 
 // x^(2^k), k < 32, in Montgomery form on the device (cached per x); `inverted`: of x^-1 instead.
 const Fr* pow2_table(Context& c, const FrBytes& x, bool inverted, int* launches);

@@ -1149,3 +1149,5 @@ int zkp_groth16_quotient(const uint8_t* a, const uint8_t* b, const uint8_t* cc, 
 }
 
 }  // extern "C"
+
+#include "qap.cuh"

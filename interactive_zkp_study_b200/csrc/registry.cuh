@@ -9,13 +9,16 @@
 
 namespace zkp {
 
-enum class HandleKind : int { G1Table = 1, G2Table = 2, Scalars = 3 };
+enum class HandleKind : int { G1Table = 1, G2Table = 2, Scalars = 3, Sparse = 4 };
 
 struct Resource {
   HandleKind kind;
   uint64_t n = 0;  // elements (points or scalars)
   int pre_c = 0;   // point tables: window width of the precomputed layout [w][i] (0 = plain)
   DevBuf buf;
+  // sparse matrices (CSR): n rows; buf = values (Montgomery), aux[0] = row_ptr, aux[1] = column indices
+  uint64_t cols = 0, nnz = 0;
+  DevBuf aux[2];
 };
 
 struct Registry {

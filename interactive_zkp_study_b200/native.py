@@ -471,3 +471,49 @@ def plonk_quotient_dev(evals12, n, ext, x, l1f, zh8, beta, gamma, alpha, t_out):
     arr = (ctypes.c_uint64 * 12)(*[h.handle for h in evals12])
     check(_lib.lib().zkp_plonk_quotient_dev(arr, n, ext, x.handle, l1f.handle, zh8.handle, buf(fe_bytes(beta)),
                                             buf(fe_bytes(gamma)), buf(fe_bytes(alpha)), t_out.handle))
+
+
+# ------------------------------------------------------------------ QAP over {1..k} at scale
+def sparse_load(row_ptr, col_idx, values, rows, cols):
+    """CSR matrix with Fr values -> device handle.  row_ptr: rows+1 offsets, col_idx: column of each
+    entry (sequences or numpy uint32 arrays), values: ints (or already 32 B/entry canonical bytes)."""
+    import numpy as np
+    rp = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+    ci = np.ascontiguousarray(col_idx, dtype=np.uint32)
+    if len(rp) != rows + 1:
+        raise ValueError("sparse_load: row_ptr needs rows + 1 entries")
+    nnz = len(ci)
+    vb = values if isinstance(values, (bytes, bytearray)) else fr_vec_bytes(values)
+    if len(vb) != 32 * nnz:
+        raise ValueError("sparse_load: one value per column index")
+    h = ctypes.c_uint64()
+    check(_lib.lib().zkp_sparse_load(rp.ctypes.data, ci.ctypes.data if nnz else None, buf(vb) if nnz else None,
+                                     rows, cols, nnz, ctypes.byref(h)))
+    out = DeviceHandle(h.value, rows, "sparse")
+    out.cols, out.nnz = cols, nnz
+    return out
+
+
+def sparse_matvec_dev(matrix, vec, out, vec_off=0, out_off=0):
+    """out[row] = sum_e value[e] * vec[col[e]] on device scalar handles (canonical)."""
+    check(_lib.lib().zkp_sparse_matvec_dev(matrix.handle, vec.handle, vec_off, out.handle, out_off))
+
+
+def fr_ap_interpolate_dev(values, k, out, scale=None, off=0, out_off=0):
+    """out[0..k) = coefficients of the polynomial p of degree < k with p(j + 1) = values[j], times scale."""
+    sc = fe_bytes(scale) if scale is not None else None
+    check(_lib.lib().zkp_fr_ap_interpolate_dev(values.handle, off, k, buf(sc), out.handle, out_off))
+
+
+def fr_ap_vanishing_dev(k):
+    """Handle with the k + 1 coefficients of Z(x) = (x - 1)(x - 2)...(x - k)."""
+    out = scalars_alloc(k + 1)
+    check(_lib.lib().zkp_fr_ap_vanishing_dev(k, out.handle, 0))
+    return out
+
+
+def fr_ap_lagrange_dev(k, x):
+    """Handle with l_1(x) .. l_k(x), the Lagrange basis of the points {1..k} at x."""
+    out = scalars_alloc(k)
+    check(_lib.lib().zkp_fr_ap_lagrange_dev(k, buf(fe_bytes(x)), out.handle, 0))
+    return out

@@ -289,3 +289,60 @@ def proof_c(sigma1_1, sigma1_2, sigma1_4, sigma1_5, Bx, Rx, Hx, s, r, prf_A, pub
     for i in range(num_gates - 1):
         c = add(c, mul(sigma1_5[i], int(Hx[i])))
     return c
+
+
+# ------------------------------------------------------------------ zkp/groth16/qap_creator_lcm.py (exact restatement)
+def qap_mk_singleton(point_loc, height, total_pts):
+    """/root/reference/zkp/groth16/qap_creator_lcm.py:50-66: the polynomial that is `height` at x = point_loc
+    and zero at the other points of {1..total_pts}.  The reference computes it in floats (height / fac);
+    here the division is the Fr inverse, which agrees with its rounded, determinant-scaled result wherever
+    the floats are exact (golden: tests/golden/groth16_qap.json)."""
+    fac = 1
+    for i in range(1, total_pts + 1):
+        if i != point_loc:
+            fac = fac * (point_loc - i) % R
+    o = [height % R * inv(fac) % R]
+    for i in range(1, total_pts + 1):
+        if i != point_loc:
+            o = g16_multiply_polys(o, [(-i) % R, 1])
+    return o
+
+
+def qap_lagrange_interp(vec):
+    """qap_creator_lcm.py:70-78: sum of the singletons; vec[i] = p(i + 1)."""
+    o = [0] * len(vec)
+    for i, v in enumerate(vec):
+        if v % R:
+            term = qap_mk_singleton(i + 1, v, len(vec))
+            o = [(a + b) % R for a, b in zip(o, term)]
+    return o
+
+
+def qap_vandermonde_det(k):
+    """determinant_fast(k_matrix(k)) of qap_creator_lcm.py:97-121: the Vandermonde determinant of the points
+    1..k, prod_{i<j} (j - i)."""
+    d = 1
+    for j in range(1, k + 1):
+        for i in range(1, j):
+            d = d * (j - i) % R
+    return d
+
+
+def r1cs_to_qap_times_lcm(A, B, C):
+    """qap_creator_lcm.py:114-135: per-wire interpolation of the transposed R1CS, A and B times det, C times
+    det^2; Z = (x-1)...(x-k).  Returns (Ax, Bx, Cx, Zx) over Fr (what getFRPoly2D/1D make of the floats)."""
+    k = len(A)
+    det = qap_vandermonde_det(k)
+    cols = lambda M: [list(c) for c in zip(*M)]
+    new_a = [[c * det % R for c in qap_lagrange_interp(col)] for col in cols(A)]
+    new_b = [[c * det % R for c in qap_lagrange_interp(col)] for col in cols(B)]
+    new_c = [[c * det % R * det % R for c in qap_lagrange_interp(col)] for col in cols(C)]
+    Z = [1]
+    for i in range(1, k + 1):
+        Z = g16_multiply_polys(Z, [(-i) % R, 1])
+    return new_a, new_b, new_c, Z
+
+
+def qap_eval_rows(M, x):
+    """poly_utils.py:86-106 ax_val / bx_val / cx_val: every wire polynomial at x."""
+    return [poly_eval(row, x) for row in M]

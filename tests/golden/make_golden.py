@@ -95,6 +95,69 @@ def groth16_toy():
     })
 
 
+# ------------------------------------------------------------------ Groth16 from the R1CS (QAP construction)
+def groth16_qap():
+    """R1CS -> QAP -> CRS -> proof for two programs, keeping the R1CS itself so that the sparse /
+    interpolating device path (zkp/groth16/qap_device.py) can be checked against every stage of the
+    reference's float-Lagrange + determinant pipeline (qap_creator_lcm.py:114-135)."""
+    from zkp.groth16.code_to_r1cs import code_to_r1cs_with_inputs, initialize_symbol
+    from zkp.groth16.qap_creator_lcm import r1cs_to_qap_times_lcm
+    from zkp.groth16 import poly_utils as pu
+    from zkp.groth16 import setup as st
+    from zkp.groth16.proving import proof_a, proof_b, proof_c, build_rpub_enum, FR
+    from zkp.groth16.verifying import verify
+    cases = []
+    programs = [
+        ("x3_plus_x_plus_5", "\ndef qeval(x):\n    y = x**3\n    return y + x + 5\n", [3]),
+        # six gates: the largest size at which the reference's float interpolation times det^2 stays exact
+        # (at 8 gates its own remainder is already non-zero)
+        ("six_gates", "\ndef qeval(x):\n    y = x**3\n    z = y * x + x\n    return z + y + 7\n", [2]),
+    ]
+    for idx, (name, code, inputs) in enumerate(programs):
+        initialize_symbol()
+        r, A, B, C = code_to_r1cs_with_inputs(code, inputs)
+        Ap, Bp, Cp, Z = r1cs_to_qap_times_lcm(A, B, C)
+        Ax, Bx, Cx = pu.getFRPoly2D(Ap), pu.getFRPoly2D(Bp), pu.getFRPoly2D(Cp)
+        Zx, Rx = pu.getFRPoly1D(Z), pu.getFRPoly1D(r)
+        k, m = pu.getNumGates(Ax), pu.getNumWires(Ax)
+        alpha, beta, gamma, delta, x_val = (FR(v + 17 * idx) for v in (3926, 3604, 2971, 1357, 3721))
+        Hx, rem = pu.hxr(Ax, Bx, Cx, Zx, r)
+        uA = [sum((Rx[i] * Ax[i][j] for i in range(m)), FR(0)) for j in range(k)]
+        uB = [sum((Rx[i] * Bx[i][j] for i in range(m)), FR(0)) for j in range(k)]
+        uC = [sum((Rx[i] * Cx[i][j] for i in range(m)), FR(0)) for j in range(k)]
+        Axv, Bxv, Cxv, Zxv = pu.ax_val(Ax, x_val), pu.bx_val(Bx, x_val), pu.cx_val(Cx, x_val), pu.zx_val(Zx, x_val)
+        pub = [0, 1]
+        s11 = st.sigma11(alpha, beta, delta)
+        s12 = st.sigma12(k, x_val)
+        s13, VAL = st.sigma13(m, alpha, beta, gamma, Axv, Bxv, Cxv, pub_r_indexs=pub)
+        s14 = st.sigma14(m, alpha, beta, delta, Axv, Bxv, Cxv, pub_r_indexs=pub)
+        s15 = st.sigma15(k, delta, x_val, Zxv)
+        s21 = st.sigma21(beta, delta, gamma)
+        s22 = st.sigma22(k, x_val)
+        rp, sp = FR(4106 + idx), FR(4565 + idx)
+        A_ = proof_a(s11, s12, Ax, Rx, rp)
+        B_ = proof_b(s21, s22, Bx, Rx, sp)
+        C_ = proof_c(s11, s12, s14, s15, Bx, Rx, Hx, sp, rp, A_, pub_r_indexs=pub)
+        ok = verify(A_, B_, C_, s11, s13, s21, build_rpub_enum(pub, Rx))
+        assert ok is True and all(int(v) == 0 for v in rem)
+        cases.append({
+            "name": name, "numGates": k, "numWires": m, "pub_r_indexs": pub,
+            "r1cs_A": [[int(v) for v in row] for row in A], "r1cs_B": [[int(v) for v in row] for row in B],
+            "r1cs_C": [[int(v) for v in row] for row in C], "witness": [int(v) for v in r],
+            "toxic": {"alpha": s(alpha), "beta": s(beta), "gamma": s(gamma), "delta": s(delta), "x_val": s(x_val)},
+            "r": s(rp), "s": s(sp),
+            "uA": svec(uA), "uB": svec(uB), "uC": svec(uC), "Zx": svec(Zx), "Hx": svec(Hx),
+            "Ax_val": svec(Axv), "Bx_val": svec(Bxv), "Cx_val": svec(Cxv), "Zx_val": s(Zxv),
+            "sigma1_1": [g1(p) for p in s11], "sigma1_2": [g1(p) for p in s12], "sigma1_3": [g1(p) for p in s13],
+            "sigma1_4": [g1(p) for p in s14], "sigma1_5": [g1(p) for p in s15],
+            "sigma2_1": [g2(p) for p in s21], "sigma2_2": [g2(p) for p in s22],
+            "proof_a": g1(A_), "proof_b": g2(B_), "proof_c": g1(C_), "verify": ok,
+        })
+    dump("groth16_qap.json", {
+        "source": "reference zkp.groth16.{code_to_r1cs,qap_creator_lcm,poly_utils,setup,proving,verifying} on oracle/shim",
+        "cases": cases})
+
+
 # ------------------------------------------------------------------ PLONK
 class SeededSecrets:
     """Stands in for the `secrets` module inside round1/round2 (they call secrets.randbelow)."""
@@ -233,6 +296,7 @@ def primitives():
 
 
 if __name__ == "__main__":
-    groth16_toy()
-    primitives()
-    plonk_all()
+    only = sys.argv[1:]
+    for fn in (groth16_toy, groth16_qap, primitives, plonk_all):
+        if not only or fn.__name__ in only:
+            fn()

@@ -134,3 +134,21 @@ def test_oracle_plonk_verifier_accepts_golden_and_rejects_tampering():
             bad = dict(proof)
             bad["z_comm"] = bn254.g1_add(bad["z_comm"], bn254.G1)
             assert plonk_verifier.verify(bad, pre, f["n"], int(f["omega"]), g2p) is False
+
+
+def test_qap_construction_matches_reference():
+    """oracle r1cs_to_qap_times_lcm (exact Fr) == the reference's float-Lagrange x determinant pipeline
+    (qap_creator_lcm.py:114-135 + getFRPoly2D) on the R1CS the reference's own compiler produced."""
+    for c in load("groth16_qap.json")["cases"]:
+        Ax, Bx, Cx, Z = ref_path.r1cs_to_qap_times_lcm(c["r1cs_A"], c["r1cs_B"], c["r1cs_C"])
+        w, k, m = c["witness"], c["numGates"], c["numWires"]
+        assert Z == ints(c["Zx"]) and len(Ax) == m and len(Ax[0]) == k
+        for M, key in ((Ax, "uA"), (Bx, "uB"), (Cx, "uC")):
+            assert ref_path.g16_multiply_vec_matrix(w, M)[:k] == ints(c[key])
+        x = int(c["toxic"]["x_val"])
+        assert ref_path.qap_eval_rows(Ax, x) == ints(c["Ax_val"])
+        assert ref_path.qap_eval_rows(Bx, x) == ints(c["Bx_val"])
+        assert ref_path.qap_eval_rows(Cx, x) == ints(c["Cx_val"])
+        assert ref_path.poly_eval(Z, x) == int(c["Zx_val"])
+        Hx, rem = ref_path.hxr(Ax, Bx, Cx, Z, w)
+        assert Hx == ints(c["Hx"]) and not any(rem)
