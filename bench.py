@@ -426,6 +426,11 @@ def run_ours(args):
         except Exception as e:  # never lose the headline line
             extras["groth16_prove_error"] = repr(e)
         try:
+            import qap_large
+            extras["groth16_r1cs_prove_2^%d" % args.log_n] = qap_large.run(args.log_n, 3, quiet=True)
+        except Exception as e:
+            extras["groth16_r1cs_prove_error"] = repr(e)
+        try:
             import plonk_large
             extras["plonk_prove_2^%d" % args.log_n] = plonk_large.run(args.log_n, 3, verify=True, quiet=True)
         except Exception as e:

@@ -14,6 +14,8 @@ with d = det Vandermonde(1..k) = prod_{n<k} n! (d^2 for C, as in r1cs_to_qap_tim
 values the reference's pipeline produces at toy size (tests/golden/groth16_qap.json), exact at any size.
 The proof elements then come from device_prover.prove (one MSM per element).
 """
+import functools
+
 import numpy as np
 
 from ... import native
@@ -23,6 +25,7 @@ from . import device_prover
 R = curve_order
 
 
+@functools.lru_cache(maxsize=16)
 def vandermonde_det(k):
     """det of k_matrix(k) (qap_creator_lcm.py:97-108): prod_{1<=i<j<=k} (j - i) = prod_{n=1}^{k-1} n!  (mod r)."""
     d, f = 1, 1
@@ -116,21 +119,33 @@ def witness_polys(dev, w, lcm=True):
 class Keys:
     """Proving key (device tables of device_prover.DeviceKey) + the verifier's small CRS part."""
 
-    def __init__(self, device_key, Z, pub_idx, priv_idx, sigma1_1, sigma1_3, sigma2_1, lcm):
-        self.device_key, self.Z, self.pub_idx, self.priv_idx = device_key, Z, pub_idx, priv_idx
+    def __init__(self, device_key, Z, pub_idx, priv_sel, sigma1_1, sigma1_3, sigma2_1, lcm):
+        self.device_key, self.Z, self.pub_idx, self.priv_sel = device_key, Z, pub_idx, priv_sel
+        self.priv_idx = priv_sel.idx
         self.sigma1_1, self.sigma1_3, self.sigma2_1, self.lcm = sigma1_1, sigma1_3, sigma2_1, lcm
 
 
-def _gather(handle, idx):
-    """Sub-vector handle[idx] (contiguous ranges stay on the device)."""
-    n = len(idx)
-    out = native.scalars_alloc(n)
-    if n and idx == list(range(idx[0], idx[0] + n)):
-        native.scalars_copy(out, 0, handle, idx[0], n)
-    elif n:
-        raw = native.scalars_download(handle, 0, handle.n)
-        native.scalars_upload(out, 0, b"".join(raw[32 * i:32 * i + 32] for i in idx), n)
-    return out
+class _Selection:
+    """An index subset of a device vector; a contiguous run (the usual case: the public wires come first)
+    is recognised once, at setup, and then gathered by a device copy."""
+
+    def __init__(self, idx):
+        self.idx = list(idx)
+        n = len(self.idx)
+        self.run = (self.idx[0], n) if n and self.idx[-1] - self.idx[0] == n - 1 and self.idx == list(range(self.idx[0], self.idx[0] + n)) else None
+
+    def __len__(self):
+        return len(self.idx)
+
+    def gather(self, handle):
+        n = len(self.idx)
+        out = native.scalars_alloc(n)
+        if self.run:
+            native.scalars_copy(out, 0, handle, self.run[0], n)
+        elif n:
+            raw = native.scalars_download(handle, 0, handle.n)
+            native.scalars_upload(out, 0, b"".join(raw[32 * i:32 * i + 32] for i in self.idx), n)
+        return out
 
 
 def setup(dev, alpha, beta, gamma, delta, x_val, pub_r_indexs=None, lcm=True, precompute=True):
@@ -138,7 +153,8 @@ def setup(dev, alpha, beta, gamma, delta, x_val, pub_r_indexs=None, lcm=True, pr
     of poly_utils.py:86-113), all vector work on the device."""
     k, m = dev.k, dev.m
     pub = [0, 1] if pub_r_indexs is None else list(pub_r_indexs)      # the reference's default (setup.py:26-27)
-    priv = [i for i in range(m) if i not in set(pub)]
+    pub_set = set(pub)
+    priv = _Selection(i for i in range(m) if i not in pub_set)
     alpha, beta, gamma, delta, x_val = (int(v) % R for v in (alpha, beta, gamma, delta, x_val))
     sA, sB, sC = _scales(k, lcm)
     # val_i = beta*A_i(x) + alpha*B_i(x) + C_i(x) for every wire: three transposed sparse products of l(x)
@@ -168,7 +184,7 @@ def setup(dev, alpha, beta, gamma, delta, x_val, pub_r_indexs=None, lcm=True, pr
     native.scalars_copy(scC, 0, scA, 0, k)
     native.scalars_upload(scC, k, enc([beta]), 1)
     if mp:
-        pv = _gather(val, priv)
+        pv = priv.gather(val)
         native.scalars_scale(pv, 0, mp, inv_delta)
         native.scalars_copy(scC, k + 1, pv, 0, mp)
         pv.free()
@@ -184,7 +200,7 @@ def setup(dev, alpha, beta, gamma, delta, x_val, pub_r_indexs=None, lcm=True, pr
             if t.n >= (1 << 12):
                 native.table_precompute(t, max(4, min(20, t.n.bit_length() - 4)))
     # the verifier's part: sigma1_1, sigma2_1 and sigma1_3 on the public wires (placeholders elsewhere, setup.py:37)
-    pub_vals = native.fr_vec_from_bytes(native.scalars_download(_gather(val, pub), 0, len(pub))) if pub else []
+    pub_vals = native.fr_vec_from_bytes(native.scalars_download(_Selection(pub).gather(val), 0, len(pub))) if pub else []
     val.free()
     s13_tab = native.g1_fixed_base_mul(g1b, enc([v * inv_gamma % R for v in pub_vals]), len(pub)) if pub else None
     s13_pts = [native.g1_from_bytes(native.table_download(s13_tab, i, 1)) for i in range(len(pub))]
@@ -203,7 +219,7 @@ def setup(dev, alpha, beta, gamma, delta, x_val, pub_r_indexs=None, lcm=True, pr
 def prove(keys, dev, w, r, s, keep=False):
     """(A, B, C) for the witness handle w (m values).  The algebra of proving.py:23-75 + poly_utils.hxr."""
     uA, uB, uC = witness_polys(dev, w, keys.lcm)
-    rx_priv = _gather(w, keys.priv_idx)
+    rx_priv = keys.priv_sel.gather(w)
     out = device_prover.prove(keys.device_key, uA, uB, uC, keys.Z, rx_priv, r, s, keep_quotient=keep)
     rx_priv.free()
     if keep:
