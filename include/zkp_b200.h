@@ -231,6 +231,10 @@ int zkp_pinned_free(void* p);
 /* Dependent-free integer-MAD microbenchmark: variant 0 = IMAD.WIDE.U32 (the roofline unit),
  * 1 = IMAD (32-bit lo), 2 = IMAD.HI.  Returns G(limb-MAC)/s over the whole chip. */
 int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effective);
+/* Single-thread latency of one operation (ns): mode 0/1/2 = 1/2/4 independent Fp products per step,
+ * 3 = XYZZ add (inlined products), 4 = XYZZ add (out-of-line products), 5 = mixed add, 6 = double.
+ * The MSM's reduction tail is bounded by these, not by throughput. */
+int zkp_latency_probe(int mode, double* ns_per_op);
 /* Field-op self-test hooks used by tests/ (field: 0 = Fp, 1 = Fr; op: 0 add,1 sub,2 mul,3 inv,4 sqr) */
 int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
 /* out[i] = a[i] + b[i] on G1 (group: 0 = G1, 1 = G2) via XYZZ, result affine; exercises all edge cases */

@@ -102,6 +102,7 @@ PROTOTYPES = {
     "zkp_pinned_alloc": (c_int, [u64, ctypes.POINTER(ctypes.c_void_p)]),
     "zkp_pinned_free": (c_int, [vp]),
     "zkp_imad_peak": (c_int, [c_int, f64p, f64p]),
+    "zkp_latency_probe": (c_int, [c_int, f64p]),
     "zkp_dbg_field_op": (c_int, [c_int, c_int, vp, vp, u64, vp]),
     "zkp_dbg_point_add": (c_int, [c_int, vp, vp, u64, vp]),
 }

@@ -72,6 +72,49 @@ void set_last_error(const std::string& s) {
 //         2: mad.hi.u32   (IMAD.HI)
 //         3: Fp Montgomery multiplication chains (136 limb-MACs each): the practical ceiling
 static constexpr int PEAK_UNROLL = 16;
+
+// One thread, dependent chains: the latency a lone thread pays per operation (what bounds the MSM's
+// reduction tail).  mode 0/1/2: 1/2/4 independent Fp product chains per iteration (time per iteration);
+// 3: XYZZ add, inlined products; 4: XYZZ add, out-of-line products; 5: XYZZ mixed add; 6: XYZZ double.
+__global__ void latency_probe_kernel(int mode, int iters, uint32_t* out) {
+  if (threadIdx.x != 0) return;
+  Fp x[4], y;
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[j].v[k] = (0x9e3779b9u * (k + 1 + 8 * j)) & (k == 7 ? 0x0fffffffu : 0xffffffffu);
+#pragma unroll
+  for (int k = 0; k < 8; k++) y.v[k] = (0x85ebca6bu * (k + 3)) & (k == 7 ? 0x0fffffffu : 0xffffffffu);
+  uint32_t s = 0;
+  if (mode <= 2) {
+    for (int it = 0; it < iters; it++) {
+      x[0] = x[0] * y;
+      if (mode >= 1) x[1] = x[1] * y;
+      if (mode >= 2) { x[2] = x[2] * y; x[3] = x[3] * y; }
+    }
+    for (int j = 0; j < 4; j++) s ^= x[j].v[0];
+  } else if (mode == 3 || mode == 5 || mode == 6) {
+    XYZZ<Fp> acc, q;
+    acc.x = x[0]; acc.y = x[1]; acc.zz = x[2]; acc.zzz = x[3];
+    q.x = y; q.y = x[1] * y; q.zz = x[2] * y; q.zzz = x[3] * y;
+    Affine<Fp> qa;
+    qa.x = q.x; qa.y = q.y;
+    for (int it = 0; it < iters; it++) {
+      if (mode == 3) acc.add(q);
+      else if (mode == 5) acc.madd(qa);
+      else acc = acc.dbl();
+    }
+    s = acc.x.v[0] ^ acc.zzz.v[0];
+  } else {
+    XYZZ<FpC> acc, q;
+    for (int k = 0; k < 8; k++) {
+      acc.x.v[k] = x[0].v[k]; acc.y.v[k] = x[1].v[k]; acc.zz.v[k] = x[2].v[k]; acc.zzz.v[k] = x[3].v[k];
+      q.x.v[k] = y.v[k]; q.y.v[k] = x[1].v[k] ^ 5; q.zz.v[k] = x[2].v[k] ^ 9; q.zzz.v[k] = x[3].v[k] ^ 3;
+    }
+    for (int it = 0; it < iters; it++) acc.add(q);
+    s = acc.x.v[0] ^ acc.zzz.v[0];
+  }
+  out[0] = s;
+}
 template <int VARIANT>
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters, uint32_t m0) {
   uint32_t seed = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
@@ -381,6 +424,31 @@ int zkp_pinned_alloc(uint64_t bytes, void** out) {
 }
 int zkp_pinned_free(void* p) {
   return guarded([&](Context&) { CUDA_CHECK(cudaFreeHost(p)); });
+}
+
+int zkp_latency_probe(int mode, double* ns_per_op) {
+  return guarded([&](Context& c) {
+    if (mode < 0 || mode > 6 || !ns_per_op) throw InvalidArgument("zkp_latency_probe: bad mode");
+    DevBuf out;
+    out.reserve(64);
+    const int iters = 2000;
+    latency_probe_kernel<<<1, 32, 0, c.stream>>>(mode, iters / 10, out.as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+      CUDA_CHECK(cudaEventRecord(g_ev0, c.stream));
+      latency_probe_kernel<<<1, 32, 0, c.stream>>>(mode, iters, out.as<uint32_t>());
+      CUDA_CHECK_LAUNCH();
+      CUDA_CHECK(cudaEventRecord(g_ev1, c.stream));
+      CUDA_CHECK(cudaEventSynchronize(g_ev1));
+      float ms;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, g_ev0, g_ev1));
+      if (ms < best) best = ms;
+    }
+    c.launches += 4;
+    *ns_per_op = (double)best * 1e6 / iters;
+    out.release();
+  });
 }
 
 int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effective) {

@@ -106,6 +106,13 @@ def imad_peak(variant=0):
     return g.value
 
 
+def latency_probe(mode):
+    """ns per operation for a lone thread (see zkp_latency_probe)."""
+    ns = ctypes.c_double()
+    check(_lib.lib().zkp_latency_probe(mode, ctypes.byref(ns)))
+    return ns.value
+
+
 def msm_profile(enable):
     check(_lib.lib().zkp_msm_profile(1 if enable else 0))
 

@@ -69,11 +69,13 @@ def preprocess(n, selector_evals, sigma_evals, srs_table, srs_size):
         c = _alloc_from(ev, n, n)
         native.ntt_dev(c, 0, key.log_n, key.omega, inverse=True)
         key.coeffs[name] = c
-        key.comm[name] = _commit(key, c, 0, n)
         e = _alloc_from(c, n, key.N8)
         native.scalars_convert(e, 0, n, True)
         native.ntt_dev(e, 0, key.log_n + key.log_ext, key.omega8, coset_shift=COSET_SHIFT)
         key.coset[name] = e
+    # the eight commitments as one pipelined launch group
+    for name, pt in zip(CIRCUIT_POLYS, _commit_many(key, [(key.coeffs[name], 0, n) for name in CIRCUIT_POLYS])):
+        key.comm[name] = pt
     key.x = native.scalars_alloc(key.N8)
     key.l1f = native.scalars_alloc(key.N8)
     key.zh8 = native.scalars_alloc(key.ext)

@@ -194,3 +194,65 @@ def test_plonk_scalar_helpers_match_reference_formulas():
     want = sum(int(v) * int(utils.lagrange_basis_eval(i, n, w, zeta)) for i, v in enumerate(pub)) % R
     assert int(utils.public_input_poly_eval(pub, n, w, zeta)) == want
     assert utils.public_input_polynomial([], n, w).is_zero()
+
+
+def test_binary_wire_format_round_trips_the_reference_objects():
+    """zkp/plonk/wire.py: the reference's serializer surface (plonk_serializers.py:23-250) over
+    the binary ABI layout -- round trips of the reference-minted proof / preprocessed data / SRS carry exactly
+    the values its decimal-string JSON carries."""
+    from interactive_zkp_study_b200.zkp.plonk import wire
+    from interactive_zkp_study_b200.zkp.plonk.polynomial import Polynomial
+    from interactive_zkp_study_b200.zkp.plonk.preprocessor import PreprocessedData
+    from interactive_zkp_study_b200.zkp.plonk.prover import Proof
+    from interactive_zkp_study_b200.zkp.plonk.srs import SRS
+    from interactive_zkp_study_b200.zkp.plonk.transcript import Transcript
+    from tests.util import load
+    f = load("plonk_chain16.json")
+    pt = lambda p: None if p is None else (FQ(int(p[0])), FQ(int(p[1])))
+    pt2 = lambda p: (FQ2([int(p[0][0]), int(p[0][1])]), FQ2([int(p[1][0]), int(p[1][1])]))
+    # scalars, points, infinity
+    assert int(wire.deserialize_fr(wire.serialize_fr(FR(curve_order - 1)))) == curve_order - 1
+    assert wire.deserialize_g1(wire.serialize_g1(None)) is None and len(wire.serialize_g1(None)) == 64
+    assert wire.deserialize_g2(wire.serialize_g2(None)) is None
+    g = pt(f["proof"]["a_comm"])
+    assert wire.deserialize_g1(wire.serialize_g1(g)) == g
+    # proof: 9 points + 7 scalars
+    proof = Proof()
+    for k, v in f["proof"].items():
+        setattr(proof, k, pt(v) if k.endswith("_comm") else FR(int(v)))
+    blob = wire.serialize_proof(proof)
+    back = wire.deserialize_proof(wire.from_text(wire.to_text(blob)))
+    for k, v in f["proof"].items():
+        got = getattr(back, k)
+        assert (got == pt(v)) if k.endswith("_comm") else (int(got) == int(v)), k
+    assert len(blob) < 1200                                  # vs ~2.6 KB of decimal JSON
+    partial = Proof()
+    partial.a_comm = g                                       # rounds not run yet stay None (plonk_routes stores partial proofs)
+    back = wire.deserialize_proof(wire.serialize_proof(partial))
+    assert back.a_comm == g and back.z_comm is None and back.r_eval is None
+    # preprocessed data
+    pp = PreprocessedData()
+    pp.n, pp.omega, pp.domain = f["n"], FR(int(f["omega"])), [FR(int(v)) for v in f["domain"]]
+    for k in f["pre"]:
+        setattr(pp, k + "_poly", Polynomial([FR(int(v)) for v in f["pre"][k]]))
+        setattr(pp, k + "_comm", pt(f["pre_comm"][k]))
+    pp.sigma, pp.num_public_inputs = f["sigma"], f["num_public_inputs"]
+    back = wire.deserialize_preprocessed(wire.serialize_preprocessed(pp))
+    assert (back.n, int(back.omega), back.sigma, back.num_public_inputs) == (pp.n, int(pp.omega), pp.sigma, pp.num_public_inputs)
+    assert [int(v) for v in back.domain] == [int(v) for v in pp.domain]
+    for k in f["pre"]:
+        assert [int(c) for c in getattr(back, k + "_poly").coeffs] == [int(v) for v in f["pre"][k]]
+        assert getattr(back, k + "_comm") == pt(f["pre_comm"][k])
+    # SRS and transcript
+    srs = SRS([pt(p) for p in f["g1_powers"]], [pt2(p) for p in f["g2_powers"]], f["srs_max_degree"])
+    back = wire.deserialize_srs(wire.serialize_srs(srs))
+    assert back.max_degree == srs.max_degree and back.g1_powers == srs.g1_powers and back.g2_powers == srs.g2_powers
+    t = Transcript()
+    t.append_scalar(b"x", FR(5)) if hasattr(t, "append_scalar") else None
+    t2 = wire.deserialize_transcript(wire.serialize_transcript(t))
+    assert bytes(t2.state) == bytes(t.state)
+    assert wire.deserialize_poly(wire.serialize_poly(None)) is None
+    with pytest.raises(ValueError):
+        wire.loads(b"nope")
+    with pytest.raises(ValueError):
+        wire.loads(blob[:-5])

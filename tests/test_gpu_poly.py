@@ -127,3 +127,21 @@ def test_groth16_quotient_matches_hxr(native, m, k):
     gh, gr = native.groth16_quotient(enc(ra), enc(rb), enc(rc), m, enc(Z), len(Z))
     assert native.fr_vec_from_bytes(gh) == Hx
     assert native.fr_vec_from_bytes(gr) == rem
+
+
+def test_wire_format_moves_device_vectors_without_python_integers(native):
+    """wire.serialize_handle / deserialize_to_handle: the bytes of a device-resident
+    polynomial are exactly what the list-level serializer writes for the same coefficients."""
+    import random
+    from interactive_zkp_study_b200.zkp.plonk import wire
+    from interactive_zkp_study_b200.zkp.plonk.polynomial import Polynomial
+    from interactive_zkp_study_b200.zkp.plonk.field import FR
+    rng = random.Random(31)
+    coeffs = [rng.randrange(1, native.R_MOD) for _ in range(777)]
+    h = native.scalars_load(native.fr_vec_bytes(coeffs), len(coeffs))
+    blob = wire.serialize_handle(h)
+    assert blob == wire.serialize_poly(Polynomial([FR(c) for c in coeffs]))
+    assert wire.serialize_handle(h, 10, 5) == blob[32 * 5:32 * 15]
+    h2 = wire.deserialize_to_handle(blob)
+    assert h2.n == len(coeffs) and native.scalars_download(h2, 0, h2.n) == blob
+    assert [int(c) for c in wire.deserialize_poly(blob).coeffs] == coeffs
