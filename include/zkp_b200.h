@@ -232,7 +232,8 @@ int zkp_pinned_free(void* p);
  * 1 = IMAD (32-bit lo), 2 = IMAD.HI.  Returns G(limb-MAC)/s over the whole chip. */
 int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effective);
 /* Single-thread latency of one operation (ns): mode 0/1/2 = 1/2/4 independent Fp products per step,
- * 3 = XYZZ add (inlined products), 4 = XYZZ add (out-of-line products), 5 = mixed add, 6 = double.
+ * 3 = XYZZ add (inlined products), 4 = XYZZ add (out-of-line products), 5 = mixed add, 6 = double;
+ * 7 / 8 = XYZZ add on a quad of lanes (inlined / out-of-line products), 9 = double on a quad.
  * The MSM's reduction tail is bounded by these, not by throughput. */
 int zkp_latency_probe(int mode, double* ns_per_op);
 /* Field-op self-test hooks used by tests/ (field: 0 = Fp, 1 = Fr; op: 0 add,1 sub,2 mul,3 inv,4 sqr) */

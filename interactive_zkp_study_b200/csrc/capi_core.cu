@@ -2,6 +2,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "ec.cuh"
+#include "ec_quad.cuh"
 #include "registry.cuh"
 
 namespace zkp {
@@ -76,7 +77,30 @@ static constexpr int PEAK_UNROLL = 16;
 // One thread, dependent chains: the latency a lone thread pays per operation (what bounds the MSM's
 // reduction tail).  mode 0/1/2: 1/2/4 independent Fp product chains per iteration (time per iteration);
 // 3: XYZZ add, inlined products; 4: XYZZ add, out-of-line products; 5: XYZZ mixed add; 6: XYZZ double.
+template <class F>
+__device__ __noinline__ uint32_t quad_probe(int mode, int iters) {
+  const int ql = threadIdx.x & 3;
+  XYZZ<F> acc, q;
+  for (int k = 0; k < 8; k++) {
+    uint32_t m = k == 7 ? 0x0fffffffu : 0xffffffffu;
+    acc.x.v[k] = (0x9e3779b9u * (k + 1)) & m; acc.y.v[k] = (0x9e3779b9u * (k + 9)) & m;
+    acc.zz.v[k] = (0x9e3779b9u * (k + 17)) & m; acc.zzz.v[k] = (0x9e3779b9u * (k + 25)) & m;
+    q.x.v[k] = (0x85ebca6bu * (k + 3)) & m; q.y.v[k] = (0x85ebca6bu * (k + 11)) & m;
+    q.zz.v[k] = (0x85ebca6bu * (k + 19)) & m; q.zzz.v[k] = (0x85ebca6bu * (k + 27)) & m;
+  }
+  for (int it = 0; it < iters; it++) {
+    if (mode == 0) acc = Quad<F>::add(acc, q, ql);
+    else acc = Quad<F>::dbl(acc, ql);
+  }
+  return acc.x.v[0] ^ acc.zzz.v[0];
+}
+
 __global__ void latency_probe_kernel(int mode, int iters, uint32_t* out) {
+  if (mode >= 7) {  // one warp, quad operations: 7 add (inlined products), 8 add (out-of-line), 9 double (out-of-line)
+    uint32_t s = mode == 7 ? quad_probe<Fp>(0, iters) : quad_probe<FpC>(mode == 8 ? 0 : 1, iters);
+    if (threadIdx.x == 0) out[0] = s;
+    return;
+  }
   if (threadIdx.x != 0) return;
   Fp x[4], y;
   for (int j = 0; j < 4; j++)
@@ -428,7 +452,7 @@ int zkp_pinned_free(void* p) {
 
 int zkp_latency_probe(int mode, double* ns_per_op) {
   return guarded([&](Context& c) {
-    if (mode < 0 || mode > 6 || !ns_per_op) throw InvalidArgument("zkp_latency_probe: bad mode");
+    if (mode < 0 || mode > 9 || !ns_per_op) throw InvalidArgument("zkp_latency_probe: bad mode");
     DevBuf out;
     out.reserve(64);
     const int iters = 2000;

@@ -30,6 +30,7 @@
 #pragma once
 #include "common.cuh"
 #include "ec.cuh"
+#include "ec_quad.cuh"
 
 namespace zkp {
 
@@ -477,6 +478,61 @@ __global__ void __launch_bounds__(64) msm_ws2_kernel(const XYZZ<F>* __restrict__
   }
 }
 
+// The narrow levels, fused: a block takes a segment of `seg` consecutive items (A_i, E_i) of one window
+// and runs log2(seg) radix-2 levels on it out of shared memory (chunk j of a level reads items 2j, 2j+1
+// and writes item j, so the recursion never leaves the segment).  Every group operation runs on a quad
+// of lanes (ec_quad.cuh: ~4 product latencies per addition instead of 14); a warp of role 0
+// (A' = 2(A0+A1)) and a warp of role 1 (E' = E0+E1+A1) serve 8 chunks.  65536 buckets -> 1 item in
+// three launches of the old radix-2 kernel (throughput-bound levels) plus two launches of this one,
+// instead of sixteen launches each two additions deep on a lone thread.
+template <class F>
+struct WsFused {
+  static constexpr int SEG = sizeof(F) == 32 ? 128 : 64;  // items per block: 2 * SEG * sizeof(XYZZ) = 32 KB
+};
+template <class F>
+__global__ void __launch_bounds__(WsFused<F>::SEG * 4) msm_ws2_fused_kernel(const XYZZ<F>* __restrict__ A,
+                                                                            const XYZZ<F>* __restrict__ E, uint32_t seg,
+                                                                            XYZZ<F>* __restrict__ A_out,
+                                                                            XYZZ<F>* __restrict__ E_out) {
+  extern __shared__ uint4 ws_smem[];
+  XYZZ<F>* sa = reinterpret_cast<XYZZ<F>*>(ws_smem);
+  XYZZ<F>* se = sa + WsFused<F>::SEG;
+  const uint64_t base = (uint64_t)blockIdx.x * seg;
+  if (!E) E = A;  // first level of the recursion: E_i = A_i (bucket b weighs b + 1)
+  for (uint32_t i = threadIdx.x; i < seg; i += blockDim.x) {
+    sa[i] = A[base + i];
+    se[i] = E[base + i];
+  }
+  __syncthreads();
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t role = warp & 1;
+  const int ql = lane & 3;
+  for (uint32_t m = seg; m > 1; m >>= 1) {
+    const uint32_t chunks = m >> 1;
+    uint32_t chunk = (warp >> 1) * 8 + (lane >> 2);
+    const bool warp_live = (warp >> 1) * 8 < chunks;  // warp-uniform: whole warps drop out as the level narrows
+    const bool live = chunk < chunks;
+    if (!live) chunk = chunks - 1;                    // partial warp: keep all lanes in the shuffles
+    XYZZ<F> r;
+    if (warp_live) {
+      if (role == 0) {
+        r = Quad<F>::dbl(Quad<F>::add(sa[2 * chunk], sa[2 * chunk + 1], ql), ql);
+      } else {
+        r = Quad<F>::add(se[2 * chunk], se[2 * chunk + 1], ql);
+        r = Quad<F>::add(r, sa[2 * chunk + 1], ql);
+      }
+    }
+    __syncthreads();  // every operand of this level has been read
+    if (warp_live && live && ql == 0) {
+      if (role == 0) sa[chunk] = r;
+      else se[chunk] = r;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) A_out[blockIdx.x] = sa[0];
+  if (threadIdx.x == 32) E_out[blockIdx.x] = se[0];
+}
+
 // Horner over the window sums (one thread), to affine, out of Montgomery form.
 // out: canonical little-endian coordinates; flag = 1 when the result is the point at infinity.
 template <class F>
@@ -521,6 +577,7 @@ struct MsmEngine {
   DevBuf ntask, task_base, len_bins, tasks, partials, folded, heavy;
   int reduce_L = 8;
   uint32_t wide_threshold = 1u << 17;  // items (all windows) above which a level is throughput bound
+  uint32_t quad_threshold = 1u << 12;  // radix-2 outputs (all windows) below which a level is latency bound
 
   // pts: device, affine Montgomery; scalars: device, canonical.  Leaves the affine canonical result
   // in `result` (and the infinity flag in `flag`), or the XYZZ Montgomery partial sum when
@@ -660,9 +717,12 @@ struct MsmEngine {
     if (pre_stride) pl.W = 1;  // one shared bucket set: reduce a single "window", no Horner
     while (n_in > 1) {
       // wide levels (many items): radix reduce_L running sums, fewest group operations per bucket;
-      // narrow levels: radix 2 on two threads, shortest dependency chain.
+      // middle levels: radix 2, one thread per output (still throughput bound);
+      // narrow levels: fused segments on quads of lanes, shortest dependency chain.
       bool wide = (uint64_t)n_in * pl.W >= (uint64_t)wide_threshold && n_in >= (uint32_t)reduce_L;
+      bool fused = !wide && (uint64_t)(n_in / 2) * pl.W <= (uint64_t)quad_threshold;
       uint32_t L = wide ? (uint32_t)reduce_L : 2u;
+      if (fused) L = n_in < (uint32_t)WsFused<FC>::SEG ? n_in : (uint32_t)WsFused<FC>::SEG;
       int logL = 0;
       while ((1u << logL) < L) logL++;
       uint32_t T = n_in / L;
@@ -672,6 +732,9 @@ struct MsmEngine {
       if (wide)
         msm_ws_level_kernel<FC><<<ceil_div((uint64_t)T * pl.W, 64), 64, 0, st>>>(
             A, E, n_in, L, logL, pl.W, lvlA[pp].template as<XYZZ<FC>>(), lvlE[pp].template as<XYZZ<FC>>());
+      else if (fused)
+        msm_ws2_fused_kernel<FC><<<T * pl.W, WsFused<FC>::SEG * 4, 2 * WsFused<FC>::SEG * sizeof(XYZZ<FC>), st>>>(
+            A, E, L, lvlA[pp].template as<XYZZ<FC>>(), lvlE[pp].template as<XYZZ<FC>>());
       else
         msm_ws2_kernel<FC><<<ceil_div((uint64_t)ceil_div((uint64_t)T * pl.W, 32) * 64, 64), 64, 0, st>>>(
             A, E, n_in, pl.W, lvlA[pp].template as<XYZZ<FC>>(), lvlE[pp].template as<XYZZ<FC>>());
@@ -681,7 +744,7 @@ struct MsmEngine {
       E = lvlE[pp].template as<XYZZ<FC>>();
       n_in = T;
       pp ^= 1;
-      tr.mark(wide ? "ws wide" : "ws2");
+      tr.mark(wide ? "ws wide" : fused ? "ws fused" : "ws2");
     }
     // n_in == 1: V_w = E_w (c == 1 never happens; for B == 1 the single bucket has weight 1 = itself)
     const XYZZ<FC>* wsum = E ? E : A;
