@@ -72,8 +72,9 @@ int zkp_free(uint64_t handle);
  * width, fold all windows into ONE bucket set and need no final doubling chain (the 254 sequential
  * doublings of the plain algorithm).  Memory: ceil(255/window_bits) x the plain table.  Results are
  * unchanged (same group element, same affine point). */
-int zkp_g1_table_precompute(uint64_t table, int window_bits);
+int zkp_g1_table_precompute(uint64_t table, int window_bits); /* 0 = width chosen for the table size */
 int zkp_g2_table_precompute(uint64_t table, int window_bits);
+int zkp_table_window_bits(uint64_t table, int* window_bits);  /* 0 = plain layout */
 /* points [offset, offset+n) of the table, scalars from the host (H2D inside the call) */
 int zkp_g1_msm_table(uint64_t table, uint64_t offset, const uint8_t* scalars, uint64_t n, uint8_t out_xy[64],
                      int* out_is_inf);

@@ -63,6 +63,21 @@ inline MsmPlan msm_plan(uint64_t n, int force_c = 0) {
   return p;
 }
 
+// Window width for a window-precomputed table of n points (zkp_*_table_precompute with window_bits = 0).
+// Measured on B200 (tools/c_sweep.py): wider windows mean fewer additions per point (ceil(255/c)) but
+// 2^(c-1) buckets to reduce, and only widths whose TOP window is well filled are good -- all windows
+// share one bucket set, so a top window of t bits piles n / 2^t extra entries on each of its few
+// buckets (c = 18: t = 3, 30 % slower than c = 17 at every size).  255 = 15*17 = 12*20 + 15 = 17*15 =
+// 19*13 + 8 = 25*10 + 5 = 36*7 + 3.
+inline int msm_auto_precomputed_c(uint64_t n) {
+  if (n >= 741455) return 20;  // 2^19.5
+  if (n >= (1u << 14)) return 17;
+  if (n >= (1u << 12)) return 15;
+  if (n >= 96) return 13;
+  if (n >= 24) return 10;
+  return 7;
+}
+
 // ---------------------------------------------------------------- stage 1: digits + histogram
 // wstride: distance between the bucket sets of consecutive windows (B for a plain table; 0 for a
 // window-precomputed table, where all windows share one bucket set).

@@ -198,7 +198,8 @@ struct GroupApi {
     return guarded([&](Context& c) {
       Resource* t = need(table, KIND, "table_precompute");
       if (t->pre_c) throw InvalidArgument("table_precompute: table is already precomputed");
-      if (window_bits < 2 || window_bits > MSM_MAX_C) throw InvalidArgument("table_precompute: window_bits must be in [2,20]");
+      if (window_bits == 0) window_bits = msm_auto_precomputed_c(t->n);
+      if (window_bits < 2 || window_bits > MSM_MAX_C) throw InvalidArgument("table_precompute: window_bits must be 0 (automatic) or in [2,20]");
       if (t->n == 0) return;
       MsmPlan pl = msm_plan(t->n, window_bits);
       if ((uint64_t)pl.W * t->n >= (1ull << 31)) throw InvalidArgument("table_precompute: W*n must be < 2^31");

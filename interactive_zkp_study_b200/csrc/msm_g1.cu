@@ -64,4 +64,15 @@ int zkp_table_download(uint64_t table, uint64_t offset, uint64_t n, uint8_t* out
   });
 }
 
+// window width of a precomputed table (0 = plain layout)
+int zkp_table_window_bits(uint64_t table, int* window_bits) {
+  return guarded([&](Context&) {
+    if (!window_bits) throw InvalidArgument("zkp_table_window_bits: null output");
+    Resource* t = registry().get(table, HandleKind::G1Table);
+    if (!t) t = registry().get(table, HandleKind::G2Table);
+    if (!t) throw BadHandle("zkp_table_window_bits: not a point table");
+    *window_bits = t->pre_c;
+  });
+}
+
 }  // extern "C"

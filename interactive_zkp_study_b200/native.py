@@ -190,10 +190,15 @@ def g2_table_load(pts_bytes, n):
     return _load("zkp_g2_table_load", pts_bytes, n, "g2")
 
 
-def table_precompute(handle, window_bits):
+def table_precompute(handle, window_bits=0):
+    """Window-precomputed layout for a static table; window_bits = 0 lets the library pick the width
+    for the table size (measured rule, csrc/msm.cuh msm_auto_precomputed_c)."""
     fn = _lib.lib().zkp_g1_table_precompute if handle.kind == "g1" else _lib.lib().zkp_g2_table_precompute
     check(fn(handle.handle, int(window_bits)))
-    handle.pre_c = int(window_bits)
+    c = ctypes.c_int()
+    check(_lib.lib().zkp_table_window_bits(handle.handle, ctypes.byref(c)))
+    handle.pre_c = c.value
+    return c.value
 
 
 def scalars_load(sc_bytes, n):

@@ -47,7 +47,7 @@ def _maybe_precompute(handle, n):
     it has no 254-step doubling chain, which is most of the latency of a small commit (a toy-size
     commit drops from ~1.5 ms to ~0.3 ms) and ~25 % of a 2^20 one.  Cost: ceil(255/c) x the memory."""
     if n >= PRECOMPUTE_MIN_POINTS:
-        native.table_precompute(handle, max(4, min(20, n.bit_length() - 3)))
+        native.table_precompute(handle)
 
 
 def g1_table(points):

@@ -44,8 +44,8 @@ def setup_from_toxic(k, alpha, beta, delta, x_val, zx_val, priv_vals, precompute
     TC = native.g1_fixed_base_mul(native.g1_bytes(G1), scC, k + 1 + m_priv + (k - 1))
     if precompute:
         for t in (TA, TB2, TC):
-            if t.n >= (1 << 12):
-                native.table_precompute(t, max(4, min(20, t.n.bit_length() - 4)))
+            if t.n >= 2:
+                native.table_precompute(t)
     return DeviceKey(k, m_priv, TA, TB2, TC)
 
 

@@ -197,8 +197,8 @@ def setup(dev, alpha, beta, gamma, delta, x_val, pub_r_indexs=None, lcm=True, pr
         h.free()
     if precompute:
         for t in (TA, TB2, TC):
-            if t.n >= (1 << 12):
-                native.table_precompute(t, max(4, min(20, t.n.bit_length() - 4)))
+            if t.n >= 2:
+                native.table_precompute(t)
     # the verifier's part: sigma1_1, sigma2_1 and sigma1_3 on the public wires (placeholders elsewhere, setup.py:37)
     pub_vals = native.fr_vec_from_bytes(native.scalars_download(_Selection(pub).gather(val), 0, len(pub))) if pub else []
     val.free()

@@ -6,7 +6,7 @@ log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 K = 8
 n = 1 << log_n
 t = nat.g1_fixed_base_mul_dev(nat.g1_bytes((1, 2)), nat.scalars_generate(2, n), n)
-nat.table_precompute(t, max(4, min(20, log_n - 3)))
+nat.table_precompute(t)
 ks = [nat.scalars_generate(100 + i, n) for i in range(K)]
 single = [nat.g1_msm_dev(t, 0, k, 0, n) for k in ks]
 assert nat.g1_msm_dev_batch(t, [(k, 0, 0, n) for k in ks]) == single

@@ -9,7 +9,7 @@ G2 = nat.g2_bytes(((108570469990230571359445707622328294813707563595785180869905
 log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 n = 1 << log_n
 t = nat.g2_fixed_base_mul_dev(G2, nat.scalars_generate(3, n), n)
-nat.table_precompute(t, max(4, min(20, log_n - 3)))
+nat.table_precompute(t)
 k = nat.scalars_generate(1, n)
 for _ in range(3):
     nat.timer_start(); r = nat.g2_msm_dev(t, 0, k, 0, n); ms = nat.timer_stop()

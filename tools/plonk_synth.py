@@ -64,7 +64,7 @@ def device_setup(circ, srs_tau=None, precompute=True):
     powers = nat.fr_prefix_product(nat.fr_vec_bytes([tau] * size), size)
     srs = nat.g1_fixed_base_mul(nat.g1_bytes((1, 2)), powers, size)
     if precompute and size >= (1 << 12):
-        nat.table_precompute(srs, max(4, min(20, size.bit_length() - 4)))
+        nat.table_precompute(srs)
     omega = int(get_root_of_unity(n))
     enc = nat.fr_vec_bytes
     sel_h = [nat.scalars_load(enc(v), n) for v in circ["sel"]]
