@@ -241,6 +241,9 @@ int zkp_latency_probe(int mode, double* ns_per_op);
 int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
 /* out[i] = a[i] + b[i] on G1 (group: 0 = G1, 1 = G2) via XYZZ, result affine; exercises all edge cases */
 int zkp_dbg_point_add(int group, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
+/* experiment: P[2i] + P[2i+1] over a plain G1 table in affine coordinates, `batch` additions per shared
+ * inversion per thread; kernel milliseconds and the first n_check sums */
+int zkp_dbg_affine_pairs(uint64_t table, int batch, double* ms, uint8_t* out_first, uint32_t n_check);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,7 @@ PROTOTYPES = {
     "zkp_g1_table_precompute": (c_int, [u64, c_int]),
     "zkp_g2_table_precompute": (c_int, [u64, c_int]),
     "zkp_table_window_bits": (c_int, [u64, ctypes.POINTER(c_int)]),
+    "zkp_dbg_affine_pairs": (c_int, [u64, c_int, f64p, vp, u32]),
     "zkp_scalars_load": (c_int, [vp, u64, u64p]),
     "zkp_free": (c_int, [u64]),
     "zkp_g1_msm_table": (c_int, [u64, u64, vp, u64, vp, intp]),

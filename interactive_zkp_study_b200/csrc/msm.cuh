@@ -382,6 +382,61 @@ __global__ void __launch_bounds__(128) msm_bucket_fold_heavy_kernel(const XYZZ<F
   }
 }
 
+// EXPERIMENT: pairwise affine additions with a shared inversion (see zkp_dbg_affine_pairs).
+// Thread t owns outputs t, t + T, ... (B of them).  Pass 1 multiplies the denominators up, one inversion,
+// pass 2 walks back: lambda = num / den, x3 = lambda^2 - x1 - x2, y3 = lambda (x1 - x3) - y1.
+// den = x2 - x1, or 2 y1 when the points are equal (num = 3 x1^2), or 1 when the sum is trivial.
+template <class F, int B>
+__global__ void __launch_bounds__(128) affine_pair_add_kernel(const Affine<F>* __restrict__ in, uint32_t n_out,
+                                                               Affine<F>* __restrict__ out) {
+  const uint32_t T = gridDim.x * blockDim.x;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  F pre[B];
+  F acc = F::one();
+#pragma unroll 1
+  for (int k = 0; k < B; k++) {
+    uint32_t i = t + (uint32_t)k * T;
+    pre[k] = acc;
+    if (i < n_out) {
+      F x1 = in[2 * i].x, x2 = in[2 * i + 1].x;
+      F d = x2 - x1;
+      if (d.is_zero()) {
+        F y1 = in[2 * i].y, y2 = in[2 * i + 1].y;
+        d = (y1 == y2 && !y1.is_zero()) ? y1.dbl() : F::one();
+      }
+      if (in[2 * i].is_inf() || in[2 * i + 1].is_inf()) d = F::one();
+      acc = acc * d;
+    }
+  }
+  F inv = acc.inv();
+#pragma unroll 1
+  for (int k = B - 1; k >= 0; k--) {
+    uint32_t i = t + (uint32_t)k * T;
+    if (i >= n_out) continue;
+    Affine<F> p = in[2 * i], q = in[2 * i + 1];
+    Affine<F> r;
+    if (p.is_inf()) { out[i] = q; continue; }
+    if (q.is_inf()) { out[i] = p; continue; }
+    F d = q.x - p.x, num = q.y - p.y;
+    if (d.is_zero()) {
+      if (num.is_zero() && !p.y.is_zero()) {
+        d = p.y.dbl();
+        F xx = p.x.sqr();
+        num = xx.dbl() + xx;
+      } else {
+        out[i] = Affine<F>::inf();
+        continue;
+      }
+    }
+    F dinv = inv * pre[k];
+    inv = inv * d;
+    F lam = num * dinv;
+    r.x = lam.sqr() - p.x - q.x;
+    r.y = lam * (p.x - r.x) - p.y;
+    out[i] = r;
+  }
+}
+
 // Window-precomputed tables: T[w][i] = 2^(c*w) * P_i, so every window's digits weigh the same and all
 // windows share ONE bucket set (no per-window sums, no final doubling chain).
 // cur[i] <- 2^c * cur[i]   (XYZZ, c doublings)

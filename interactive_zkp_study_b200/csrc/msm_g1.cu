@@ -64,6 +64,48 @@ int zkp_table_download(uint64_t table, uint64_t offset, uint64_t n, uint8_t* out
   });
 }
 
+// EXPERIMENT (not on any product path): out[i] = P[2i] + P[2i+1] in affine coordinates with one shared
+// inversion per `batch` additions per thread (Montgomery's trick), to measure what a batched-affine
+// bucket accumulation could reach against the XYZZ mixed addition.  ms: kernel time; out_first: the
+// first `n_check` sums (canonical) for a correctness check.
+int zkp_dbg_affine_pairs(uint64_t table, int batch, double* ms, uint8_t* out_first, uint32_t n_check) {
+  return guarded([&](Context& c) {
+    Resource* t = need(table, HandleKind::G1Table, "zkp_dbg_affine_pairs");
+    if (t->pre_c || !ms) throw InvalidArgument("zkp_dbg_affine_pairs: needs a plain table");
+    uint32_t n_out = (uint32_t)(t->n / 2);
+    DevBuf out;
+    out.reserve((size_t)n_out * sizeof(Affine<Fp>));
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+      CUDA_CHECK(cudaEventRecord(e0, c.stream));
+      uint32_t threads = ceil_div(n_out, (uint32_t)batch);
+      if (batch == 8) affine_pair_add_kernel<Fp, 8><<<ceil_div(threads, 128), 128, 0, c.stream>>>(t->buf.as<Affine<Fp>>(), n_out, out.as<Affine<Fp>>());
+      else if (batch == 16) affine_pair_add_kernel<Fp, 16><<<ceil_div(threads, 128), 128, 0, c.stream>>>(t->buf.as<Affine<Fp>>(), n_out, out.as<Affine<Fp>>());
+      else if (batch == 32) affine_pair_add_kernel<Fp, 32><<<ceil_div(threads, 128), 128, 0, c.stream>>>(t->buf.as<Affine<Fp>>(), n_out, out.as<Affine<Fp>>());
+      else throw InvalidArgument("zkp_dbg_affine_pairs: batch must be 8, 16 or 32");
+      CUDA_CHECK_LAUNCH();
+      CUDA_CHECK(cudaEventRecord(e1, c.stream));
+      CUDA_CHECK(cudaEventSynchronize(e1));
+      float m;
+      CUDA_CHECK(cudaEventElapsedTime(&m, e0, e1));
+      if (m < best) best = m;
+    }
+    *ms = best;
+    if (out_first && n_check) {
+      if (n_check > n_out) n_check = n_out;
+      fe_from_mont_kernel<Fp><<<ceil_div(n_check * 2, 256), 256, 0, c.stream>>>(out.as<Fp>(), (uint64_t)n_check * 2);
+      CUDA_CHECK(cudaMemcpyAsync(out_first, out.p, (size_t)n_check * 64, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    out.release();
+  });
+}
+
 // window width of a precomputed table (0 = plain layout)
 int zkp_table_window_bits(uint64_t table, int* window_bits) {
   return guarded([&](Context&) {
