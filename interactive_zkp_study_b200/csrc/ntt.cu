@@ -55,11 +55,6 @@ __global__ void twiddle_table_kernel(const Fr* __restrict__ pow2tab, uint32_t co
   if (i < count) out[i] = pow_from_table(pow2tab, i);
 }
 
-__global__ void scale_by_powers_kernel(Fr* __restrict__ v, uint64_t n, const Fr* __restrict__ pow2tab) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && i) v[i] = v[i] * pow_from_table(pow2tab, (uint32_t)i);
-}
-
 // ------------------------------------------------------------------ the pass kernel
 struct NttPassArgs {
   const Fr* src;
@@ -70,8 +65,10 @@ struct NttPassArgs {
   uint32_t S;         // stages in this pass
   uint32_t log_g;     // log2 of sub-transforms per tile; tile = 2^(S+log_g) elements
   int bitrev_in;      // first pass: gather src[bitrev(i)]
-  const Fr* pre_pow2;   // forward coset: multiply input j (natural index) by shift^j   (first pass)
-  const Fr* post_pow2;  // inverse coset: multiply output j by shift^-j                 (last pass)
+  // coset scalings as two-level power tables: shift^j = lo[j & 1023] * hi[j >> 10]  (2 products per element
+  // instead of a square-and-multiply walk over the bits of j: ~11 products, as much as the transform itself)
+  const Fr* pre_pow;    // forward coset: multiply input j (natural index) by shift^j   (first pass)
+  const Fr* post_pow;   // inverse coset: multiply output j by shift^-j                 (last pass)
   int scale_n_inv;      // last pass of an inverse: multiply by n^-1
   Fr n_inv;             // Montgomery
 };
@@ -124,7 +121,7 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassArgs a) {
       // batched transforms: the permutation acts on the index inside one transform (low log_n bits)
       uint32_t src_i = a.log_n ? (__brev((uint32_t)gi & (n - 1)) >> (32 - a.log_n)) : 0;
       x = a.src[(gi & ~(uint64_t)(n - 1)) | src_i];
-      if (a.pre_pow2 && src_i) x = x * pow_from_table(a.pre_pow2, src_i);
+      if (a.pre_pow && src_i) x = x * power_at(a.pre_pow, src_i);
     } else {
       x = a.src[gi];
     }
@@ -195,7 +192,7 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassArgs a) {
     if (last) {
       if (a.scale_n_inv) x = x * a.n_inv;
       uint32_t li = (uint32_t)gi & (n - 1);
-      if (a.post_pow2 && li) x = x * pow_from_table(a.post_pow2, li);
+      if (a.post_pow && li) x = x * power_at(a.post_pow, li);
     }
     a.dst[gi] = x;
   }
@@ -254,11 +251,29 @@ static const Fr* twiddle_table(Context& c, const FrBytes& omega, bool inverted, 
   return buf.as<Fr>();
 }
 
-int scale_by_powers(Context& c, Fr* v, uint64_t n, const Fr* pow2tab) {
-  if (n <= 1) return 0;
-  scale_by_powers_kernel<<<ceil_div(n, 256), 256, 0, c.stream>>>(v, n, pow2tab);
+// lo[j] = x^j (j < 1024) followed by hi[k] = x^(1024 k) (k < max(1, 2^log_n / 1024)), Montgomery; cached per (x, log_n)
+static std::map<std::vector<uint8_t>, DevBuf> g_coset_cache;
+const Fr* power_table(Context& c, const FrBytes& x, bool inverted, uint32_t log_n, int* launches) {
+  std::vector<uint8_t> key(x.b, x.b + 32);
+  key.push_back(inverted ? 1 : 0);
+  key.push_back((uint8_t)log_n);
+  auto it = g_coset_cache.find(key);
+  if (it != g_coset_cache.end()) return it->second.as<Fr>();
+  if (g_coset_cache.size() >= 64) {
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    for (auto& kv : g_coset_cache) kv.second.release();
+    g_coset_cache.clear();
+  }
+  const Fr* p2 = pow2_table(c, x, inverted, launches);
+  uint32_t hi = log_n > 10 ? (1u << (log_n - 10)) : 1u;
+  DevBuf& buf = g_coset_cache[key];
+  buf.reserve((size_t)(1024 + hi) * sizeof(Fr));
+  twiddle_table_kernel<<<4, 256, 0, c.stream>>>(p2, 1024, buf.as<Fr>());
   CUDA_CHECK_LAUNCH();
-  return 1;
+  twiddle_table_kernel<<<ceil_div(hi, 256), 256, 0, c.stream>>>(p2 + 10, hi, buf.as<Fr>() + 1024);  // (x^1024)^k
+  CUDA_CHECK_LAUNCH();
+  if (launches) (*launches) += 2;
+  return buf.as<Fr>();
 }
 
 // n^-1 mod r in Montgomery form, computed on the host: n = 2^k so n^-1 = ((r+1)/2)^k; the host only
@@ -296,14 +311,14 @@ int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes&
   const Fr* pre = nullptr;
   const Fr* post = nullptr;
   if (coset_shift) {
-    if (inverse) post = pow2_table(c, *coset_shift, true, &launches);
-    else pre = pow2_table(c, *coset_shift, false, &launches);
+    if (inverse) post = power_table(c, *coset_shift, true, log_n, &launches);
+    else pre = power_table(c, *coset_shift, false, log_n, &launches);
   }
   NttPassArgs a;
   a.tw = tw;
   a.log_n = log_n;
-  a.pre_pow2 = pre;
-  a.post_pow2 = post;
+  a.pre_pow = pre;
+  a.post_pow = post;
   a.scale_n_inv = inverse ? 1 : 0;
   host_n_inv_mont(log_n, &a.n_inv);
 
@@ -332,7 +347,7 @@ int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes&
   }
   uint32_t done = S1;
   a.bitrev_in = 0;
-  a.pre_pow2 = nullptr;
+  a.pre_pow = nullptr;
   a.src = scratch;
   a.dst = scratch;  // in place: every tile reads and writes exactly its own elements
   while (done < log_n) {

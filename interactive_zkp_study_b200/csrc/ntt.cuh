@@ -24,7 +24,15 @@ int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes&
 // x^(2^k), k < 32, in Montgomery form on the device (cached per x); `inverted`: of x^-1 instead.
 const Fr* pow2_table(Context& c, const FrBytes& x, bool inverted, int* launches);
 
-// v[i] *= x^i   (powers from a pow2 table)
-int scale_by_powers(Context& c, Fr* v, uint64_t n, const Fr* pow2tab);
+// Two-level power table of x (or x^-1) covering exponents below 2^log_n: 1024 low powers x^j followed by
+// the high powers x^(1024 k); x^e = lo[e & 1023] * hi[e >> 10], two products instead of a
+// square-and-multiply walk over the bits of e.  Montgomery form, cached per (x, inverted, log_n).
+const Fr* power_table(Context& c, const FrBytes& x, bool inverted, uint32_t log_n, int* launches);
+__device__ __forceinline__ Fr power_at(const Fr* __restrict__ tab, uint32_t e) {
+  Fr lo = tab[e & 1023u];
+  uint32_t h = e >> 10;
+  return h ? lo * tab[1024 + h] : lo;
+}
+
 
 }  // namespace zkp

@@ -359,31 +359,28 @@ __global__ void fr_add_const_kernel(Fr* __restrict__ v, Fr k, uint64_t n) {
   uint64_t i = IDX64;
   if (i < n) v[i] = v[i] + k;
 }
-// v[i] = first * base^i (canonical out); pow2tab: base^(2^k) Montgomery
-__global__ void fr_fill_powers_kernel(Fr* __restrict__ v, uint64_t n, Fr first, const Fr* __restrict__ pow2tab) {
+// v[i] = first * base^i (canonical out); ptab: two-level power table of base (ntt.cuh)
+__global__ void fr_fill_powers_kernel(Fr* __restrict__ v, uint64_t n, Fr first, const Fr* __restrict__ ptab) {
   uint64_t i = IDX64;
   if (i >= n) return;
-  Fr r = first;
-  uint64_t e = i;
-  for (int k = 0; e; k++, e >>= 1)
-    if (e & 1) r = r * pow2tab[k];
-  v[i] = r;
+  v[i] = i ? first * power_at(ptab, (uint32_t)i) : first;
+}
+// v[i] *= x^i
+__global__ void fr_scale_powers_kernel(Fr* __restrict__ v, uint64_t n, const Fr* __restrict__ ptab) {
+  uint64_t i = IDX64;
+  if (i < n && i) v[i] = v[i] * power_at(ptab, (uint32_t)i);
 }
 __global__ void fr_is_zero_kernel(const Fr* __restrict__ v, uint64_t n, int* __restrict__ flag) {
   uint64_t i = IDX64;
   if (i < n && !v[i].is_zero()) *flag = 0;
 }
 // q_k = zeta^-(k+1) * (T - P_k - d_k), d_j = c_j zeta^j, P = exclusive prefix sums of d, T = sum d.
-// zinv_pow2: (zeta^-1)^(2^k) Montgomery.  All values canonical.
+// zinv_tab: two-level power table of zeta^-1 (ntt.cuh).  All values canonical.
 __global__ void fr_div_linear_finish_kernel(const Fr* __restrict__ d, const Fr* __restrict__ P, const Fr* __restrict__ T,
-                                            const Fr* __restrict__ zinv_pow2, uint64_t n_out, Fr* __restrict__ q) {
+                                            const Fr* __restrict__ zinv_tab, uint64_t n_out, Fr* __restrict__ q) {
   uint64_t k = IDX64;
   if (k >= n_out) return;
-  Fr s = *T - P[k] - d[k];
-  uint64_t e = k + 1;
-  for (int b = 0; e; b++, e >>= 1)
-    if (e & 1) s = s * zinv_pow2[b];
-  q[k] = s;
+  q[k] = (*T - P[k] - d[k]) * power_at(zinv_tab, (uint32_t)(k + 1));
 }
 
 // PLONK grand-product factors (permutation.py:120-135), canonical in/out:
@@ -391,15 +388,12 @@ __global__ void fr_div_linear_finish_kernel(const Fr* __restrict__ d, const Fr* 
 //   den_i = (a_i + beta s1_i + gamma)(b_i + beta s2_i + gamma)(c_i + beta s3_i + gamma)
 __global__ void plonk_perm_terms_kernel(const Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ c,
                                         const Fr* __restrict__ s1, const Fr* __restrict__ s2, const Fr* __restrict__ s3,
-                                        uint64_t n, const Fr* __restrict__ omega_pow2, Fr beta_c, Fr gamma_c,
+                                        uint64_t n, const Fr* __restrict__ omega_tab, Fr beta_c, Fr gamma_c,
                                         Fr* __restrict__ num, Fr* __restrict__ den) {
   uint64_t i = IDX64;
   if (i >= n) return;
   Fr beta = beta_c.to_mont(), gamma = gamma_c.to_mont();
-  Fr w = Fr::one();
-  uint64_t e = i;
-  for (int k = 0; e; k++, e >>= 1)
-    if (e & 1) w = w * omega_pow2[k];
+  Fr w = power_at(omega_tab, (uint32_t)i);  // two-level power table (ntt.cuh); entry 0 is one
   Fr bw = beta * w;
   Fr am = a[i].to_mont() + gamma, bm = b[i].to_mont() + gamma, cm = c[i].to_mont() + gamma;
   Fr nu = (am + bw) * (bm + bw.dbl()) * (cm + bw.dbl() + bw);
@@ -943,7 +937,8 @@ int zkp_scalars_fill_powers(uint64_t h, uint64_t off, uint64_t n, const uint8_t 
     FrBytes bb;
     memcpy(bb.b, base, 32);
     int launches = 0;
-    const Fr* tab = pow2_table(c, bb, false, &launches);
+    if (n > (uint64_t(1) << 28)) throw InvalidArgument("zkp_scalars_fill_powers: n must be <= 2^28");
+    const Fr* tab = power_table(c, bb, false, log2_ceil(n), &launches);
     fr_fill_powers_kernel<<<GRID_1D(n)>>>(d, n, fr_from_bytes(first), tab);
     CUDA_CHECK_LAUNCH();
     c.launches += launches + 1;
@@ -1022,14 +1017,16 @@ int zkp_fr_div_linear_dev(uint64_t src, uint64_t src_off, uint64_t n, const uint
     FrBytes zb;
     memcpy(zb.b, zeta, 32);
     int launches = 0;
-    const Fr* zp = pow2_table(c, zb, false, &launches);
-    const Fr* zip = pow2_table(c, zb, true, &launches);
+    if (n > (uint64_t(1) << 28)) throw InvalidArgument("zkp_fr_div_linear_dev: n must be <= 2^28");
+    const Fr* zp = power_table(c, zb, false, log2_ceil(n + 1), &launches);
+    const Fr* zip = power_table(c, zb, true, log2_ceil(n + 1), &launches);
     Fr* d = g_arena.alloc(n);
     Fr* P = g_arena.alloc(n);
     Fr* T = g_arena.alloc(1);
     CUDA_CHECK(cudaMemcpyAsync(d, p, n * 32, cudaMemcpyDeviceToDevice, c.stream));
-    launches += scale_by_powers(c, d, n, zp);
-    launches += scan_dev<true>(c, d, n, P, T);
+    fr_scale_powers_kernel<<<GRID_1D(n)>>>(d, n, zp);
+    CUDA_CHECK_LAUNCH();
+    launches += 1 + scan_dev<true>(c, d, n, P, T);
     fr_div_linear_finish_kernel<<<GRID_1D(n - 1)>>>(d, P, T, zip, n - 1, q);
     CUDA_CHECK_LAUNCH();
     c.launches += launches + 1;
@@ -1046,7 +1043,7 @@ int zkp_plonk_perm_terms_dev(uint64_t a, uint64_t b, uint64_t cc, uint64_t s1, u
     FrBytes ob;
     memcpy(ob.b, omega, 32);
     int launches = 0;
-    const Fr* tab = pow2_table(c, ob, false, &launches);
+    const Fr* tab = power_table(c, ob, false, log2_ceil(n), &launches);
     plonk_perm_terms_kernel<<<GRID_1D(n)>>>(hptr(a, 0, n, w), hptr(b, 0, n, w), hptr(cc, 0, n, w), hptr(s1, 0, n, w),
                                             hptr(s2, 0, n, w), hptr(s3, 0, n, w), n, tab, fr_from_bytes(beta),
                                             fr_from_bytes(gamma), hptr(num, 0, n, w), hptr(den, 0, n, w));
