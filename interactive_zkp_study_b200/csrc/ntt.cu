@@ -259,9 +259,13 @@ const Fr* power_table(Context& c, const FrBytes& x, bool inverted, uint32_t log_
   key.push_back((uint8_t)log_n);
   auto it = g_coset_cache.find(key);
   if (it != g_coset_cache.end()) return it->second.as<Fr>();
-  if (g_coset_cache.size() >= 64) {
+  if (g_coset_cache.size() >= 64) {  // per-proof challenges (zeta, zeta*omega, ...) would otherwise accumulate
+    // two generations: a table handed out earlier in the current call stays valid until the NEXT purge
+    static std::vector<DevBuf> graveyard;
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
-    for (auto& kv : g_coset_cache) kv.second.release();
+    for (auto& b : graveyard) b.release();
+    graveyard.clear();
+    for (auto& kv : g_coset_cache) graveyard.push_back(kv.second);
     g_coset_cache.clear();
   }
   const Fr* p2 = pow2_table(c, x, inverted, launches);
