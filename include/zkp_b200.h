@@ -156,7 +156,8 @@ int zkp_groth16_quotient(const uint8_t* a, const uint8_t* b, const uint8_t* c, u
 /* The same on device-resident coefficient vectors (the 2^20-constraint configuration cannot go through
  * the reference's dense numWires x numGates lists: SURVEY F12).  Returns two new scalar handles
  * (quotient: 2*len - z_len coefficients; remainder: z_len - 1).  The inverse power series of the
- * reversed divisor is cached per z handle (Z(x) is fixed per circuit). */
+ * reversed divisor is cached per z handle (Z(x) is fixed per circuit).  rem_out may be NULL: the
+ * remainder (zero for a satisfied instance; three more transforms) is then not computed. */
 int zkp_groth16_quotient_dev(uint64_t a, uint64_t b, uint64_t c, uint64_t len, uint64_t z, uint64_t z_len,
                              uint64_t* h_out, uint64_t* rem_out);
 /* Device-resident Fr vector utilities used to assemble MSM scalar vectors without leaving HBM. */
@@ -177,6 +178,13 @@ int zkp_scalars_convert(uint64_t h, uint64_t off, uint64_t n, int to_montgomery)
 int zkp_scalars_is_zero(uint64_t h, uint64_t off, uint64_t n, int* out_all_zero);
 int zkp_fr_batch_inverse_dev(uint64_t h, uint64_t off, uint64_t n, int montgomery);
 int zkp_fr_scan_dev(int op, uint64_t dst, uint64_t dst_off, uint64_t src, uint64_t src_off, uint64_t n); /* 0 product, 1 sum */
+/* up to 16 polynomials evaluated in the same launches, item k at xs[k] (round4.py:39-81: six evaluations) */
+int zkp_fr_poly_eval_multi_dev(uint32_t count, const uint64_t* handles, const uint64_t* offs, const uint64_t* lens,
+                               const uint8_t* xs, uint8_t* out);
+/* dst[i] = sum_k coeffs[k] * src_k[i], i < n (items shorter than n contribute to their own length): the
+ * scalar-times-polynomial sums of round5.py:90-160 in one pass; dst must not overlap a source */
+int zkp_fr_lincomb_dev(uint64_t dst, uint64_t dst_off, uint64_t n, uint32_t count, const uint64_t* handles,
+                       const uint64_t* offs, const uint64_t* lens, const uint8_t* coeffs);
 /* (p(x) - p(zeta)) / (x - zeta): poly_div by a linear factor (round5.py:165-171, kzg.py:95-104) */
 int zkp_fr_div_linear_dev(uint64_t src, uint64_t src_off, uint64_t n, const uint8_t zeta[32], uint64_t dst,
                           uint64_t dst_off);

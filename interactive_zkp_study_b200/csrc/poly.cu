@@ -209,6 +209,56 @@ static int poly_eval_dev_impl(Context& c, const Fr* coeffs, uint64_t n, const ui
   return launches;
 }
 
+// Several polynomials evaluated in the same launches (blockIdx.y = item): PLONK round 4 needs six
+// evaluations of ~n coefficients (round4.py:39-81), each only a few latency-bound Horner levels deep.
+static constexpr int MULTI_MAX = 16;
+struct MultiEvalArgs {
+  const Fr* coeffs[MULTI_MAX];
+  uint64_t n[MULTI_MAX];
+  int point[MULTI_MAX];  // which of the evaluation points
+};
+__global__ void horner_powers_multi_kernel(const Fr* __restrict__ x_canon, int points, Fr* __restrict__ xs, int levels) {
+  int p = (int)IDX64;
+  if (p >= points) return;
+  Fr x = x_canon[p].to_mont();
+  for (int l = 0; l < levels; l++) {
+    xs[p * levels + l] = x;
+    for (int k = 1; k < HORNER_CHUNK; k <<= 1) x = x.sqr();
+  }
+}
+__global__ void horner_multi_kernel(MultiEvalArgs a, int level, int levels, const Fr* __restrict__ xs,
+                                    const Fr* __restrict__ prev, uint64_t stride_prev, Fr* __restrict__ cur,
+                                    uint64_t stride_cur) {
+  const int k = blockIdx.y;
+  uint64_t m = a.n[k];
+  for (int l = 0; l < level; l++) m = (m + HORNER_CHUNK - 1) / HORNER_CHUNK;
+  const Fr* in = level == 0 ? a.coeffs[k] : prev + (uint64_t)k * stride_prev;
+  uint64_t j = IDX64;
+  uint64_t beg = j * HORNER_CHUNK;
+  if (beg >= m) return;
+  uint64_t end = beg + HORNER_CHUNK < m ? beg + HORNER_CHUNK : m;
+  Fr x = xs[a.point[k] * levels + level];
+  Fr acc = Fr::zero();
+  for (uint64_t i = end; i > beg; i--) acc = acc * x + in[i - 1];
+  cur[(uint64_t)k * stride_cur + j] = acc;
+}
+
+// dst[i] = sum_k coeff_k * src_k[i] over the items long enough to have an i-th element (canonical in/out)
+struct LinCombArgs {
+  const Fr* src[MULTI_MAX];
+  uint64_t len[MULTI_MAX];
+  Fr coeff[MULTI_MAX];  // Montgomery
+  int count;
+};
+__global__ void fr_lincomb_kernel(LinCombArgs a, uint64_t n, Fr* __restrict__ dst) {
+  uint64_t i = IDX64;
+  if (i >= n) return;
+  Fr acc = Fr::zero();
+  for (int k = 0; k < a.count; k++)
+    if (i < a.len[k]) acc = acc + a.src[k][i] * a.coeff[k];
+  dst[i] = acc;
+}
+
 // out[j] = sum_i vec[i] * mat[i*cols + j]   (canonical in/out)
 __global__ void fr_vec_matrix_kernel(const Fr* __restrict__ vec, const Fr* __restrict__ mat, uint64_t rows, uint64_t cols,
                                      Fr* __restrict__ out) {
@@ -538,7 +588,7 @@ static int poly_divmod_dev(Context& c, const Fr* a, uint64_t la, const Fr* b, ui
   fr_reverse_kernel<<<GRID_1D(m)>>>(qr, m, m, q);
   CUDA_CHECK_LAUNCH();
   launches++;
-  if (lb >= 2) {
+  if (lb >= 2 && r) {  // r == nullptr: the caller only wants the quotient
     // r = (a - b q) mod (x^N - 1), N >= lb-1: exact because deg r < lb-1 <= N
     uint64_t lr = lb - 1;
     uint32_t lg = log2_ceil(lr);
@@ -814,7 +864,7 @@ int zkp_groth16_quotient_dev(uint64_t a, uint64_t b, uint64_t cc, uint64_t len, 
     Resource* rb = need(b, HandleKind::Scalars, "zkp_groth16_quotient_dev");
     Resource* rc = need(cc, HandleKind::Scalars, "zkp_groth16_quotient_dev");
     Resource* rz = need(z, HandleKind::Scalars, "zkp_groth16_quotient_dev");
-    if (!h_out || !rem_out || !len || z_len < 2) throw InvalidArgument("zkp_groth16_quotient_dev: bad argument");
+    if (!h_out || !len || z_len < 2) throw InvalidArgument("zkp_groth16_quotient_dev: bad argument");
     if (len > ra->n || len > rb->n || len > rc->n || z_len > rz->n) throw InvalidArgument("zkp_groth16_quotient_dev: length exceeds a vector");
     uint64_t lp = 2 * len - 1;
     if (lp < z_len) throw InvalidArgument("zkp_groth16_quotient_dev: divisor longer than the product");
@@ -848,21 +898,29 @@ int zkp_groth16_quotient_dev(uint64_t a, uint64_t b, uint64_t cc, uint64_t len, 
     hq->kind = HandleKind::Scalars;
     hq->n = m;
     hq->buf.reserve_pooled(m * 32);
-    auto hr = std::make_unique<Resource>();
-    hr->kind = HandleKind::Scalars;
-    hr->n = z_len - 1;
-    hr->buf.reserve_pooled(z_len * 32);
-    launches += poly_divmod_dev(c, dp, lp, dz, z_len, hq->buf.as<Fr>(), hr->buf.as<Fr>(), false,
+    // rem_out == NULL: the prover only needs H (the remainder of a satisfied instance is zero and costs
+    // three more transforms to compute)
+    std::unique_ptr<Resource> hr;
+    if (rem_out) {
+      hr = std::make_unique<Resource>();
+      hr->kind = HandleKind::Scalars;
+      hr->n = z_len - 1;
+      hr->buf.reserve_pooled(z_len * 32);
+    }
+    launches += poly_divmod_dev(c, dp, lp, dz, z_len, hq->buf.as<Fr>(), hr ? hr->buf.as<Fr>() : nullptr, false,
                                 g_div_cache.inv.as<Fr>(), &g_div_cache.filled);
     fr_from_mont_kernel<<<GRID_1D(m)>>>(hq->buf.as<Fr>(), m, hq->buf.as<Fr>());
     CUDA_CHECK_LAUNCH();
-    fr_from_mont_kernel<<<GRID_1D(z_len - 1)>>>(hr->buf.as<Fr>(), z_len - 1, hr->buf.as<Fr>());
-    CUDA_CHECK_LAUNCH();
-    launches += 2;
+    launches++;
+    if (hr) {
+      fr_from_mont_kernel<<<GRID_1D(z_len - 1)>>>(hr->buf.as<Fr>(), z_len - 1, hr->buf.as<Fr>());
+      CUDA_CHECK_LAUNCH();
+      launches++;
+    }
     c.launches += launches;
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
     *h_out = registry().put(std::move(hq));
-    *rem_out = registry().put(std::move(hr));
+    if (hr) *rem_out = registry().put(std::move(hr));
   });
 }
 
@@ -984,6 +1042,90 @@ int zkp_fr_batch_inverse_dev(uint64_t h, uint64_t off, uint64_t n, int montgomer
     fr_batch_inverse_kernel<<<ceil_div(T, 128), 128, 0, c.stream>>>(d, n, T, montgomery ? 1 : 0, tmp);
     CUDA_CHECK_LAUNCH();
     CUDA_CHECK(cudaMemcpyAsync(d, tmp, n * 32, cudaMemcpyDeviceToDevice, c.stream));
+    c.launches++;
+  });
+}
+
+int zkp_fr_poly_eval_multi_dev(uint32_t count, const uint64_t* handles, const uint64_t* offs, const uint64_t* lens,
+                               const uint8_t* xs, uint8_t* out) {
+  return guarded([&](Context& c) {
+    if (count == 0) return;
+    if (count > (uint32_t)MULTI_MAX || !handles || !offs || !lens || !xs || !out)
+      throw InvalidArgument("zkp_fr_poly_eval_multi_dev: 1..16 items, no null arguments");
+    ArenaScope scope;
+    MultiEvalArgs a;
+    std::vector<FrBytes> points;
+    uint64_t max_n = 1;
+    for (uint32_t k = 0; k < count; k++) {
+      if (!lens[k]) throw InvalidArgument("zkp_fr_poly_eval_multi_dev: empty polynomial");
+      a.coeffs[k] = hptr(handles[k], offs[k], lens[k], "zkp_fr_poly_eval_multi_dev");
+      a.n[k] = lens[k];
+      if (lens[k] > max_n) max_n = lens[k];
+      FrBytes x;
+      memcpy(x.b, xs + 32 * k, 32);
+      size_t p = 0;
+      while (p < points.size() && !(points[p] == x)) p++;
+      if (p == points.size()) points.push_back(x);
+      a.point[k] = (int)p;
+    }
+    int levels = 0;
+    for (uint64_t m = max_n; m > 1; m = (m + HORNER_CHUNK - 1) / HORNER_CHUNK) levels++;
+    if (levels == 0) levels = 1;
+    Fr* xc = g_arena.alloc(points.size());
+    Fr* xp = g_arena.alloc(points.size() * levels);
+    CUDA_CHECK(cudaMemcpyAsync(xc, points.data(), points.size() * 32, cudaMemcpyHostToDevice, c.stream));
+    horner_powers_multi_kernel<<<1, 32, 0, c.stream>>>(xc, (int)points.size(), xp, levels);
+    CUDA_CHECK_LAUNCH();
+    int launches = 1;
+    const Fr* prev = nullptr;
+    uint64_t stride_prev = 0, m = max_n;
+    Fr* cur = nullptr;
+    for (int l = 0; l < levels; l++) {
+      uint64_t np = (m + HORNER_CHUNK - 1) / HORNER_CHUNK;
+      cur = g_arena.alloc(np * count);
+      dim3 grid((unsigned)ceil_div(np, (uint64_t)256), count);
+      horner_multi_kernel<<<grid, 256, 0, c.stream>>>(a, l, levels, xp, prev, stride_prev, cur, np);
+      CUDA_CHECK_LAUNCH();
+      launches++;
+      prev = cur;
+      stride_prev = np;
+      m = np;
+    }
+    // m == 1: the results are contiguous
+    CUDA_CHECK(cudaMemcpyAsync(out, cur, (size_t)count * 32, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.launches += launches;
+  });
+}
+
+int zkp_fr_lincomb_dev(uint64_t dst, uint64_t dst_off, uint64_t n, uint32_t count, const uint64_t* handles,
+                       const uint64_t* offs, const uint64_t* lens, const uint8_t* coeffs) {
+  return guarded([&](Context& c) {
+    if (!n) return;
+    if (count > (uint32_t)MULTI_MAX || (count && (!handles || !offs || !lens || !coeffs)))
+      throw InvalidArgument("zkp_fr_lincomb_dev: at most 16 items, no null arguments");
+    ArenaScope scope;
+    Fr* d = hptr(dst, dst_off, n, "zkp_fr_lincomb_dev");
+    LinCombArgs a;
+    a.count = (int)count;
+    if (count) {
+      // coefficients -> Montgomery on the device in one go
+      Fr* dk = g_arena.alloc(count);
+      CUDA_CHECK(cudaMemcpyAsync(dk, coeffs, (size_t)count * 32, cudaMemcpyHostToDevice, c.stream));
+      fr_to_mont_kernel<<<1, 32, 0, c.stream>>>(dk, count, dk);
+      CUDA_CHECK_LAUNCH();
+      CUDA_CHECK(cudaMemcpyAsync(a.coeff, dk, (size_t)count * 32, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      c.launches++;
+    }
+    for (uint32_t k = 0; k < count; k++) {
+      if (lens[k] > n) throw InvalidArgument("zkp_fr_lincomb_dev: an item is longer than the destination");
+      a.src[k] = hptr(handles[k], offs[k], lens[k], "zkp_fr_lincomb_dev");
+      if (a.src[k] < d + n && d < a.src[k] + lens[k]) throw InvalidArgument("zkp_fr_lincomb_dev: destination overlaps a source");
+      a.len[k] = lens[k];
+    }
+    fr_lincomb_kernel<<<GRID_1D(n)>>>(a, n, d);
+    CUDA_CHECK_LAUNCH();
     c.launches++;
   });
 }

@@ -266,11 +266,13 @@ def fr_poly_eval_dev(h, off, n, x):
     return int.from_bytes(out, "little")
 
 
-def groth16_quotient_dev(a, b, c, length, z, z_len):
+def groth16_quotient_dev(a, b, c, length, z, z_len, want_remainder=True):
+    """(H, remainder) handles; with want_remainder=False only H is computed and (H, None) returned."""
     hq, hr = ctypes.c_uint64(), ctypes.c_uint64()
     check(_lib.lib().zkp_groth16_quotient_dev(a.handle, b.handle, c.handle, length, z.handle, z_len,
-                                              ctypes.byref(hq), ctypes.byref(hr)))
-    return DeviceHandle(hq.value, 2 * length - z_len, "fr"), DeviceHandle(hr.value, z_len - 1, "fr")
+                                              ctypes.byref(hq), ctypes.byref(hr) if want_remainder else None))
+    return (DeviceHandle(hq.value, 2 * length - z_len, "fr"),
+            DeviceHandle(hr.value, z_len - 1, "fr") if want_remainder else None)
 
 
 def g1_fixed_base_mul_dev(base_bytes, scalars, n):
@@ -430,6 +432,28 @@ def vec_op_dev(op, dst, dst_off, a, a_off, b, b_off, n):
 
 def axpy_dev(dst, dst_off, k, src, src_off, n):
     check(_lib.lib().zkp_fr_axpy_dev(dst.handle, dst_off, buf(fe_bytes(k)), src.handle, src_off, n))
+
+
+def fr_poly_eval_multi_dev(items):
+    """items = [(handle, offset, length, x)] (at most 16) -> the values, one batched set of launches."""
+    k = len(items)
+    if not k:
+        return []
+    arr = lambda vals: (ctypes.c_uint64 * k)(*vals)
+    out = bytearray(32 * k)
+    xs = b"".join(fe_bytes(it[3]) for it in items)
+    check(_lib.lib().zkp_fr_poly_eval_multi_dev(k, arr([it[0].handle for it in items]), arr([it[1] for it in items]),
+                                                arr([it[2] for it in items]), buf(xs), buf(out)))
+    return fr_vec_from_bytes(bytes(out))
+
+
+def lincomb_dev(dst, dst_off, n, items):
+    """dst[dst_off + i] = sum over items (coeff, handle, offset, length) of coeff * handle[offset + i], i < n."""
+    k = len(items)
+    arr = lambda vals: (ctypes.c_uint64 * max(k, 1))(*vals)
+    check(_lib.lib().zkp_fr_lincomb_dev(dst.handle, dst_off, n, k, arr([it[1].handle for it in items]),
+                                        arr([it[2] for it in items]), arr([it[3] for it in items]),
+                                        buf(b"".join(fe_bytes(it[0]) for it in items)) if k else None))
 
 
 def scalars_add_const(h, off, n, k):

@@ -55,7 +55,8 @@ def prove(key, uA, uB, uC, Z, rx_priv, r, s, keep_quotient=False):
     reference's point types (and the quotient / remainder handles when keep_quotient)."""
     k, mp = key.k, key.m_priv
     r, s = int(r) % R, int(s) % R
-    hq, hr = native.groth16_quotient_dev(uA, uB, uC, k, Z, k + 1)     # H: k-1 coefficients, rem: k
+    # H: k-1 coefficients; the remainder (k coefficients, zero for a satisfied instance) only on request
+    hq, hr = native.groth16_quotient_dev(uA, uB, uC, k, Z, k + 1, want_remainder=keep_quotient)
     one = native.fr_vec_bytes([1])
     scA = native.scalars_alloc(k + 2)
     native.scalars_copy(scA, 0, uA, 0, k)
@@ -82,5 +83,4 @@ def prove(key, uA, uB, uC, Z, rx_priv, r, s, keep_quotient=False):
     if keep_quotient:
         return out + (hq, hr)
     hq.free()
-    hr.free()
     return out

@@ -157,10 +157,10 @@ def prove(key, a_vals, b_vals, c_vals, blinds=None, keep=False):
     # ---- round 4
     zeta = int(tr.challenge_scalar(b"zeta"))
     ev = native.fr_poly_eval_dev
-    a_e, b_e, c_e = (ev(wires[k], 0, n + 2, zeta) for k in "abc")
-    s1_e = ev(key.coeffs["s_sigma1"], 0, n, zeta)
-    s2_e = ev(key.coeffs["s_sigma2"], 0, n, zeta)
-    zw_e = ev(z, 0, n + 3, zeta * w % R)
+    # the six openings in one batched set of Horner launches
+    a_e, b_e, c_e, s1_e, s2_e, zw_e = native.fr_poly_eval_multi_dev(
+        [(wires[k], 0, n + 2, zeta) for k in "abc"]
+        + [(key.coeffs["s_sigma1"], 0, n, zeta), (key.coeffs["s_sigma2"], 0, n, zeta), (z, 0, n + 3, zeta * w % R)])
     for name, val in (("a_eval", a_e), ("b_eval", b_e), ("c_eval", c_e), ("s_sigma1_eval", s1_e),
                       ("s_sigma2_eval", s2_e), ("z_omega_eval", zw_e)):
         setattr(proof, name, FR(val))
@@ -173,25 +173,25 @@ def prove(key, a_vals, b_vals, c_vals, blinds=None, keep=False):
     ab = (a_e + beta * s1_e + gamma) * (b_e + beta * s2_e + gamma) % R
     perm_s3 = alpha * ab % R * beta % R * zw_e % R
     const = (-alpha * ab % R * zw_e % R * (c_e + gamma) - alpha * alpha % R * l1_zeta) % R   # pi(zeta) = 0
+    # linearisation polynomial: seven scalar-times-polynomial terms in one pass
     r = native.scalars_alloc(n + 3)
-    for name, k in (("q_m", a_e * b_e % R), ("q_l", a_e), ("q_r", b_e), ("q_o", c_e), ("q_c", 1),
-                    ("s_sigma3", (-perm_s3) % R)):
-        native.axpy_dev(r, 0, k, key.coeffs[name], 0, n)
-    native.axpy_dev(r, 0, (perm_z + alpha * alpha % R * l1_zeta) % R, z, 0, n + 3)
+    native.lincomb_dev(r, 0, n + 3,
+                       [(k, key.coeffs[name], 0, n) for name, k in
+                        (("q_m", a_e * b_e % R), ("q_l", a_e), ("q_r", b_e), ("q_o", c_e), ("q_c", 1),
+                         ("s_sigma3", (-perm_s3) % R))]
+                       + [((perm_z + alpha * alpha % R * l1_zeta) % R, z, 0, n + 3)])
     native.scalars_add_const(r, 0, 1, const)
     r_eval = ev(r, 0, n + 3, zeta)
     proof.r_eval = FR(r_eval)
     zeta_n = pow(zeta, n, R)
     P = native.scalars_alloc(n + 6)
-    native.axpy_dev(P, 0, 1, t, 0, n)
-    native.axpy_dev(P, 0, zeta_n, t, n, n)
-    native.axpy_dev(P, 0, zeta_n * zeta_n % R, t, 2 * n, n + 6)
-    native.axpy_dev(P, 0, v, r, 0, n + 3)
+    terms = [(1, t, 0, n), (zeta_n, t, n, n), (zeta_n * zeta_n % R, t, 2 * n, n + 6), (v, r, 0, n + 3)]
     vp = v
     for h, length in ((wires["a"], n + 2), (wires["b"], n + 2), (wires["c"], n + 2),
                       (key.coeffs["s_sigma1"], n), (key.coeffs["s_sigma2"], n)):
         vp = vp * v % R
-        native.axpy_dev(P, 0, vp, h, 0, length)
+        terms.append((vp, h, 0, length))
+    native.lincomb_dev(P, 0, n + 6, terms)                # the batched opening polynomial in one pass
     W = native.scalars_alloc(n + 5)
     native.div_linear_dev(P, 0, n + 6, zeta, W, 0)
     Ww = native.scalars_alloc(n + 2)

@@ -145,3 +145,31 @@ def test_wire_format_moves_device_vectors_without_python_integers(native):
     h2 = wire.deserialize_to_handle(blob)
     assert h2.n == len(coeffs) and native.scalars_download(h2, 0, h2.n) == blob
     assert [int(c) for c in wire.deserialize_poly(blob).coeffs] == coeffs
+
+
+def test_batched_evaluation_and_linear_combination(native):
+    """zkp_fr_poly_eval_multi_dev / zkp_fr_lincomb_dev against Horner and Python sums (ragged lengths,
+    two evaluation points, a zero coefficient, a single-coefficient polynomial)."""
+    import random
+    from oracle import ref_path
+    rng = random.Random(77)
+    Rm = native.R_MOD
+    lens = [1, 5, 64, 65, 4097, 5000, 5003]
+    polys = [[rng.randrange(Rm) for _ in range(n)] for n in lens]
+    hs = [native.scalars_load(native.fr_vec_bytes(p), len(p)) for p in polys]
+    x0, x1 = rng.randrange(Rm), rng.randrange(Rm)
+    items = [(h, 0, len(p), x0 if i % 3 else x1) for i, (h, p) in enumerate(zip(hs, polys))]
+    got = native.fr_poly_eval_multi_dev(items)
+    assert got == [ref_path.poly_eval(p, x0 if i % 3 else x1) for i, p in enumerate(polys)]
+    assert native.fr_poly_eval_multi_dev([(hs[5], 7, 100, x0)]) == [ref_path.poly_eval(polys[5][7:107], x0)]
+    coeffs = [rng.randrange(Rm) for _ in lens]
+    coeffs[2] = 0
+    n = 5003
+    dst = native.scalars_generate(9, n)                  # pre-filled: the call overwrites, it does not accumulate
+    native.lincomb_dev(dst, 0, n, [(c, h, 0, len(p)) for c, h, p in zip(coeffs, hs, polys)])
+    want = [sum(c * p[i] for c, p in zip(coeffs, polys) if i < len(p)) % Rm for i in range(n)]
+    assert native.fr_vec_from_bytes(native.scalars_download(dst, 0, n)) == want
+    with pytest.raises(native.ZkpB200Error):
+        native.lincomb_dev(dst, 0, 10, [(1, hs[3], 0, 65)])          # item longer than the destination
+    with pytest.raises(native.ZkpB200Error):
+        native.lincomb_dev(hs[6], 0, 5003, [(1, hs[6], 0, 5003)])    # in-place is refused
