@@ -160,6 +160,12 @@ int zkp_groth16_quotient(const uint8_t* a, const uint8_t* b, const uint8_t* c, u
  * remainder (zero for a satisfied instance; three more transforms) is then not computed. */
 int zkp_groth16_quotient_dev(uint64_t a, uint64_t b, uint64_t c, uint64_t len, uint64_t z, uint64_t z_len,
                              uint64_t* h_out, uint64_t* rem_out);
+/* The three MSMs of one proof (proving.py:23-75 as one MSM per element): A = <sa, ta> and C' = <sc, tc>
+ * in G1 on one stream, B = <sb, tb2> in G2 on a second one, so the G2 work overlaps the G1 work.
+ * Whole tables from index 0, na / nb / nc entries; out_is_inf = {A, B, C'} flags (may be NULL). */
+int zkp_groth16_msms_dev(uint64_t ta, uint64_t sa, uint64_t na, uint64_t tb2, uint64_t sb, uint64_t nb, uint64_t tc,
+                         uint64_t sc, uint64_t nc, uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64],
+                         int out_is_inf[3]);
 /* Device-resident Fr vector utilities used to assemble MSM scalar vectors without leaving HBM. */
 int zkp_scalars_alloc(uint64_t n, uint64_t* handle);
 int zkp_scalars_copy(uint64_t dst, uint64_t dst_off, uint64_t src, uint64_t src_off, uint64_t n);

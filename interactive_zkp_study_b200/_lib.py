@@ -88,6 +88,7 @@ PROTOTYPES = {
     "zkp_scalars_is_zero": (c_int, [u64, u64, u64, intp]),
     "zkp_fr_batch_inverse_dev": (c_int, [u64, u64, u64, c_int]),
     "zkp_fr_scan_dev": (c_int, [c_int, u64, u64, u64, u64, u64]),
+    "zkp_groth16_msms_dev": (c_int, [u64, u64, u64, u64, u64, u64, u64, u64, u64, vp, vp, vp, ctypes.POINTER(c_int)]),
     "zkp_fr_poly_eval_multi_dev": (c_int, [u32, u64p, u64p, u64p, vp, vp]),
     "zkp_fr_lincomb_dev": (c_int, [u64, u64, u64, u32, u64p, u64p, u64p, vp]),
     "zkp_fr_div_linear_dev": (c_int, [u64, u64, u64, vp, u64, u64]),

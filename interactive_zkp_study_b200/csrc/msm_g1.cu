@@ -4,6 +4,9 @@
 namespace zkp {
 int g_force_window_bits = 0;
 }
+namespace zkp {
+int g2_msm_enqueue(Context& c, uint64_t table, uint64_t scalars, uint64_t n, int slot, char* dev_out);  // msm_g2.cu
+}
 using namespace zkp;
 using Api = GroupApi<Fp>;
 
@@ -61,6 +64,49 @@ int zkp_table_download(uint64_t table, uint64_t offset, uint64_t n, uint8_t* out
     } else {
       throw BadHandle("zkp_table_download: not a point table");
     }
+  });
+}
+
+// The three multi-scalar multiplications of one Groth16 proof (proving.py:23-75 reduced to one MSM per
+// element, device_prover.py): B (G2) runs on the second stream beside A and C (G1) on the first.  The G2
+// accumulation keeps only 8 warps per SM busy (228 registers per thread), so blocks of the G1 kernels
+// co-reside with it and fill the integer pipe, and each lane's latency-bound tail hides behind the other.
+int zkp_groth16_msms_dev(uint64_t ta, uint64_t sa, uint64_t na, uint64_t tb2, uint64_t sb, uint64_t nb, uint64_t tc,
+                         uint64_t sc, uint64_t nc, uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64],
+                         int out_is_inf[3]) {
+  return guarded([&](Context& c) {
+    if (!out_a || !out_b || !out_c) throw InvalidArgument("zkp_groth16_msms_dev: null output");
+    Resource* rta = need(ta, HandleKind::G1Table, "zkp_groth16_msms_dev");
+    Resource* rtc = need(tc, HandleKind::G1Table, "zkp_groth16_msms_dev");
+    Resource* rsa = need(sa, HandleKind::Scalars, "zkp_groth16_msms_dev");
+    Resource* rsc = need(sc, HandleKind::Scalars, "zkp_groth16_msms_dev");
+    if (na > rta->n || na > rsa->n || nc > rtc->n || nc > rsc->n) throw InvalidArgument("zkp_groth16_msms_dev: range out of bounds");
+    static DevBuf res;  // A: [0,64) flag [64,68) | C: [128,192) flag [192,196) | B: [256,384) flag [384,388)
+    res.reserve(512);
+    char* r = res.as<char>();
+    CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
+    CUDA_CHECK(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
+    c.launches += g2_msm_enqueue(c, tb2, sb, nb, 1, r + 256);
+    MsmEngine<Fp>& e = Api::engine(0);
+    c.launches += Api::run_on_table(c, rta, 0, rsa->buf.as<uint32_t>(), na, false, 0);
+    CUDA_CHECK(cudaMemcpyAsync(r, e.result.p, 64, cudaMemcpyDeviceToDevice, c.stream));
+    CUDA_CHECK(cudaMemcpyAsync(r + 64, e.flag.p, sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+    c.launches += Api::run_on_table(c, rtc, 0, rsc->buf.as<uint32_t>(), nc, false, 0);
+    CUDA_CHECK(cudaMemcpyAsync(r + 128, e.result.p, 64, cudaMemcpyDeviceToDevice, c.stream));
+    CUDA_CHECK(cudaMemcpyAsync(r + 192, e.flag.p, sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+    CUDA_CHECK(cudaEventRecord(c.ev_join, c.stream2));
+    CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
+    uint8_t host[512];
+    CUDA_CHECK(cudaMemcpyAsync(host, r, 512, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    int fa, fc, fb;
+    memcpy(&fa, host + 64, 4);
+    memcpy(&fc, host + 192, 4);
+    memcpy(&fb, host + 384, 4);
+    if (fa) memset(out_a, 0, 64); else memcpy(out_a, host, 64);
+    if (fc) memset(out_c, 0, 64); else memcpy(out_c, host + 128, 64);
+    if (fb) memset(out_b, 0, 128); else memcpy(out_b, host + 256, 128);
+    if (out_is_inf) { out_is_inf[0] = fa; out_is_inf[1] = fb; out_is_inf[2] = fc; }
   });
 }
 

@@ -7,6 +7,23 @@ using Api = GroupApi<Fp2>;
 // zkp_table_download (msm_g1.cu) needs the G2 download path
 template struct zkp::GroupApi<Fp2>;
 
+namespace zkp {
+// G2 MSM enqueued on lane `slot` (1 = the second stream); result (128 B) and infinity flag (4 B) are
+// copied to dev_out on that lane.  Used by zkp_groth16_msms_dev (msm_g1.cu) to run the G2 element of a
+// Groth16 proof beside the two G1 elements.
+int g2_msm_enqueue(Context& c, uint64_t table, uint64_t scalars, uint64_t n, int slot, char* dev_out) {
+  Resource* t = need(table, HandleKind::G2Table, "zkp_groth16_msms_dev");
+  Resource* s = need(scalars, HandleKind::Scalars, "zkp_groth16_msms_dev");
+  if (n > t->n || n > s->n) throw InvalidArgument("zkp_groth16_msms_dev: G2 range out of bounds");
+  cudaStream_t st = slot ? c.stream2 : c.stream;
+  int launches = Api::run_on_table(c, t, 0, s->buf.as<uint32_t>(), n, false, slot);
+  MsmEngine<Fp2>& e = Api::engine(slot);
+  CUDA_CHECK(cudaMemcpyAsync(dev_out, e.result.p, 128, cudaMemcpyDeviceToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(dev_out + 128, e.flag.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return launches;
+}
+}  // namespace zkp
+
 extern "C" {
 
 int zkp_g2_msm(const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t out_xy[128], int* out_is_inf) {

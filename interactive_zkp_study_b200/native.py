@@ -275,6 +275,16 @@ def groth16_quotient_dev(a, b, c, length, z, z_len, want_remainder=True):
             DeviceHandle(hr.value, z_len - 1, "fr") if want_remainder else None)
 
 
+def groth16_msms_dev(ta, sa, na, tb2, sb, nb, tc, sc, nc):
+    """A (G1), B (G2), C' (G1) of one proof with the G2 MSM overlapped on a second stream."""
+    oa, ob, oc = bytearray(64), bytearray(128), bytearray(64)
+    inf = (ctypes.c_int * 3)()
+    check(_lib.lib().zkp_groth16_msms_dev(ta.handle, sa.handle, na, tb2.handle, sb.handle, nb, tc.handle, sc.handle, nc,
+                                          buf(oa), buf(ob), buf(oc), inf))
+    return (g1_from_bytes(bytes(oa), bool(inf[0])), g2_from_bytes(bytes(ob), bool(inf[1])),
+            g1_from_bytes(bytes(oc), bool(inf[2])))
+
+
 def g1_fixed_base_mul_dev(base_bytes, scalars, n):
     h = ctypes.c_uint64()
     check(_lib.lib().zkp_g1_fixed_base_mul_dev(buf(base_bytes), scalars.handle, n, ctypes.byref(h)))

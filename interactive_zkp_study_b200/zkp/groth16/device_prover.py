@@ -61,11 +61,9 @@ def prove(key, uA, uB, uC, Z, rx_priv, r, s, keep_quotient=False):
     scA = native.scalars_alloc(k + 2)
     native.scalars_copy(scA, 0, uA, 0, k)
     native.scalars_upload(scA, k, one + native.fe_bytes(r), 2)
-    A = native.g1_msm_dev(key.TA, 0, scA, 0, k + 2)
     scB = native.scalars_alloc(k + 2)
     native.scalars_copy(scB, 0, uB, 0, k)
     native.scalars_upload(scB, k, one + native.fe_bytes(s), 2)
-    B = native.g2_msm_dev(key.TB2, 0, scB, 0, k + 2)
     nC = k + 1 + mp + (k - 1)
     scC = native.scalars_alloc(nC)
     native.scalars_copy(scC, 0, uB, 0, k)
@@ -75,7 +73,8 @@ def prove(key, uA, uB, uC, Z, rx_priv, r, s, keep_quotient=False):
         native.scalars_copy(scC, k + 1, rx_priv, 0, mp)
     if k > 1:
         native.scalars_copy(scC, k + 1 + mp, hq, 0, k - 1)
-    X = native.g1_msm_dev(key.TC, 0, scC, 0, nC)
+    # A and X in G1 on one stream, B in G2 beside them on a second one
+    A, B, X = native.groth16_msms_dev(key.TA, scA, k + 2, key.TB2, scB, k + 2, key.TC, scC, nC)
     C = native.g1_msm(native.g1_bytes(A) + native.g1_bytes(X), native.fe_bytes(s) + one, 2)
     for h in (scA, scB, scC):
         h.free()
