@@ -356,13 +356,13 @@ def run_ours(args):
     pinned = nat.PinnedBuffer(32 * n)
     pinned.write(nat.scalars_download(k_h[0], 0, n))
 
+    e2e_scalars = nat.scalars_alloc(n) if world > 1 else None
+
     def step_e2e():
         if world == 1:
             return nat.g1_msm_table(table, 0, pinned.addr, n)
-        sc = nat.scalars_load(pinned.addr, n)          # H2D of this rank's scalar shard
-        r = sharded_step(sc)
-        sc.free()
-        return r
+        nat.scalars_upload(e2e_scalars, 0, pinned.addr, n)   # H2D of this rank's scalar shard (inside the timed region)
+        return sharded_step(e2e_scalars)
 
     for _ in range(max(1, warmup // 2)):
         step_e2e()
