@@ -285,3 +285,64 @@ def test_partial_wire_format_and_device_pointer_exchange(native):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,want_c", [(5, 7), (40, 10), (300, 13), (5000, 15)])
+def test_automatic_window_width(native, n, want_c):
+    """window_bits = 0: the library picks the width for the table size (msm_auto_precomputed_c) and the MSM
+    on the precomputed table still equals the oracle's sum, whole table and sub-range."""
+    rng = random.Random(n)
+    base = [bn254.g1_mul(bn254.G1, rng.randrange(1, R)) for _ in range(4)]
+    pts, acc = [], base[0]
+    for i in range(n):
+        acc = bn254.g1_add(acc, base[i % 4])
+        pts.append(acc)
+    scalars = [rng.randrange(R) for _ in range(n)]
+    table = native.g1_table_load(native.g1_vec_bytes(pts), n)
+    assert native.table_precompute(table) == want_c and table.pre_c == want_c
+    m = min(n, 200)                      # the oracle's double-and-add loop is slow: check a sub-range of large tables
+    off = n - m
+    assert native.g1_msm_table(table, off, native.fr_vec_bytes(scalars[:m]), m) == bn254.g1_msm(pts[off:], scalars[:m])
+    if n <= 300:
+        assert native.g1_msm_table(table, 0, native.fr_vec_bytes(scalars), n) == bn254.g1_msm(pts, scalars)
+
+
+def test_groth16_three_msms_overlapped(native):
+    """zkp_groth16_msms_dev: G1, G2, G1 results equal the three separate calls (and the oracle)."""
+    rng = random.Random(91)
+    n1, n2, n3 = 70, 33, 150
+    p1, p3 = _points_g1(rng, n1), _points_g1(rng, n3)
+    g2b = [bn254.g2_mul(bn254.G2, rng.randrange(1, 1 << 64)) for _ in range(3)]
+    p2, acc = [], g2b[0]
+    for i in range(n2):
+        acc = bn254.g2_add(acc, g2b[i % 3])
+        p2.append(acc)
+    s1, s2, s3 = ([rng.randrange(R) for _ in range(k)] for k in (n1, n2, n3))
+    ta = native.g1_table_load(native.g1_vec_bytes(p1), n1)
+    tb = native.g2_table_load(native.g2_vec_bytes(p2), n2)
+    tc = native.g1_table_load(native.g1_vec_bytes(p3), n3)
+    native.table_precompute(tc)                                     # mixed plain / precomputed tables
+    ha, hb, hc = (native.scalars_load(native.fr_vec_bytes(s), len(s)) for s in (s1, s2, s3))
+    A, B, C = native.groth16_msms_dev(ta, ha, n1, tb, hb, n2, tc, hc, n3)
+    assert A == bn254.g1_msm(p1, s1) and B == bn254.g2_msm(p2, s2) and C == bn254.g1_msm(p3, s3)
+    zero = native.scalars_alloc(n2)
+    assert native.groth16_msms_dev(ta, ha, n1, tb, zero, n2, tc, hc, n3)[1] is None     # infinity in the G2 slot
+
+
+def test_latency_probe_and_affine_experiment_run(native):
+    """Diagnostics stay callable: single-thread / quad latencies are positive, and the batched-affine
+    experiment kernel computes correct sums."""
+    import ctypes
+    from interactive_zkp_study_b200 import _lib
+    for mode in (0, 3, 8, 9):
+        assert native.latency_probe(mode) > 0
+    rng = random.Random(3)
+    pts = _points_g1(rng, 64)
+    pts[10] = pts[11]                    # a doubling
+    pts[20] = None                       # an infinity operand
+    pts[31] = (pts[30][0], bn254.P - pts[30][1])   # P + (-P)
+    table = native.g1_table_load(native.g1_vec_bytes(pts), 64)
+    ms, out = ctypes.c_double(), bytearray(64 * 32)
+    native.check(_lib.lib().zkp_dbg_affine_pairs(table.handle, 8, ctypes.byref(ms), native.buf(out), 32))
+    got = [native.g1_from_bytes(bytes(out[64 * i:64 * i + 64])) for i in range(32)]
+    assert got == [bn254.g1_add(pts[2 * i], pts[2 * i + 1]) for i in range(32)]
