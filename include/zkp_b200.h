@@ -253,7 +253,8 @@ int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effecti
 int zkp_latency_probe(int mode, double* ns_per_op);
 /* Field-op self-test hooks used by tests/ (field: 0 = Fp, 1 = Fr; op: 0 add,1 sub,2 mul,3 inv,4 sqr) */
 int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
-/* out[i] = a[i] + b[i] on G1 (group: 0 = G1, 1 = G2) via XYZZ, result affine; exercises all edge cases */
+/* out[i] = a[i] + b[i] (group: 0 = G1, 1 = G2; 2 / 3 = the same through the quad-lane operations of
+ * csrc/ec_quad.cuh) via XYZZ, result affine; exercises all edge cases */
 int zkp_dbg_point_add(int group, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
 /* experiment: P[2i] + P[2i+1] over a plain G1 table in affine coordinates, `batch` additions per shared
  * inversion per thread; kernel milliseconds and the first n_check sums */

@@ -222,6 +222,26 @@ __global__ void dbg_point_add_kernel(const Affine<F>* a, const Affine<F>* b, uin
   out[i] = {r.x.from_mont(), r.y.from_mont()};
 }
 
+// The same sum through the quad-lane operations of ec_quad.cuh (four lanes per pair): a + b by Quad::add,
+// and 2*(a + b) - (a + b) folded in through Quad::dbl and a second Quad::add so the doubling path and the
+// P + (-P) path of the combination are exercised too:  r = (2s) + (-s) with s = a + b.
+template <class F>
+__global__ void dbg_point_add_quad_kernel(const Affine<F>* a, const Affine<F>* b, uint64_t n, Affine<F>* out) {
+  const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t i = gt >> 2;
+  const int ql = threadIdx.x & 3;
+  const bool live = i < n;
+  if (!live) i = n - 1;  // whole warps take part in the shuffles
+  Affine<F> p = {a[i].x.to_mont(), a[i].y.to_mont()};
+  Affine<F> q = {b[i].x.to_mont(), b[i].y.to_mont()};
+  XYZZ<F> s = Quad<F>::add(XYZZ<F>::from_affine(p), XYZZ<F>::from_affine(q), ql);
+  XYZZ<F> r = Quad<F>::add(Quad<F>::dbl(s, ql), s.neg(), ql);
+  if (live && ql == 0) {
+    Affine<F> o = r.to_affine();
+    out[i] = {o.x.from_mont(), o.y.from_mont()};
+  }
+}
+
 // ------------------------------------------------------------------ synthetic scalars
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;
@@ -543,14 +563,21 @@ int zkp_dbg_point_add(int group, const uint8_t* a, const uint8_t* b, uint64_t n,
   return guarded([&](Context& c) {
     if (!a || !b || !out) throw InvalidArgument("zkp_dbg_point_add: null argument");
     if (n == 0) return;
-    size_t sz = group == 0 ? 64 : 128;
+    if (group < 0 || group > 3) throw InvalidArgument("zkp_dbg_point_add: group must be 0 (G1), 1 (G2), 2 / 3 (the same on quads of lanes)");
+    size_t sz = (group & 1) == 0 ? 64 : 128;
     DevBuf da, db, dout;
     da.reserve(n * sz);
     db.reserve(n * sz);
     dout.reserve(n * sz);
     CUDA_CHECK(cudaMemcpyAsync(da.p, a, n * sz, cudaMemcpyHostToDevice, c.stream));
     CUDA_CHECK(cudaMemcpyAsync(db.p, b, n * sz, cudaMemcpyHostToDevice, c.stream));
-    if (group == 0)
+    if (group == 2)
+      dbg_point_add_quad_kernel<Fp><<<ceil_div(4 * n, 64), 64, 0, c.stream>>>(da.as<G1Affine>(), db.as<G1Affine>(), n,
+                                                                             dout.as<G1Affine>());
+    else if (group == 3)
+      dbg_point_add_quad_kernel<Fp2><<<ceil_div(4 * n, 64), 64, 0, c.stream>>>(da.as<G2Affine>(), db.as<G2Affine>(), n,
+                                                                              dout.as<G2Affine>());
+    else if (group == 0)
       dbg_point_add_kernel<Fp><<<ceil_div(n, 64), 64, 0, c.stream>>>(da.as<G1Affine>(), db.as<G1Affine>(), n,
                                                                     dout.as<G1Affine>());
     else

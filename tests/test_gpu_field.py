@@ -38,7 +38,10 @@ def test_field_ops_bit_exact(native, field, mod):
     assert _unvec(native.dbg_field_op(field, 5, _vec(a[:m]), None, m)) == got  # Fermat chain agrees
 
 
-def test_g1_add_all_cases(native):
+@pytest.mark.parametrize("quad", [0, 2])
+def test_g1_add_all_cases(native, quad):
+    """quad = 2: the same sums through the four-lane group operations of ec_quad.cuh (add, double, and the
+    P + P / P + (-P) / infinity cases inside them)."""
     rng = random.Random(7)
     pts = [bn254.g1_mul(bn254.G1, rng.randrange(1, R)) for _ in range(40)]
     a, b = [], []
@@ -47,18 +50,19 @@ def test_g1_add_all_cases(native):
     a += [None, pts[0], None, pts[1], pts[2]]
     b += [pts[0], None, None, pts[1], bn254.g1_neg(pts[2])]  # inf+P, P+inf, inf+inf, P+P, P+(-P)
     n = len(a)
-    out = native.dbg_point_add(0, native.g1_vec_bytes(a), native.g1_vec_bytes(b), n)
+    out = native.dbg_point_add(quad, native.g1_vec_bytes(a), native.g1_vec_bytes(b), n)
     got = [native.g1_from_bytes(out[64 * i:64 * i + 64]) for i in range(n)]
     assert got == [bn254.g1_add(x, y) for x, y in zip(a, b)]
 
 
-def test_g2_add_all_cases(native):
+@pytest.mark.parametrize("quad", [1, 3])
+def test_g2_add_all_cases(native, quad):
     rng = random.Random(8)
     pts = [bn254.g2_mul(bn254.G2, rng.randrange(1, 1 << 64)) for _ in range(12)]
     a = pts[0:6] + [None, pts[0], None, pts[1], pts[2]]
     b = pts[6:12] + [pts[0], None, None, pts[1], bn254.g2_neg(pts[2])]
     n = len(a)
     enc = lambda v: b"".join(native.g2_bytes(p) for p in v)
-    out = native.dbg_point_add(1, enc(a), enc(b), n)
+    out = native.dbg_point_add(quad, enc(a), enc(b), n)
     got = [native.g2_from_bytes(out[128 * i:128 * i + 128]) for i in range(n)]
     assert got == [bn254.g2_add(x, y) for x, y in zip(a, b)]
