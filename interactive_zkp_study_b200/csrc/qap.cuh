@@ -14,7 +14,8 @@
 // summed bottom-up over a subproduct tree: a node holds M = prod (x - x_j) and N = sum_j c_j M / (x - x_j)
 // over its leaves; parent: M = M_l M_r, N = N_l M_r + N_r M_l.  Every level is a batch of equal-size
 // cyclic products -> batched NTTs (ntt_device, log_batch).  The M side depends on k only: its
-// transformed children are cached per k, so an interpolation costs two batched transforms per level.
+// transformed children are cached per k; the N side climbs in evaluation form (ap_interpolate), two
+// batched half-size transforms per level.
 // Setup needs the Lagrange basis at the toxic point, l_j(x) = Z(x) w_j / (x - x_j): one batch inversion.
 #pragma once
 
@@ -91,16 +92,6 @@ __global__ void ap_unwrap_kernel(Fr* __restrict__ lev, uint64_t K, uint32_t log_
   uint64_t two_s = uint64_t(1) << log_2s;
   if (p >= (K >> log_2s)) return;
   if ((p + 1) * two_s <= k) lev[p * two_s] = lev[p * two_s] - Fr::one();
-}
-// N^_p = N^_l * M^_r + N^_r * M^_l     (N canonical, M^ Montgomery -> canonical)
-__global__ void ap_combine_kernel(const Fr* __restrict__ nch, const Fr* __restrict__ mch, uint64_t K, uint32_t log_s,
-                                  Fr* __restrict__ out) {
-  uint64_t idx = IDX64;
-  if (idx >= K) return;
-  uint64_t two_s = uint64_t(2) << log_s;
-  uint64_t p = idx >> (log_s + 1), t = idx & (two_s - 1);
-  uint64_t l = (2 * p) * two_s + t, r = (2 * p + 1) * two_s + t;
-  out[idx] = nch[l] * mch[r] + nch[r] * mch[l];
 }
 // leaves of the N tree: c_j = y_j * w_j (* scale); zero beyond k
 __global__ void ap_leaf_n_kernel(const Fr* __restrict__ y, const Fr* __restrict__ w, uint64_t K, uint64_t k, int scaled,
@@ -216,36 +207,60 @@ static int ap_domain_build(Context& c, uint64_t k) {
   return launches;
 }
 
-// coefficients (canonical) of the polynomial of degree < k through (j + 1, y[j]), times `scale`
+// N^_p on H_2s from the children's values: child q has its s values on H_s in `ev` (the even points of
+// H_2s) and its s values on the coset w_2s * H_s in `odd` (the odd points).  N canonical, M^ Montgomery.
+__global__ void ap_combine_eval_kernel(const Fr* __restrict__ ev, const Fr* __restrict__ odd, const Fr* __restrict__ mch,
+                                       uint64_t K, uint32_t log_s, Fr* __restrict__ out) {
+  uint64_t idx = IDX64;
+  if (idx >= K) return;
+  const uint64_t s = uint64_t(1) << log_s, two_s = s << 1;
+  const uint64_t p = idx >> (log_s + 1), t = idx & (two_s - 1);
+  const Fr* src = (t & 1) ? odd : ev;
+  const uint64_t h = t >> 1;
+  const Fr nl = src[(2 * p) * s + h], nr = src[(2 * p + 1) * s + h];
+  out[idx] = nl * mch[(2 * p + 1) * two_s + t] + nr * mch[(2 * p) * two_s + t];
+}
+
+// coefficients (canonical) of the polynomial of degree < k through (j + 1, y[j]), times `scale`.
+// The N side climbs the tree in EVALUATION form: a node of size s carries its s values on the s-th roots
+// of unity H_s.  Its parent needs both children on H_2s = H_s (have) + w_2s H_s (the coset): one inverse
+// transform and one coset transform of size s per child, then N^_p = N^_l M^_r + N^_r M^_l pointwise
+// against the cached M^.  2 K l butterfly stages per level instead of the 3 K (l + 1) of
+// pad -> transform(2s) -> combine -> inverse(2s), and no padding pass; one inverse transform of size K at the root.
 static int ap_interpolate(Context& c, const Fr* y, uint64_t k, const Fr* scale_mont, Fr* out) {
   int launches = ap_domain_build(c, k);
   const uint64_t K = g_ap.K;
   const uint32_t L = g_ap.L;
-  Fr* lev = g_arena.alloc(K);
+  Fr* ev = g_arena.alloc(K);
+  Fr* odd = g_arena.alloc(K);
   Fr* nxt = g_arena.alloc(K);
-  Fr* ch = g_arena.alloc(2 * K);
-  Fr* scratch = g_arena.alloc(2 * K);
+  Fr* scratch = g_arena.alloc(K);
   ap_leaf_n_kernel<<<GRID_1D(K)>>>(y, g_ap.weights.as<Fr>(), K, k, scale_mont ? 1 : 0, scale_mont ? *scale_mont : host_fr_one_mont(),
-                                   lev);
+                                   ev);
   CUDA_CHECK_LAUNCH();
   launches++;
   for (uint32_t l = 0; l < L; l++) {
     const Fr* mch = g_ap.mhat.as<Fr>() + (size_t)l * 2 * K;
-    FrBytes w = omega_for(l + 1);
-    ap_pad_kernel<<<GRID_1D(2 * K)>>>(lev, K, l, k, 0, ch);
+    const Fr* odd_src = ev;  // l == 0: a constant takes the same value everywhere
+    if (l > 0) {
+      FrBytes w = omega_for(l), shift = omega_for(l + 1);
+      CUDA_CHECK(cudaMemcpyAsync(odd, ev, K * sizeof(Fr), cudaMemcpyDeviceToDevice, c.stream));
+      launches += ntt_device(c, odd, scratch, l, w, true, nullptr, L - l);
+      launches += ntt_device(c, odd, scratch, l, w, false, &shift, L - l);
+      odd_src = odd;
+    }
+    ap_combine_eval_kernel<<<GRID_1D(K)>>>(ev, odd_src, mch, K, l, nxt);
     CUDA_CHECK_LAUNCH();
-    launches += 1 + ntt_device(c, ch, scratch, l + 1, w, false, nullptr, L - l);
-    ap_combine_kernel<<<GRID_1D(K)>>>(ch, mch, K, l, nxt);
-    CUDA_CHECK_LAUNCH();
-    launches += 1 + ntt_device(c, nxt, scratch, l + 1, w, true, nullptr, L - l - 1);
-    Fr* t = lev;
-    lev = nxt;
+    launches++;
+    Fr* t = ev;
+    ev = nxt;
     nxt = t;
   }
-  CUDA_CHECK(cudaMemcpyAsync(out, lev, k * sizeof(Fr), cudaMemcpyDeviceToDevice, c.stream));
-  g_arena.free(lev);
+  launches += ntt_device(c, ev, scratch, L, omega_for(L), true, nullptr, 0);
+  CUDA_CHECK(cudaMemcpyAsync(out, ev, k * sizeof(Fr), cudaMemcpyDeviceToDevice, c.stream));
+  g_arena.free(ev);
+  g_arena.free(odd);
   g_arena.free(nxt);
-  g_arena.free(ch);
   g_arena.free(scratch);
   return launches;
 }
