@@ -533,6 +533,31 @@ static int poly_mul_dev(Context& c, const Fr* a, uint64_t la, const Fr* b, uint6
   return launches;
 }
 
+// out[0..out_len) = (a * b)[0..out_len) where b (lb coefficients) is given by its forward transform `bhat` of
+// size 2^lg >= la + lb - 1 (a fixed operand: the transform is computed once and kept by the caller).
+static int poly_mul_cached_dev(Context& c, const Fr* a, uint64_t la, const Fr* bhat, uint64_t lb, uint32_t lg, Fr* out,
+                               uint64_t out_len) {
+  int launches = 0;
+  uint64_t full = la + lb - 1;
+  uint64_t N = uint64_t(1) << lg;
+  Fr* fa = g_arena.alloc(N);
+  Fr* scratch = g_arena.alloc(N);
+  CUDA_CHECK(cudaMemcpyAsync(fa, a, la * sizeof(Fr), cudaMemcpyDeviceToDevice, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(fa + la, 0, (N - la) * sizeof(Fr), c.stream));
+  FrBytes w = omega_for(lg);
+  launches += ntt_device(c, fa, scratch, lg, w, false, nullptr);
+  fr_mul_inplace_kernel<<<GRID_1D(N)>>>(fa, bhat, N);
+  CUDA_CHECK_LAUNCH();
+  launches++;
+  launches += ntt_device(c, fa, scratch, lg, w, true, nullptr);
+  uint64_t take = out_len < full ? out_len : full;
+  CUDA_CHECK(cudaMemcpyAsync(out, fa, take * sizeof(Fr), cudaMemcpyDeviceToDevice, c.stream));
+  if (out_len > full) CUDA_CHECK(cudaMemsetAsync(out + full, 0, (out_len - full) * sizeof(Fr), c.stream));
+  g_arena.free(fa);
+  g_arena.free(scratch);
+  return launches;
+}
+
 // g = f^-1 mod x^m by Newton iteration (f[0] != 0); f has lf coefficients.  g: m elements.
 static int series_inverse_dev(Context& c, const Fr* f, uint64_t lf, uint64_t m, Fr* g) {
   int launches = 0;
@@ -560,8 +585,10 @@ static int series_inverse_dev(Context& c, const Fr* f, uint64_t lf, uint64_t m, 
 // All device Montgomery.  vanishing: b is x^(lb-1) - 1 (fast path).
 // inv_cache: optional persistent buffer holding rev(b)^-1 mod x^m from an earlier call with the same
 // divisor (the Groth16 Z(x) is fixed per circuit); *inv_cached tells whether it is already filled.
+// inv_hat: optional buffer of 2^log2_ceil(2m - 1) elements next to inv_cache that keeps the forward
+// transform of the cached inverse (one transform less per division by the same divisor).
 static int poly_divmod_dev(Context& c, const Fr* a, uint64_t la, const Fr* b, uint64_t lb, Fr* q, Fr* r, bool vanishing,
-                           Fr* inv_cache = nullptr, bool* inv_cached = nullptr) {
+                           Fr* inv_cache = nullptr, bool* inv_cached = nullptr, Fr* inv_hat = nullptr) {
   int launches = 0;
   uint64_t m = la - lb + 1;
   if (vanishing && lb >= 2) {
@@ -580,11 +607,21 @@ static int poly_divmod_dev(Context& c, const Fr* a, uint64_t la, const Fr* b, ui
   fr_reverse_kernel<<<GRID_1D(lrb)>>>(b, lb, lrb, rb);
   CUDA_CHECK_LAUNCH();
   launches += 2;
+  const uint32_t lg_q = log2_ceil(2 * m - 1);
   if (!(inv_cached && *inv_cached)) {
     launches += series_inverse_dev(c, rb, lrb, m, g);
     if (inv_cached) *inv_cached = true;
+    if (inv_hat) {
+      uint64_t N = uint64_t(1) << lg_q;
+      Fr* scratch = g_arena.alloc(N);
+      CUDA_CHECK(cudaMemcpyAsync(inv_hat, g, m * sizeof(Fr), cudaMemcpyDeviceToDevice, c.stream));
+      CUDA_CHECK(cudaMemsetAsync(inv_hat + m, 0, (N - m) * sizeof(Fr), c.stream));
+      launches += ntt_device(c, inv_hat, scratch, lg_q, omega_for(lg_q), false, nullptr);
+      g_arena.free(scratch);
+    }
   }
-  launches += poly_mul_dev(c, ra, m, g, m, qr, m);
+  if (inv_hat) launches += poly_mul_cached_dev(c, ra, m, inv_hat, m, lg_q, qr, m);
+  else launches += poly_mul_dev(c, ra, m, g, m, qr, m);
   fr_reverse_kernel<<<GRID_1D(m)>>>(qr, m, m, q);
   CUDA_CHECK_LAUNCH();
   launches++;
@@ -786,7 +823,7 @@ int zkp_fr_poly_divmod(const uint8_t* a, uint64_t a_len, const uint8_t* b, uint6
 // ------------------------------------------------------------------ device-resident Fr vectors (handles)
 struct DivisorCache {
   uint64_t z_handle = 0, z_len = 0, m = 0;
-  DevBuf inv;
+  DevBuf inv, inv_hat;  // rev(Z)^-1 mod x^m and its forward transform
   bool filled = false;
 };
 static DivisorCache g_div_cache;
@@ -893,6 +930,7 @@ int zkp_groth16_quotient_dev(uint64_t a, uint64_t b, uint64_t cc, uint64_t len, 
       g_div_cache.m = m;
       g_div_cache.filled = false;
       g_div_cache.inv.reserve(m * sizeof(Fr));
+      g_div_cache.inv_hat.reserve((size_t(1) << log2_ceil(2 * m - 1)) * sizeof(Fr));
     }
     auto hq = std::make_unique<Resource>();
     hq->kind = HandleKind::Scalars;
@@ -908,7 +946,7 @@ int zkp_groth16_quotient_dev(uint64_t a, uint64_t b, uint64_t cc, uint64_t len, 
       hr->buf.reserve_pooled(z_len * 32);
     }
     launches += poly_divmod_dev(c, dp, lp, dz, z_len, hq->buf.as<Fr>(), hr ? hr->buf.as<Fr>() : nullptr, false,
-                                g_div_cache.inv.as<Fr>(), &g_div_cache.filled);
+                                g_div_cache.inv.as<Fr>(), &g_div_cache.filled, g_div_cache.inv_hat.as<Fr>());
     fr_from_mont_kernel<<<GRID_1D(m)>>>(hq->buf.as<Fr>(), m, hq->buf.as<Fr>());
     CUDA_CHECK_LAUNCH();
     launches++;
