@@ -32,6 +32,18 @@ def test_field_ops_bit_exact(native, field, mod):
     assert _unvec(native.dbg_field_op(field, 1, ab, bb, n)) == [(x - y) % mod for x, y in zip(a, b)]
     assert _unvec(native.dbg_field_op(field, 2, ab, bb, n)) == [(x * y) % mod for x, y in zip(a, b)]
     assert _unvec(native.dbg_field_op(field, 4, ab, None, n)) == [(x * x) % mod for x in a]
+    # limb patterns IN MONTGOMERY FORM (the device squares x = a R mod p): all-ones low limbs, top bits of
+    # every limb set (the dedicated squaring doubles the operand across limb boundaries), single-limb values
+    rinv = pow(1 << 256, -1, mod)
+    top = mod >> 224
+    pats = [mod - 1, (1 << 224) - 1, ((top - 1) << 224) | ((1 << 224) - 1), int("80000000" * 7, 16),
+            (0x20000000 << 224) | int("80000000" * 7, 16), int("ffffffff" * 7, 16) ^ int("0000ffff" * 7, 16),
+            0xffffffff, 0xffffffff << 32, 0xffffffff << 192, 0x80000000, (0x80000000 << 96) | 0x80000000,
+            (1 << 253) + (1 << 31), int("7fffffff" * 7, 16), int("0000000180000000" * 3, 16)]
+    pats = [x % mod for x in pats]
+    pa = [x * rinv % mod for x in pats]
+    assert _unvec(native.dbg_field_op(field, 4, _vec(pa), None, len(pa))) == [(x * x) % mod for x in pa]
+    assert _unvec(native.dbg_field_op(field, 2, _vec(pa), _vec(pa[::-1]), len(pa))) == [(x * y) % mod for x, y in zip(pa, pa[::-1])]
     m = 300
     got = _unvec(native.dbg_field_op(field, 3, _vec(a[:m]), None, m))
     assert got == [bn254.inv(x, mod) for x in a[:m]]  # inv(0) == 0 as in py_ecc (binary extended Euclid)
