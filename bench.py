@@ -169,7 +169,7 @@ def cpu_baseline(nat, table, scalars_handle):
     """Oracle (port of the reference's commit loop) on one host core, bounded sample; also a parity
     check of the GPU result on that sample."""
     from oracle import bn254
-    sample = 1024
+    sample = 2048                        # ~10 s of single-core CPU work at ~5 ms per point
     raw = nat.table_download(table, 0, sample)
     pts = [nat.g1_from_bytes(raw[64 * i:64 * i + 64]) for i in range(sample)]
     scal = nat.fr_vec_from_bytes(nat.scalars_download(scalars_handle, 0, sample))
