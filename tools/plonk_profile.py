@@ -12,7 +12,8 @@ dp.prove(key, *wit)
 acc = collections.defaultdict(lambda: [0, 0.0])
 names = ["scalars_alloc", "scalars_copy", "ntt_dev", "vec_op_dev", "scalars_load", "g1_msm_dev", "plonk_perm_terms_dev",
          "batch_inverse_dev", "scan_dev", "scalars_convert", "plonk_quotient_dev", "scalars_is_zero", "fr_poly_eval_dev",
-         "axpy_dev", "scalars_add_const", "div_linear_dev", "scalars_upload"]
+         "axpy_dev", "scalars_add_const", "div_linear_dev", "scalars_upload", "g1_msm_dev_batch", "fr_poly_eval_multi_dev",
+         "lincomb_dev"]
 orig = {k: getattr(nat, k) for k in names}
 def wrap(k):
     f = orig[k]
