@@ -374,16 +374,7 @@ def run_ours(args):
     for _ in range(max(1, warmup // 2)):
         step_e2e()
     barrier()
-    if os.environ.get("ZKP_BENCH_DEBUG") and world > 1:      # host-side split of one e2e step, for diagnosis
-        for _ in range(3):
-            t0 = time.perf_counter()
-            nat.scalars_upload(e2e_scalars, 0, pinned.addr, n)
-            t1 = time.perf_counter()
-            sharded_step(e2e_scalars)
-            t2 = time.perf_counter()
-            sys.stderr.write("[rank %d] e2e step: upload %.2f ms, sharded MSM %.2f ms\n" % (rank, (t1 - t0) * 1e3, (t2 - t1) * 1e3))
-        barrier()
-    if os.environ.get("ZKP_BENCH_DEBUG") and world > 1:      # the same split inside a tight loop (no I/O between steps)
+    if os.environ.get("ZKP_BENCH_DEBUG") and world > 1:      # diagnosis: host-side split of the e2e step, untimed
         tu = tm = tg = tc = 0.0
         for _ in range(steps):
             t0 = time.perf_counter()
