@@ -256,3 +256,44 @@ def test_binary_wire_format_round_trips_the_reference_objects():
         wire.loads(b"nope")
     with pytest.raises(ValueError):
         wire.loads(blob[:-5])
+
+
+def test_sparse_r1cs_host_logic():
+    """qap_device host side: CSR construction from the reference's dense R1CS, the transpose
+    used for the CRS terms, and the determinant factor of r1cs_to_qap_times_lcm -- no device needed."""
+    import numpy as np
+    from interactive_zkp_study_b200.zkp.groth16 import qap_device as qd
+    from oracle import ref_path
+    from tests.util import load
+    for c in load("groth16_qap.json")["cases"]:
+        A, B, C = c["r1cs_A"], c["r1cs_B"], c["r1cs_C"]
+        r1cs = qd.SparseR1CS.from_dense(A, B, C)
+        k, m = c["numGates"], c["numWires"]
+        assert (r1cs.k, r1cs.m) == (k, m)
+        for dense, (rp, ci, vals), which in zip((A, B, C), r1cs.mats, range(3)):
+            back = [[0] * m for _ in range(k)]
+            for g in range(k):
+                for e in range(int(rp[g]), int(rp[g + 1])):
+                    back[g][int(ci[e])] = vals[e]
+            assert back == [[int(v) % curve_order for v in row] for row in dense]
+            t_rp, t_ci, t_vals = r1cs.transposed(which)          # m x k
+            assert len(t_rp) == m + 1 and int(t_rp[-1]) == len(ci)
+            tb = [[0] * k for _ in range(m)]
+            for w in range(m):
+                cols = [int(x) for x in t_ci[int(t_rp[w]):int(t_rp[w + 1])]]
+                assert cols == sorted(cols)
+                for e, g in zip(range(int(t_rp[w]), int(t_rp[w + 1])), cols):
+                    tb[w][g] = t_vals[e]
+            assert tb == [list(col) for col in zip(*back)]
+        # the witness satisfies the sparse system: (A.w) o (B.w) = C.w
+        w = c["witness"]
+        dot = lambda mat, g: sum(v * w[int(ci)] for ci, v in zip(mat[1][int(mat[0][g]):int(mat[0][g + 1])],
+                                                               mat[2][int(mat[0][g]):int(mat[0][g + 1])])) % curve_order
+        for g in range(k):
+            assert dot(r1cs.mats[0], g) * dot(r1cs.mats[1], g) % curve_order == dot(r1cs.mats[2], g)
+    for k in (1, 2, 4, 6, 9):
+        assert qd.vandermonde_det(k) == ref_path.qap_vandermonde_det(k)
+    rows = qd.SparseR1CS.from_rows(2, 3, [{0: 1}, {2: 5, 1: 7}], [{1: 1}, {0: 1}], [{2: 1}, {2: 1}])
+    assert list(rows.mats[0][1]) == [0, 1, 2] and rows.mats[0][2] == [1, 7, 5]      # columns sorted within a row
+    sel = qd._Selection([2, 3, 4])
+    assert sel.run == (2, 3) and qd._Selection([0, 2]).run is None and len(qd._Selection([])) == 0
