@@ -3,16 +3,24 @@
 
 Metric (BASELINE.json): BN254 G1 MSM throughput, Mpts/s, 2^20 synthetic random points / scalars per
 GPU (configs[1]); weak scaling over N GPUs (each rank owns a contiguous point range of the same
-size, one 128-byte partial sum per rank is gathered and folded -- SURVEY.md 8e).
+size; the library gathers one 128-byte partial sum per rank over NCCL and folds it -- SURVEY.md 8e).
+Every line also carries `strong_2p26`: BASELINE configs[4], 2^26 points in total split over the N ranks
+by point range (the >= 6x at 8 GPUs target), verified on the device at every N.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log-n 20]
 
 One JSON line on stdout (rank 0).  `value` is timed with CUDA events on the library's stream with
 points and scalars resident in HBM; `e2e` is the same MSM through the reference-facing C-ABI call
 with the scalars in pinned HOST memory (H2D inside the timed region, affine result read back);
-`roofline` is the bucket-accumulation kernel against the integer-MAD peak measured live on the same
+`roofline` is the bucket-accumulation kernel against the IMAD.WIDE peak measured live on the same
 GPU (MEASURED_PEAKS.json carries no integer peak); `cpu_baseline` is the oracle's restatement of the
-reference's commit() loop timed on this box's host cores on a bounded sample.
+reference's CPU path (commit loop, fft, hxr, proof_a) timed on this box's host cores on bounded samples.
+Every MSM that is timed is first checked against  sum_i k_i (s_i G) == <k, s> G  with the dot product
+computed on the device (zkp_fr_dot_dev) and one oracle scalar multiplication: verification is on at
+every size and every N.
+
+torch appears here only as launcher plumbing (barrier and max-over-ranks of the timings, as the bench
+contract prescribes); the product path -- including the NCCL exchange -- is inside libzkp_b200.so.
 """
 import argparse
 import json
@@ -30,7 +38,10 @@ UNIT = "Mpts/s"
 SEED_SCALARS = 0x5EED0001
 SEED_POINTS = 0x5EED0002
 MACS_PER_FP_MUL = 136                      # 8-limb CIOS: 8*(8+1+8) limb-MACs   
+MACS_PER_FP_SQR = 108                      # dedicated squaring: 36 + 72 (ff.cuh sqr_inline)
+MADD_MACS = 8 * MACS_PER_FP_MUL + 2 * MACS_PER_FP_SQR      # XYZZ mixed addition 8M + 2S = 1304 limb-MACs
 MODEL_ACC_MACS_PER_POINT = 160 * MACS_PER_FP_MUL  # SURVEY model: 16 windows x 10 Fp-mul (XYZZ mixed add) = 21 760
+M64 = (1 << 64) - 1
 
 
 def windows_for(c):
@@ -164,10 +175,10 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------ our arm (GPU)
+# ------------------------------------------------------------------ CPU legs of the metric (oracle = port of the reference)
 def cpu_baseline(nat, table, scalars_handle):
     """Oracle (port of the reference's commit loop) on one host core, bounded sample; also a parity
-    check of the GPU result on that sample."""
+    check of the GPU result on that sample.  Further legs: the reference's fft, hxr and proof_a."""
     from oracle import bn254
     sample = 2048                        # ~10 s of single-core CPU work at ~5 ms per point
     raw = nat.table_download(table, 0, sample)
@@ -179,14 +190,101 @@ def cpu_baseline(nat, table, scalars_handle):
     got = nat.g1_msm_dev(table, 0, scalars_handle, 0, sample)
     if got != want:
         raise SystemExit("PARITY FAILURE: GPU MSM differs from the oracle on the cpu_baseline sample")
-    return {"value": sample / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
-            "sample": "first %d points/scalars of the workload, oracle/bn254.g1_msm (reference kzg.commit loop, "
-                      "affine double-and-add, py_ecc semantics); GPU result on the same sample is bit-identical" % sample}
+    out = {"value": sample / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
+           "sample": "first %d points/scalars of the workload, oracle/bn254.g1_msm (reference kzg.commit loop, "
+                     "affine double-and-add, py_ecc semantics); GPU result on the same sample is bit-identical" % sample}
+    try:
+        out["legs"] = cpu_legs(nat)
+    except Exception as e:  # never lose the headline line
+        out["legs_error"] = repr(e)
+    return out
 
 
-def ntt_extra(nat, log_n):
+def cpu_legs(nat):
+    """fft 2^14 (polynomial.py:292-341), hxr at numGates 64 (poly_utils.py:116-125), proof_a at 12 x 12
+    (proving.py:23-33): oracle/ref_path restatements on one core, each compared with the GPU result."""
+    import random
+    from oracle import bn254, ref_path
+    R = bn254.R
+    rng = random.Random(41)
+    legs = {}
+    # ---- fft
+    log_n = 14
+    n = 1 << log_n
+    vals = [rng.randrange(R) for _ in range(n)]
+    w = ref_path.get_root_of_unity(n)
+    t0 = time.perf_counter()
+    want = ref_path.fft(vals, w)
+    dt = time.perf_counter() - t0
+    got = nat.fr_vec_from_bytes(nat.fr_ntt(nat.fr_vec_bytes(vals), log_n, w))
+    legs["fft"] = {"n": n, "seconds": dt, "value": n / dt / 1e6, "unit": "Melem/s", "cores": 1, "kind": "port",
+                   "reference": "zkp/plonk/polynomial.py:292-341 (recursive radix-2)", "gpu_bit_identical": got == want}
+    # ---- hxr: numGates k, numWires m
+    k, m = 64, 66
+    Ax, Bx, Cx = ([[rng.randrange(R) for _ in range(k)] for _ in range(m)] for _ in range(3))
+    Rv = [rng.randrange(R) for _ in range(m)]
+    Z = [1]
+    for j in range(1, k + 1):            # (x-1)...(x-k), qap_creator_lcm.py:128-135
+        Z = ref_path.poly_mul(Z, [(-j) % R, 1])
+    t0 = time.perf_counter()
+    hx, rem = ref_path.hxr(Ax, Bx, Cx, Z, Rv)
+    dt = time.perf_counter() - t0
+    from interactive_zkp_study_b200.zkp.groth16 import poly_utils
+    FR = poly_utils.FR
+    t1 = time.perf_counter()
+    ghx, grem = poly_utils.hxr([[FR(v) for v in row] for row in Ax], [[FR(v) for v in row] for row in Bx],
+                               [[FR(v) for v in row] for row in Cx], [FR(v) for v in Z], [FR(v) for v in Rv])
+    gdt = time.perf_counter() - t1
+    legs["hxr"] = {"num_gates": k, "num_wires": m, "seconds": dt, "cores": 1, "kind": "port",
+                   "reference": "zkp/groth16/poly_utils.py:116-125 (mat-vec + schoolbook product + long division)",
+                   "gpu_mirror_seconds_incl_python_lists": gdt,
+                   "gpu_bit_identical": [int(v) for v in ghx] == [v % R for v in hx] and [int(v) for v in grem] == [v % R for v in rem]}
+    # ---- proof_a: the numWires x numGates loop of scalar multiplications
+    k, m = 12, 12
+    x = rng.randrange(1, R)
+    sigma1_2 = [bn254.g1_mul(bn254.G1, pow(x, j, R)) for j in range(k)]
+    sigma1_1 = [bn254.g1_mul(bn254.G1, rng.randrange(1, R)) for _ in range(3)]
+    Ax = [[rng.randrange(R) for _ in range(k)] for _ in range(m)]
+    Rv = [rng.randrange(R) for _ in range(m)]
+    r = rng.randrange(R)
+    t0 = time.perf_counter()
+    want = ref_path.proof_a(sigma1_1, sigma1_2, Ax, Rv, r)
+    dt = time.perf_counter() - t0
+    from interactive_zkp_study_b200.zkp.groth16 import proving
+    from interactive_zkp_study_b200.compat import FQ
+    pt = lambda p: (FQ(p[0]), FQ(p[1]))
+    t1 = time.perf_counter()
+    got = proving.proof_a([pt(p) for p in sigma1_1], [pt(p) for p in sigma1_2], [[proving.FR(v) for v in row] for row in Ax],
+                          [proving.FR(v) for v in Rv], r)
+    gdt = time.perf_counter() - t1
+    legs["proof_a"] = {"num_gates": k, "num_wires": m, "seconds": dt, "scalar_muls": m * k + m + 1, "cores": 1, "kind": "port",
+                       "reference": "zkp/groth16/proving.py:23-33", "gpu_mirror_seconds_incl_table_upload": gdt,
+                       "gpu_bit_identical": (int(got[0]), int(got[1])) == want}
+    return legs
+
+
+# ------------------------------------------------------------------ sub-records (other rows of the metric)
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    return 6650.0, "fallback of B200_PROFILING.md (no MEASURED_PEAKS.json)"
+
+
+def profile_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture of this round, or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path)).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def ntt_record(nat, log_n, peak_tmacs):
     """Forward Fr NTT of 2^log_n resident elements: achieved integer and HBM rates."""
-    import ctypes
     from interactive_zkp_study_b200 import _lib
     n = 1 << log_n
     omega = pow(5, (nat.R_MOD - 1) >> log_n, nat.R_MOD)
@@ -204,19 +302,74 @@ def ntt_extra(nat, log_n):
         best = min(best, nat.timer_stop())
     h.free()
     macs = 68.0 * n * log_n
-    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    hbm = peaks.get("hbm_gbs", 6650.0)
-    return {"n": n, "ms": best, "gelem_per_s": n / best / 1e6, "t_mac_per_s": macs / best / 1e9,
-            "hbm_gbs_algorithmic": 64.0 * n / best / 1e6, "hbm_frac": 64.0 * n / best / 1e6 / hbm,
-            "hbm_peak_gbs": hbm, "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-            "note": "68*n*log2(n) limb-MACs and 64 B/element (one read + one write); the 254-bit NTT is integer bound (10.6 MAC/B needed)"}
+    hbm, src = measured_hbm_peak()
+    ach = macs / best / 1e9
+    return {"n": n, "ms": best, "gelem_per_s": n / best / 1e6,
+            "roofline": {"bound": "imad", "kernel": "ntt_pass_kernel", "achieved": ach, "peak": peak_tmacs,
+                         "unit": "T limb-MAC/s", "frac": ach / peak_tmacs, "traffic": profile_traffic("ntt_pass_kernel"),
+                         "algorithmic_macs": macs,
+                         "hbm_view": {"algorithmic_bytes": 64.0 * n, "achieved_gbs": 64.0 * n / best / 1e6,
+                                      "frac": 64.0 * n / best / 1e6 / hbm, "peak_gbs": hbm, "peak_source": src}},
+            "note": "68*n*log2(n) limb-MACs ((n/2) log2 n products of 136) and 64 B/element (one read + one write); "
+                    "the 254-bit NTT is integer bound (10.6 MAC/B needed)"}
 
 
+def g2_record(nat, log_n, peak_tmacs):
+    """G2 MSM of 2^log_n points on its window-precomputed table: the accumulation kernel's integer rate."""
+    from oracle import bn254
+    n = 1 << log_n
+    s_h = nat.scalars_generate(0x5EED0003, n)
+    k_h = nat.scalars_generate(SEED_SCALARS + 0x33, n)
+    table = nat.g2_fixed_base_mul_dev(nat.g2_bytes(bn254.G2), s_h, n)
+    c = nat.table_precompute(table)
+    got = nat.g2_msm_dev(table, 0, k_h, 0, n)
+    ok = got == bn254.g2_mul(bn254.G2, nat.fr_dot_dev(k_h, 0, s_h, 0, n))
+    nat.msm_profile(True)
+    best, acc = 1e9, 0.0
+    for _ in range(4):
+        nat.timer_start()
+        nat.g2_msm_dev(table, 0, k_h, 0, n)
+        ms = nat.timer_stop()
+        if ms < best:
+            best, acc = ms, nat.msm_last_profile("accumulate")
+    nat.msm_profile(False)
+    for h in (s_h, k_h, table):
+        h.free()
+    W = windows_for(c)
+    # Fp2 product = 3 Fp products (Karatsuba), Fp2 squaring = 2: mixed addition 8 M2 + 2 S2 = 28 Fp products
+    macs = n * W * 28 * MACS_PER_FP_MUL
+    ach = macs / (acc * 1e-6) / 1e12
+    return {"n": n, "ms": best, "value": n / best / 1e3, "unit": UNIT, "window_bits": c, "verified": bool(ok),
+            "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel<Fp2>", "achieved": ach, "peak": peak_tmacs,
+                         "unit": "T limb-MAC/s", "frac": ach / peak_tmacs, "kernel_ms": acc * 1e-3,
+                         "traffic": profile_traffic("msm_accumulate_kernel<Fp2>"), "algorithmic_macs_per_launch": macs,
+                         "algorithmic_note": "%d windows x (8 Fp2 products + 2 Fp2 squarings = 28 Fp products) x 136" % W}}
+
+
+def groth16_record(log_k, peak_tmacs):
+    """Second half of the BASELINE metric: Groth16 prove ms at 2^log_k constraints (config 3), with the
+    SURVEY 8d work model as its roofline."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import groth16_large
+    res = groth16_large.run(log_k, 3, verify=True, quiet=True)
+    k = 1 << log_k
+    # SURVEY 8d: 4 G1 MSMs + 1 G2 MSM at the model's per-point cost + ~1e10 for the quotient
+    macs = 4 * k * msm_macs_per_point(k) + k * 3 * msm_macs_per_point(k) + 1.0e10 * k / (1 << 20)
+    ach = macs / (res["prove_ms"] * 1e-3) / 1e12
+    res["verified"] = bool(res.pop("verified_against_discrete_logs"))
+    res["roofline"] = {"bound": "imad", "achieved": ach, "peak": peak_tmacs, "unit": "T limb-MAC/s", "frac": ach / peak_tmacs,
+                       "algorithmic_macs": macs,
+                       "algorithmic_note": "SURVEY 8d model: 4 G1 MSMs + 1 G2 MSM (x3) of 2^%d points at 23 664 MAC/pt + 1e10 for the quotient; "
+                                           "the prover here folds them into 2 G1 MSMs (k+2 and 3k-2 points) + 1 G2 MSM" % log_k}
+    return res
+
+
+# ------------------------------------------------------------------ our arm (GPU)
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
+    dist = torch = None
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -224,20 +377,72 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     os.environ.setdefault("ZKP_B200_DEVICE", str(local_rank))
     from interactive_zkp_study_b200 import native as nat
+    from interactive_zkp_study_b200 import sharded
+    from oracle import bn254
     info = nat.device_info()
+
+    def barrier():
+        nat.sync()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks_int(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    comm = None
+    if world > 1:
+        # the library's own NCCL communicator; its 128-byte id rides on the launcher's process group
+        def exchange(mine):
+            box = [mine]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        comm = sharded.Communicator(rank, world, exchange_id=exchange)
+
+    def stream(seed, first, count):
+        # element i of the global stream == element (i - first) of a stream with a shifted counter
+        return nat.scalars_generate((seed + 64 * first) & M64, count)
+
+    def expected_point(k, s, count):
+        """(sum over ALL ranks of <k, s>) * G on rank 0: device dot products + one oracle scalar multiplication."""
+        local = nat.fr_dot_dev(k, 0, s, 0, count)
+        if dist is None:
+            return bn254.g1_mul(bn254.G1, local)
+        box = [None] * world
+        dist.all_gather_object(box, local)
+        return bn254.g1_mul(bn254.G1, sum(box) % bn254.R) if rank == 0 else None
+
+    def msm_resident(table, k, count):
+        if world == 1:
+            return nat.g1_msm_dev(table, 0, k, 0, count)
+        return nat.g1_msm_multi(table, 0, k, 0, count)
+
+    def msm_from_host(table, addr, count):
+        if world == 1:
+            return nat.g1_msm_table(table, 0, addr, count)
+        return nat.g1_msm_multi_table(table, 0, addr, count)
 
     n = 1 << args.log_n                 # points per GPU
     steps, warmup = args.steps, args.warmup
     G1 = nat.g1_bytes((1, 2))
     # this rank's point range [rank*n, (rank+1)*n): P_i = s_i * G with s_i from the synthetic stream
-    # (known discrete logs -> O(n) check of any MSM), scalars k_i from a second stream
-    def stream(seed, first, count):
-        # element i of the global stream == element (i - first) of a stream with a shifted counter
-        return nat.scalars_generate((seed + 64 * first) & ((1 << 64) - 1), count)
+    # (known discrete logs -> O(1)-host check of any MSM), scalars k_i from a second stream
     s_h = stream(SEED_POINTS, rank * n, n)
     table = nat.g1_fixed_base_mul_dev(G1, s_h, n)
     plain_ms = None
     pre_c = 0
+    precompute_s = 0.0
     if not args.plain:
         # first the plain-table number (no precomputation), for the record
         kk = stream(SEED_SCALARS + 0x9000, rank * n, n)
@@ -257,55 +462,18 @@ def run_ours(args):
     n_vec = 4                            # rotate scalar vectors so no step reuses cached digits
     k_h = [stream(SEED_SCALARS + 0x1000 * v, rank * n, n) for v in range(n_vec)]
 
-    def barrier():
-        nat.sync()
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    exchange = None
-    if world > 1:
-        from interactive_zkp_study_b200 import sharded
-        exchange = sharded.PartialExchange()   # CUDA send/recv buffers of the one 128 B-per-rank gather
-
-    def sharded_step(k):
-        """Local Pippenger -> XYZZ partial written into the NCCL send buffer -> all-gather over NVLink ->
-        rank 0 folds straight out of the receive buffer (interactive_zkp_study_b200/sharded.py)."""
-        return sharded.g1_msm_sharded(exchange, table, k, n)
-
     def step_resident(i):
-        k = k_h[i % n_vec]
-        if world == 1:
-            return nat.g1_msm_dev(table, 0, k, 0, n)
-        return sharded_step(k)
+        return msm_resident(table, k_h[i % n_vec], n)
 
-    # ---- correctness of the exact workload before timing (size-independent check, SURVEY 8d)
-    if rank == 0 and world == 1 and args.verify and args.log_n <= 22:
-        from oracle import bn254, synthetic
-        s = synthetic.scalars(SEED_POINTS, n)
-        k = synthetic.scalars(SEED_SCALARS, n)
-        want = bn254.g1_mul(bn254.G1, sum(a * b for a, b in zip(k, s)) % bn254.R)
-        if step_resident(0) != want:
-            raise SystemExit("PARITY FAILURE: 2^%d MSM != (sum k_i s_i) * G" % args.log_n)
-
-    if world > 1 and args.verify and n * world <= (1 << 23):
-        # sharded MSM == (sum over ALL ranks' ranges of k_i s_i) * G, checked on rank 0.  The expected value is
-        # seconds of pure-Python work on rank 0: the other ranks wait for it on the HOST (a gloo barrier), not
-        # inside a collective spinning on their GPUs -- with the peers parked in NCCL for that long, the gathers
-        # of the following ~40 steps measured 3.4 ms instead of 0.1 ms (2 and 4 ranks).
-        want = None
-        if rank == 0:
-            from oracle import bn254, synthetic
-            s = synthetic.scalars(SEED_POINTS, n * world)
-            k = synthetic.scalars(SEED_SCALARS, n * world)
-            want = bn254.g1_mul(bn254.G1, sum(a * b for a, b in zip(k, s)) % bn254.R)
-            del s, k
-        host_group = dist.new_group(backend="gloo")
-        dist.barrier(group=host_group)
-        got = step_resident(0)
-        if rank == 0 and got != want:
-            raise SystemExit("PARITY FAILURE: sharded MSM over %d GPUs != (sum k_i s_i) * G" % world)
+    # ---- correctness of the exact workload before timing (size-independent check): every vector
+    verified = None
+    if args.verify:
+        verified = True
+        for v in range(n_vec):
+            want = expected_point(k_h[v], s_h, n)
+            got = step_resident(v)
+            if rank == 0 and got != want:
+                raise SystemExit("PARITY FAILURE: 2^%d x %d MSM != <k, s> * G (vector %d)" % (args.log_n, world, v))
 
     # clocks are sampled from here to the end of the timed region: the region itself lasts < 0.1 s and
     # nvidia-smi delivers a sample every ~50-100 ms, so the integer-peak microbenchmarks (also a
@@ -315,8 +483,8 @@ def run_ours(args):
         sampler.start()
     peak = {}
     if rank == 0:
-        peak = {"imad_wide_u32": nat.imad_peak(0), "imad_lo": nat.imad_peak(1), "imad_hi_u32": nat.imad_peak(2),
-                "fp_mul_chain": nat.imad_peak(3)}
+        peak = {"imad_wide_u32": nat.imad_peak(0), "imad_wide_u32_dependent_multiplicand": nat.imad_peak(4),
+                "imad_lo": nat.imad_peak(1), "imad_hi_u32": nat.imad_peak(2), "fp_mul_chain": nat.imad_peak(3)}
 
     # ---- resident-input timing (value)
     for i in range(warmup):
@@ -335,17 +503,24 @@ def run_ours(args):
     barrier()
     launches = nat.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else {}
-    nat.msm_profile(False)
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
+    ms = max_over_ranks(ms)
+    launches = sum_over_ranks_int(launches)
     total_points = n * world
     value = total_points * steps / (ms * 1e-3) / 1e6
+
+    # the accumulation kernel alone (no bucket-range parts: nothing overlaps it), same table and vectors
+    iso_acc_us = iso_msm_us = None
+    if rank == 0 and world == 1:
+        nat.msm_set_option("split", 1)
+        nat.g1_msm_dev(table, 0, k_h[0], 0, n)
+        iso_acc_us = iso_msm_us = 0.0
+        reps = 5
+        for i in range(reps):
+            nat.g1_msm_dev(table, 0, k_h[(i + 1) % n_vec], 0, n)
+            iso_acc_us += nat.msm_last_profile("accumulate") / reps
+            iso_msm_us += nat.msm_last_profile(None) / reps
+        nat.msm_set_option("split", 0)
+    nat.msm_profile(False)
 
     # for the record: the same MSMs submitted as ONE pipelined batch call (two streams: the tail of MSM k
     # overlaps the accumulation of MSM k+1), the call shape of a prover that commits in groups
@@ -362,136 +537,167 @@ def run_ours(args):
     # ---- end-to-end timing: scalars in pinned host memory, H2D inside, affine result read back
     pinned = nat.PinnedBuffer(32 * n)
     pinned.write(nat.scalars_download(k_h[0], 0, n))
-
-    e2e_scalars = nat.scalars_alloc(n) if world > 1 else None
-
-    def step_e2e():
-        if world == 1:
-            return nat.g1_msm_table(table, 0, pinned.addr, n)
-        nat.scalars_upload(e2e_scalars, 0, pinned.addr, n)   # H2D of this rank's scalar shard (inside the timed region)
-        return sharded_step(e2e_scalars)
-
+    e2e_want = step_resident(0)
     for _ in range(max(1, warmup // 2)):
-        step_e2e()
+        got = msm_from_host(table, pinned.addr, n)
+    if got != e2e_want:
+        raise SystemExit("PARITY FAILURE: host-scalar MSM differs from the resident one")
     barrier()
-    if os.environ.get("ZKP_BENCH_DEBUG") and world > 1:      # diagnosis: host-side split of the e2e step, untimed
-        tu = tm = tg = tc = 0.0
-        for _ in range(steps):
-            t0 = time.perf_counter()
-            nat.scalars_upload(e2e_scalars, 0, pinned.addr, n)
-            t1 = time.perf_counter()
-            nat.g1_msm_dev_partial(table, 0, e2e_scalars, 0, n, out_addr=exchange.send_addr)
-            t2 = time.perf_counter()
-            exchange.all_gather()
-            t3 = time.perf_counter()
-            if rank == 0:
-                nat.g1_combine_partials(exchange.recv_addr, world)
-            t4 = time.perf_counter()
-            tu += t1 - t0; tm += t2 - t1; tg += t3 - t2; tc += t4 - t3
-        sys.stderr.write("[rank %d] tight loop per step: upload %.2f, partial MSM %.2f, gather %.2f, combine %.2f ms\n"
-                         % (rank, tu / steps * 1e3, tm / steps * 1e3, tg / steps * 1e3, tc / steps * 1e3))
-        barrier()
     nat.timer_start()
     for _ in range(steps):
-        step_e2e()
+        msm_from_host(table, pinned.addr, n)
     e2e_ms = nat.timer_stop()
-    if os.environ.get("ZKP_BENCH_DEBUG"):
-        sys.stderr.write("[rank %d] e2e loop: %.2f ms for %d steps (device events)\n" % (rank, e2e_ms, steps))
     barrier()
-    if dist is not None:
-        import torch
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks(e2e_ms)
     e2e_value = total_points * steps / (e2e_ms * 1e-3) / 1e6
+    pinned.free()
 
+    base = cpu_baseline(nat, table, k_h[0]) if (rank == 0 and world == 1 and args.cpu) else None
+    for h in [table, s_h] + k_h:
+        h.free()
+
+    # ---- BASELINE configs[4]: 2^26 points in total, sharded by point range over the ranks (strong scaling)
+    strong = None
+    if args.strong_log_n:
+        total_s = 1 << args.strong_log_n
+        start, count = sharded.shard_range(total_s, rank, world)
+        ss = stream(SEED_POINTS, start, count)
+        tab = nat.g1_fixed_base_mul_dev(G1, ss, count)
+        t0 = time.perf_counter()
+        c_s = nat.table_precompute(tab)
+        pre_s = time.perf_counter() - t0
+        kv = [stream(SEED_SCALARS + 0x1000 * v, start, count) for v in range(2)]
+        ok = True
+        for v in range(2):
+            want = expected_point(kv[v], ss, count)
+            got = msm_resident(tab, kv[v], count)
+            if rank == 0 and got != want:
+                ok = False
+        if rank == 0 and not ok:
+            raise SystemExit("PARITY FAILURE: sharded 2^%d MSM over %d GPUs != <k, s> * G" % (args.strong_log_n, world))
+        s_steps, s_warm = 4, 2
+        for i in range(s_warm):
+            msm_resident(tab, kv[i % 2], count)
+        barrier()
+        nat.timer_start()
+        for i in range(s_steps):
+            msm_resident(tab, kv[i % 2], count)
+        sms = max_over_ranks(nat.timer_stop())
+        barrier()
+        # end to end: this rank's scalar shard from pinned host memory
+        pin = nat.PinnedBuffer(32 * count)
+        step_bytes = 1 << 28
+        for off in range(0, 32 * count, step_bytes):
+            m = min(step_bytes, 32 * count - off) // 32
+            pin.write(nat.scalars_download(kv[0], off // 32, m), off)
+        msm_from_host(tab, pin.addr, count)
+        barrier()
+        nat.timer_start()
+        for _ in range(2):
+            msm_from_host(tab, pin.addr, count)
+        s_e2e = max_over_ranks(nat.timer_stop()) / 2
+        barrier()
+        pin.free()
+        strong = {"workload": "BN254 G1 MSM, 2^%d points in total, sharded by contiguous point range (configs[4])" % args.strong_log_n,
+                  "total_points": total_s, "points_per_gpu": count, "n_gpus": world, "scaling": "strong",
+                  "ms_per_step": sms / s_steps, "value": total_s / (sms / s_steps) / 1e3, "unit": UNIT, "steps": s_steps,
+                  "warmup": s_warm, "verified": True,
+                  "verification": "result == (sum over ranks of <k, s> on the device) * G for both scalar vectors",
+                  "e2e": {"ms_per_step": s_e2e, "value": total_s / s_e2e / 1e3, "unit": UNIT,
+                          "h2d_bytes_per_step": 32 * total_s, "d2h_bytes_per_step": 64 * world},
+                  "table": "window-precomputed, c = %d, %.1f GiB per GPU, built once in %.1f s" % (
+                      c_s, windows_for(c_s) * count * 64 / 2**30, pre_s)}
+        for h in [tab, ss] + kv:
+            h.free()
+
+    if comm is not None:
+        comm.close()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (bucket accumulation) against the measured integer peak
+    # ---- roofline of the dominant kernel (bucket accumulation) against the measured IMAD.WIDE peak
+    peak_gmacs = peak["imad_wide_u32"]
+    peak_t = peak_gmacs / 1e3
     acc_s = acc_us / steps * 1e-6
-    peak_gmacs = max(peak["imad_hi_u32"], peak["imad_wide_u32"])
-    acc_macs = n * W_actual * 10 * MACS_PER_FP_MUL   # the mixed additions this launch really performs
+    acc_macs = n * W_actual * MADD_MACS          # the mixed additions this launch really performs (squarings at 108)
     achieved = acc_macs / acc_s / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "accumulate_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
     roofline = {
-        "bound": "imad", "kernel": "msm_accumulate_kernel<Fp>", "achieved": achieved, "peak": peak_gmacs / 1e3,
-        "unit": "T limb-MAC/s (one IMAD.WIDE.U32 = 32x32+64->64)", "frac": achieved / (peak_gmacs / 1e3),
-        "traffic": traffic,
+        "bound": "imad", "kernel": "msm_accumulate_kernel<Fp>", "achieved": achieved, "peak": peak_t,
+        "unit": "T limb-MAC/s (one IMAD.WIDE.U32 = 32x32+64->64)", "frac": achieved / peak_t,
+        "traffic": profile_traffic("msm_accumulate_kernel<Fp>"),
         "algorithmic_macs_per_launch": acc_macs,
-        "algorithmic_note": "%d windows x 10 Fp-mul (XYZZ mixed add) x 136 limb-MAC per point; the SURVEY 8d model "
-                            "(16 windows, 21 760 MAC/pt) is used for whole_msm.frac" % W_actual,
+        "algorithmic_note": "%d windows x (8 products x 136 + 2 squarings x 108 = 1304 limb-MAC per XYZZ mixed addition) per point; "
+                            "with squarings counted as products (SURVEY 8d) the figure is x %.4f" % (W_actual, 1360.0 / MADD_MACS),
         "kernel_ms": acc_s * 1e3, "kernel_share_of_step": acc_us / max(msm_us, 1e-9),
-        "peak_source": "measured live on this GPU by zkp_imad_peak (dependent-free IMAD.HI.U32 / IMAD.WIDE.U32 chains); "
-                       "MEASURED_PEAKS.json has no integer peak",
+        "kernel_timing": "CUDA events on the library stream around the accumulate launches of every timed step "
+                         "(the bucket-range parts run back to back; earlier parts' reductions overlap them on side streams)",
+        "isolated": None if iso_acc_us is None else {
+            "kernel_ms": iso_acc_us * 1e-3, "achieved": acc_macs / (iso_acc_us * 1e-6) / 1e12,
+            "frac": acc_macs / (iso_acc_us * 1e-6) / 1e12 / peak_t, "msm_ms": iso_msm_us * 1e-3,
+            "note": "same MSM with one bucket-range part (nothing overlaps the kernel)"},
+        "peak_source": "measured live on this GPU by zkp_imad_peak(0): IMAD.WIDE.U32, 12 independent accumulators per thread, "
+                       "shared multiplicand, immediate multiplier; MEASURED_PEAKS.json has no integer peak",
         "peaks_gmacs": peak,
         "whole_msm": {"macs_per_point_model": msm_macs_per_point(n),
-                      "frac": (n * msm_macs_per_point(n) / (msm_us / steps * 1e-6) / 1e12) / (peak_gmacs / 1e3)},
+                      "frac": (n * msm_macs_per_point(n) / (msm_us / steps * 1e-6) / 1e12) / peak_t,
+                      "note": "SURVEY 8d model (16 windows + amortised bucket reduction, squarings as products) over the whole MSM time"},
         "hbm_view": {"algorithmic_bytes_per_launch": n * W_actual * 68,
                      "achieved_gbs": n * W_actual * 68 / acc_s / 1e9,
                      "note": "windows x (64 B point gather + 4 B index) per point: far below the HBM roof, the kernel is integer bound"},
     }
-    base = cpu_baseline(nat, table, k_h[0]) if world == 1 else None
-    extras = {}
+    sub = {}
     if world == 1 and args.extras and args.log_n <= 20:
-        # second half of the BASELINE metric: Groth16 prove ms @2^20 constraints (config 3), and the Fr NTT
-        for h in [table] + k_h:
-            h.free()
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import groth16_large
-            extras["groth16_prove_2^%d" % args.log_n] = groth16_large.run(args.log_n, 3, verify=True, quiet=True)
-        except Exception as e:  # never lose the headline line
-            extras["groth16_prove_error"] = repr(e)
+        for name, fn in (("groth16_prove", lambda: groth16_record(args.log_n, peak_t)),
+                         ("g2_msm", lambda: g2_record(nat, args.log_n, peak_t)),
+                         ("fr_ntt", lambda: ntt_record(nat, args.log_n, peak_t))):
+            try:
+                sub[name] = fn()
+            except Exception as e:  # never lose the headline line
+                sub[name + "_error"] = repr(e)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
         try:
             import qap_large
-            extras["groth16_r1cs_prove_2^%d" % args.log_n] = qap_large.run(args.log_n, 3, quiet=True)
+            sub["groth16_r1cs_prove"] = qap_large.run(args.log_n, 3, quiet=True)
         except Exception as e:
-            extras["groth16_r1cs_prove_error"] = repr(e)
+            sub["groth16_r1cs_prove_error"] = repr(e)
         try:
             import plonk_large
-            extras["plonk_prove_2^%d" % args.log_n] = plonk_large.run(args.log_n, 3, verify=True, quiet=True)
+            sub["plonk_prove"] = plonk_large.run(args.log_n, 3, verify=True, quiet=True)
         except Exception as e:
-            extras["plonk_prove_error"] = repr(e)
-        try:
-            extras["fr_ntt"] = ntt_extra(nat, args.log_n)
-        except Exception as e:
-            extras["fr_ntt_error"] = repr(e)
+            sub["plonk_prove_error"] = repr(e)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32x8 (254-bit modular integers, Montgomery)", "data": "synthetic",
+        "dtype": "u32x8 (254-bit modular integers, Montgomery)", "data": "synthetic", "verified": verified,
         "config": {
             "workload": "BN254 G1 MSM, 2^%d synthetic points per GPU (configs[1]); P_i = s_i*G, scalars uniform in [0,r)" % args.log_n,
             "points_per_gpu": n, "total_points": total_points,
-            "sharding": "contiguous point ranges, one 128 B XYZZ partial per rank gathered over NCCL" if world > 1 else "single GPU",
+            "sharding": ("contiguous point ranges; zkp_g1_msm_multi: local Pippenger -> ncclAllGather of one 128 B XYZZ partial per rank "
+                         "-> fold, on the library's stream") if world > 1 else "single GPU",
             "table": ("window-precomputed static table T[w][i] = 2^(%d w) P_i, %d windows, %.0f MiB per GPU, built once in %.0f ms "
                       "(zkp_g1_table_precompute; SRS/CRS tables are fixed per circuit)" % (pre_c, W_actual, W_actual * n * 64 / 2**20, precompute_s * 1e3))
                      if pre_c else "plain affine table, 64 B/point",
             "plain_table": None if plain_ms is None else {"ms_per_step": plain_ms, "value": n / plain_ms / 1e3, "unit": UNIT,
                                                           "note": "same MSM without the precomputed windows (16 windows + Horner), this rank only"},
-            "l2": "working set (point table + scalars + 2x60 MiB digit/index arrays + bucket partials) exceeds the 126 MB L2; "
+            "l2": "working set (point table + scalars + 2x100 MiB pair/index arrays + bucket partials) exceeds the 126 MB L2; "
                   "a different scalar vector every step",
+            "verification": "every timed scalar vector: result == (sum over ranks of <k, s>, zkp_fr_dot_dev) * G",
             "device": info["name"],
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / steps,
-                "h2d_bytes_per_step": 32 * n * world, "d2h_bytes_per_step": 64,
-                "path": "zkp_g1_msm_table: device-resident point table (static SRS), scalars from pinned host memory"},
+                "h2d_bytes_per_step": 32 * n * world, "d2h_bytes_per_step": 64 * world,
+                "path": ("zkp_g1_msm_table" if world == 1 else "zkp_g1_msm_multi_table") +
+                        ": device-resident point table (static SRS), scalars from pinned host memory"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": base,
+        "strong_2p%d" % args.strong_log_n if args.strong_log_n else "strong": strong,
         "pipelined_batch": pipelined,
-        "extras": extras,
     }
+    line.update(sub)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -504,9 +710,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=20, help="log2 of the points per GPU")
-    ap.add_argument("--no-verify", dest="verify", action="store_false")
+    ap.add_argument("--strong-log-n", type=int, default=26, help="log2 of the TOTAL points of the sharded sub-record (0 = skip)")
+    ap.add_argument("--no-verify", dest="verify", action="store_false", help="debugging only; no committed number uses it")
     ap.add_argument("--plain", action="store_true", help="do not precompute the window table")
-    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the Groth16-prove and NTT extras")
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the Groth16 / PLONK / G2 / NTT sub-records")
+    ap.add_argument("--no-cpu", dest="cpu", action="store_false", help="skip the CPU baseline legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -102,6 +102,35 @@ int zkp_g1_msm_dev_partial(uint64_t table, uint64_t offset, uint64_t scalars, ui
 int zkp_g1_combine_partials(const uint8_t* partials, uint32_t count, uint8_t out_xy[64], int* out_is_inf);
 /* Window-width override for experiments (0 = automatic). */
 int zkp_msm_set_window_bits(int c);
+/* Engine tunables for measurements (0 = automatic): "sort" 1 = counting sort with global atomics, 2 = radix
+ * partition through shared memory; "split" 1..4 = bucket-range parts of an MSM on a precomputed table
+ * (the reduction of one part overlaps the accumulation of the next); "window_bits" as above.  Results are
+ * identical under every setting. */
+int zkp_msm_set_option(const char* name, int value);
+
+/* ---- multi-GPU: points sharded by contiguous range, one process per GPU -----------------
+ * Scales the commit loop zkp/plonk/kzg.py:59-67 (and the proof-element sums of zkp/groth16/proving.py:
+ * 23-75) across the GPUs of one box.  The library owns one NCCL communicator per process (NCCL is bound
+ * with dlopen when the first of these calls is made; a single-GPU process never needs it):
+ *   rank 0:      zkp_comm_unique_id(id)  -> hand the 128 bytes to every rank (any host channel)
+ *   every rank:  zkp_comm_init(rank, world, id)   (collective; after zkp_init on that rank's device)
+ * zkp_g1_msm_multi is then a collective call: every rank passes ITS shard (table / scalar handles and the
+ * local range), runs the single-GPU Pippenger on it, and the un-normalised XYZZ partial sums (128 B per
+ * rank in G1, 256 B in G2) are all-gathered over NVLink and folded on the library's stream with no host
+ * synchronisation in between; every rank receives the affine result.  zkp_g1_msm_multi_table takes the
+ * rank's scalars from host memory (H2D inside the call).  world == 1 is allowed. */
+#define ZKP_COMM_ID_BYTES 128
+int zkp_comm_unique_id(uint8_t out_id[ZKP_COMM_ID_BYTES]);
+int zkp_comm_init(int rank, int world, const uint8_t id[ZKP_COMM_ID_BYTES]);
+int zkp_comm_info(int* rank, int* world, int* nccl_version);
+int zkp_comm_barrier(void); /* all ranks: returns once every rank's library stream has reached this point */
+int zkp_comm_destroy(void);
+int zkp_g1_msm_multi(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n,
+                     uint8_t out_xy[64], int* out_is_inf);
+int zkp_g1_msm_multi_table(uint64_t table, uint64_t offset, const uint8_t* scalars, uint64_t n, uint8_t out_xy[64],
+                           int* out_is_inf);
+int zkp_g2_msm_multi(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n,
+                     uint8_t out_xy[128], int* out_is_inf);
 
 /* ---- fixed-base batch scalar multiplication (CRS generation) -------------------
  * out[i] = scalars[i] * base.  Replaces SRS.generate (zkp/plonk/srs.py:78-82) and
@@ -184,6 +213,9 @@ int zkp_scalars_convert(uint64_t h, uint64_t off, uint64_t n, int to_montgomery)
 int zkp_scalars_is_zero(uint64_t h, uint64_t off, uint64_t n, int* out_all_zero);
 int zkp_fr_batch_inverse_dev(uint64_t h, uint64_t off, uint64_t n, int montgomery);
 int zkp_fr_scan_dev(int op, uint64_t dst, uint64_t dst_off, uint64_t src, uint64_t src_off, uint64_t n); /* 0 product, 1 sum */
+/* out = sum_i a[i] * b[i] mod r (canonical).  With points P_i = s_i * G it verifies an MSM of any size with
+ * one scalar multiplication on the host: sum_i k_i P_i == (<k, s>) * G. */
+int zkp_fr_dot_dev(uint64_t a, uint64_t a_off, uint64_t b, uint64_t b_off, uint64_t n, uint8_t out[32]);
 /* up to 16 polynomials evaluated in the same launches, item k at xs[k] (round4.py:39-81: six evaluations) */
 int zkp_fr_poly_eval_multi_dev(uint32_t count, const uint64_t* handles, const uint64_t* offs, const uint64_t* lens,
                                const uint8_t* xs, uint8_t* out);
@@ -241,24 +273,6 @@ int zkp_msm_last_profile(const char* stage, float* out_us);
 /* Page-locked host staging buffers for the end-to-end measurement (H2D from pinned memory). */
 int zkp_pinned_alloc(uint64_t bytes, void** out);
 int zkp_pinned_free(void* p);
-
-/* ---- diagnostics --------------------------------------------------------------------------- */
-/* Dependent-free integer-MAD microbenchmark: variant 0 = IMAD.WIDE.U32 (the roofline unit),
- * 1 = IMAD (32-bit lo), 2 = IMAD.HI.  Returns G(limb-MAC)/s over the whole chip. */
-int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effective);
-/* Single-thread latency of one operation (ns): mode 0/1/2 = 1/2/4 independent Fp products per step,
- * 3 = XYZZ add (inlined products), 4 = XYZZ add (out-of-line products), 5 = mixed add, 6 = double;
- * 7 / 8 = XYZZ add on a quad of lanes (inlined / out-of-line products), 9 = double on a quad.
- * The MSM's reduction tail is bounded by these, not by throughput. */
-int zkp_latency_probe(int mode, double* ns_per_op);
-/* Field-op self-test hooks used by tests/ (field: 0 = Fp, 1 = Fr; op: 0 add,1 sub,2 mul,3 inv,4 sqr) */
-int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
-/* out[i] = a[i] + b[i] (group: 0 = G1, 1 = G2; 2 / 3 = the same through the quad-lane operations of
- * csrc/ec_quad.cuh) via XYZZ, result affine; exercises all edge cases */
-int zkp_dbg_point_add(int group, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
-/* experiment: P[2i] + P[2i+1] over a plain G1 table in affine coordinates, `batch` additions per shared
- * inversion per thread; kernel milliseconds and the first n_check sums */
-int zkp_dbg_affine_pairs(uint64_t table, int batch, double* ms, uint8_t* out_first, uint32_t n_check);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,35 @@
+/* libzkp_b200 -- diagnostics and self-test hooks (csrc/diag.cu).
+ *
+ * NOT part of the product ABI: nothing on a prover path calls these.  bench.py uses zkp_imad_peak for
+ * the roofline denominator (MEASURED_PEAKS.json carries no integer peak), tools/ use zkp_latency_probe,
+ * and tests/test_gpu_field.py drives the field / group-law kernels through zkp_dbg_*.
+ * Same conventions as include/zkp_b200.h (return codes, zkp_last_error, 32-byte little-endian elements).
+ */
+#ifndef ZKP_B200_DIAG_H
+#define ZKP_B200_DIAG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Integer-MAD microbenchmarks, G(limb-MAC)/s over the whole chip.  variant 0 = IMAD.WIDE.U32 peak (the
+ * roofline unit: 12 independent accumulators per thread, shared multiplicand, immediate multiplier);
+ * 1 = IMAD (32-bit lo); 2 = IMAD.HI; 3 = chains of whole Fp Montgomery products (136 limb-MACs each);
+ * 4 = IMAD.WIDE.U32 with a dependent multiplicand and four register operands (reads below variant 0). */
+int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effective);
+/* Single-thread latency of one operation (ns): mode 0/1/2 = 1/2/4 independent Fp products per step,
+ * 3 = XYZZ add (inlined products), 4 = XYZZ add (out-of-line products), 5 = mixed add, 6 = double;
+ * 7 / 8 = XYZZ add on a quad of lanes (inlined / out-of-line products), 9 = double on a quad.
+ * The MSM's reduction tail is bounded by these, not by throughput. */
+int zkp_latency_probe(int mode, double* ns_per_op);
+/* Field-op self-test hooks used by tests/ (field: 0 = Fp, 1 = Fr; op: 0 add,1 sub,2 mul,3 inv,4 sqr) */
+int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
+/* out[i] = a[i] + b[i] (group: 0 = G1, 1 = G2; 2 / 3 = the same through the quad-lane operations of
+ * csrc/ec_quad.cuh) via XYZZ, result affine; exercises all edge cases */
+int zkp_dbg_point_add(int group, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKP_B200_DIAG_H */

@@ -48,7 +48,6 @@ PROTOTYPES = {
     "zkp_g1_table_precompute": (c_int, [u64, c_int]),
     "zkp_g2_table_precompute": (c_int, [u64, c_int]),
     "zkp_table_window_bits": (c_int, [u64, ctypes.POINTER(c_int)]),
-    "zkp_dbg_affine_pairs": (c_int, [u64, c_int, f64p, vp, u32]),
     "zkp_scalars_load": (c_int, [vp, u64, u64p]),
     "zkp_free": (c_int, [u64]),
     "zkp_g1_msm_table": (c_int, [u64, u64, vp, u64, vp, intp]),
@@ -59,6 +58,16 @@ PROTOTYPES = {
     "zkp_g1_msm_dev_partial": (c_int, [u64, u64, u64, u64, u64, vp]),
     "zkp_g1_combine_partials": (c_int, [vp, u32, vp, intp]),
     "zkp_msm_set_window_bits": (c_int, [c_int]),
+    "zkp_msm_set_option": (c_int, [ctypes.c_char_p, c_int]),
+    "zkp_comm_unique_id": (c_int, [vp]),
+    "zkp_comm_init": (c_int, [c_int, c_int, vp]),
+    "zkp_comm_info": (c_int, [intp, intp, intp]),
+    "zkp_comm_barrier": (c_int, []),
+    "zkp_comm_destroy": (c_int, []),
+    "zkp_g1_msm_multi": (c_int, [u64, u64, u64, u64, u64, vp, intp]),
+    "zkp_g1_msm_multi_table": (c_int, [u64, u64, vp, u64, vp, intp]),
+    "zkp_g2_msm_multi": (c_int, [u64, u64, u64, u64, u64, vp, intp]),
+    "zkp_fr_dot_dev": (c_int, [u64, u64, u64, u64, u64, vp]),
     "zkp_g1_fixed_base_mul": (c_int, [vp, vp, u64, u64p]),
     "zkp_g2_fixed_base_mul": (c_int, [vp, vp, u64, u64p]),
     "zkp_g1_fixed_base_mul_dev": (c_int, [vp, u64, u64, u64p]),

@@ -17,7 +17,7 @@ OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libzkp_b200.so")
 ROOT = os.path.dirname(HERE)
 
-UNITS = ["capi_core.cu", "msm_g1.cu", "msm_g2.cu", "ntt.cu", "poly.cu"]
+UNITS = ["capi_core.cu", "comm.cu", "diag.cu", "msm_g1.cu", "msm_g2.cu", "ntt.cu", "poly.cu"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -42,8 +42,9 @@ def _digest(unit):
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(f.encode())
             h.update(fh.read())
-    with open(os.path.join(ROOT, "include", "zkp_b200.h"), "rb") as fh:
-        h.update(fh.read())
+    for f in ("zkp_b200.h", "zkp_b200_diag.h"):
+        with open(os.path.join(ROOT, "include", f), "rb") as fh:
+            h.update(fh.read())
     return h.hexdigest()
 
 
@@ -75,7 +76,11 @@ def build(force=False, verbose=False):
             print(log)
     if relink:
         objs = [os.path.join(OBJ, u.replace(".cu", ".o")) for u in units]
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs
+        # shared CUDA runtime (libcudart.so.12 is on the loader path of this image and of the GPU box; the rpath
+        # covers a bare toolkit install): the .so then carries no copy of the runtime.  libdl for the NCCL binding.
+        link = ["-cudart", "static"] if os.environ.get("ZKP_B200_STATIC_CUDART") else \
+            ["-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + link + ["-ldl"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (p.stdout, p.stderr))

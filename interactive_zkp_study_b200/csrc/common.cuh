@@ -1,5 +1,5 @@
 // Shared host-side plumbing for libzkp_b200: error reporting, the per-process device context
-// (one device per process, as bench.py / torchrun launch it), a grow-only workspace arena.
+// (one device per process, one process per GPU), a grow-only workspace arena.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -53,6 +53,35 @@ struct DevBuf {
   void reserve_pooled(size_t bytes);
   void recycle();
 };
+
+// A temporary device buffer owned by one scope: released when the scope ends, also when it ends by an
+// exception (DevBuf itself is a plain handle that long-lived workspaces copy around, so it has no destructor).
+struct ScopedDevBuf : DevBuf {
+  ScopedDevBuf() = default;
+  ScopedDevBuf(const ScopedDevBuf&) = delete;
+  ScopedDevBuf& operator=(const ScopedDevBuf&) = delete;
+  ~ScopedDevBuf() { release(); }
+  // hands the allocation over to a long-lived owner
+  DevBuf detach() {
+    DevBuf out;
+    out.p = p;
+    out.cap = cap;
+    p = nullptr;
+    cap = 0;
+    return out;
+  }
+};
+// Same for buffers taken from the size-matched pool (reserve_pooled): back to the pool at scope end.
+struct PooledDevBuf : DevBuf {
+  PooledDevBuf() = default;
+  PooledDevBuf(const PooledDevBuf&) = delete;
+  PooledDevBuf& operator=(const PooledDevBuf&) = delete;
+  ~PooledDevBuf() { recycle(); }
+};
+
+// [offset, offset + n) inside [0, limit) without wrapping: ctypes turns a negative Python int into
+// 2^64 - k, and `offset + n > limit` would let that through.
+inline bool range_ok(uint64_t offset, uint64_t n, uint64_t limit) { return offset <= limit && n <= limit - offset; }
 
 struct Context {
   int device = -1;

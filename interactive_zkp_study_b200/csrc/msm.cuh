@@ -82,53 +82,7 @@ inline int msm_auto_precomputed_c(uint64_t n) {
 // wstride: distance between the bucket sets of consecutive windows (B for a plain table; 0 for a
 // window-precomputed table, where all windows share one bucket set).
 static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, int c, int W, uint32_t B,
-                                  uint32_t wstride, uint32_t* __restrict__ codes, uint32_t* __restrict__ hist) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t s[9];
-  const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * i);
-  uint4 lo = sp[0], hi = sp[1];
-  s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
-  s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
-  s[8] = 0;
-  // reduce mod r (2^256 / r < 6): the group has order r, so k*P == (k mod r)*P (field.py:88).
-  for (int it = 0; it < 6; it++) {
-    uint32_t t[8];
-    uint32_t borrow = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      uint64_t d = (uint64_t)s[k] - FrParams::MOD_(k) - borrow;
-      t[k] = (uint32_t)d;
-      borrow = (uint32_t)(d >> 63);
-    }
-    if (borrow) break;
-#pragma unroll
-    for (int k = 0; k < 8; k++) s[k] = t[k];
-  }
-  uint32_t carry = 0;
-  const uint32_t mask = (1u << c) - 1;
-  for (int w = 0; w < W; w++) {
-    int pos = w * c;
-    int word = pos >> 5, sh = pos & 31;
-    uint32_t v = 0;
-    if (word < 8) {
-      uint64_t two = (uint64_t)s[word] | ((uint64_t)s[word + 1] << 32);
-      v = (uint32_t)(two >> sh) & mask;
-    }
-    v += carry;
-    uint32_t code = MSM_INVALID;
-    if (v > B) {  // digit = v - 2^c  (negative), |digit| = 2^c - v in [1, B-1]
-      uint32_t mag = (1u << c) - v;
-      carry = 1;
-      if (mag != 0) code = (((uint32_t)w * wstride + (mag - 1)) << 1) | 1u;
-    } else {
-      carry = 0;
-      if (v != 0) code = (((uint32_t)w * wstride + (v - 1)) << 1);
-    }
-    codes[(uint64_t)w * n + i] = code;
-    if (code != MSM_INVALID) atomicAdd(&hist[code >> 1], 1u);
-  }
-}
+                                  uint32_t wstride, uint32_t* __restrict__ codes, uint32_t* __restrict__ hist);
 
 // ---------------------------------------------------------------- exclusive scan (u32), 3 kernels
 static constexpr int SCAN_BLOCK = 1024;
@@ -147,7 +101,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t val, uint32_t*
   if (lane == 31) warp_sums[wid] = inc;
   __syncthreads();
   if (wid == 0) {
-    uint32_t ws = warp_sums[lane];
+    uint32_t ws = lane < ((blockDim.x + 31) >> 5) ? warp_sums[lane] : 0u;  // blocks of fewer than 32 warps
     uint32_t winc = ws;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -223,6 +177,152 @@ static __global__ void msm_scatter_kernel(const uint32_t* __restrict__ codes, ui
   if (pre_stride) i += (uint32_t)(idx / n) * pre_stride + pre_offset;
   uint32_t pos = atomicAdd(&cursor[code >> 1], 1u);
   sorted[pos] = i | ((code & 1u) << 31);
+}
+
+// ---------------------------------------------------------------- stage 2 (large inputs): radix partition
+// The counting sort above pays one global atomic per digit in each of its two passes (13.6 M + 13.6 M
+// at 2^20 points, c = 20: 80 + 168 us, atomic bound).  For large inputs the (bucket, entry) pairs are
+// instead partitioned on the HIGH bits of the bucket with block-local shared-memory histograms, then
+// every bin -- 2^low_bits consecutive buckets, low_bits = 10 or 8 -- is sorted by one block entirely in shared memory:
+//   P1a  count   : a block walks its contiguous range of scalars, recodes them and histograms the bins
+//                  of its digits in shared memory; per-block counts go out as blk_hist[bin][block];
+//   scan         : exclusive scan of blk_hist (bin-major) = where block b's share of bin k starts;
+//   P1b  scatter : the same blocks recode again (cheaper than storing and re-reading the digits) and
+//                  write {low bucket bits | sign, entry} pairs to their reserved slots;
+//   P2   sort    : one block per bin: histogram of the low bits, scan (this IS the bucket offsets
+//                  array of the bin), scatter of the entries to their final places.
+// No global atomics; every global access is a coalesced stream except the pair writes of P1b (runs of
+// a few hundred bytes) and the final scatter (inside one bin's 100 KB, L2-resident).
+static constexpr int MSM_PART_THREADS = 256;   // P1 block size; P2 runs 2^low_bits threads (one scan item each)
+
+// Canonical scalar i reduced mod r into s[0..8] (s[8] = 0): the group has order r, so
+// k*P == (k mod r)*P (field.py:88).  2^256 / r < 6.
+__device__ __forceinline__ void msm_load_scalar(const uint32_t* __restrict__ scalars, uint64_t i, uint32_t (&s)[9]) {
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * i);
+  uint4 lo = sp[0], hi = sp[1];
+  s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
+  s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+  s[8] = 0;
+  for (int it = 0; it < 6; it++) {
+    uint32_t t[8];
+    uint32_t borrow = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint64_t d = (uint64_t)s[k] - FrParams::MOD_(k) - borrow;
+      t[k] = (uint32_t)d;
+      borrow = (uint32_t)(d >> 63);
+    }
+    if (borrow) break;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = t[k];
+  }
+}
+
+// Signed c-bit digit of window w given the carry of the windows below; returns the code
+// (bucket << 1 | sign) or MSM_INVALID for a zero digit, and updates the carry.
+__device__ __forceinline__ uint32_t msm_digit_code(const uint32_t (&s)[9], int w, int c, uint32_t B, uint32_t wstride,
+                                                   uint32_t& carry) {
+  int pos = w * c;
+  int word = pos >> 5, sh = pos & 31;
+  uint32_t v = 0;
+  if (word < 8) {
+    uint64_t two = (uint64_t)s[word] | ((uint64_t)s[word + 1] << 32);
+    v = (uint32_t)(two >> sh) & ((1u << c) - 1);
+  }
+  v += carry;
+  if (v > B) {  // digit = v - 2^c (negative), |digit| = 2^c - v in [1, B-1]
+    uint32_t mag = (1u << c) - v;
+    carry = 1;
+    return mag ? ((((uint32_t)w * wstride + (mag - 1)) << 1) | 1u) : MSM_INVALID;
+  }
+  carry = 0;
+  return v ? (((uint32_t)w * wstride + (v - 1)) << 1) : MSM_INVALID;
+}
+
+struct MsmPartArgs {
+  const uint32_t* scalars;
+  uint64_t n;
+  int c, W;
+  uint32_t B, wstride;
+  uint32_t nbins, nblocks, pts_per_block;
+  uint32_t pre_stride, pre_offset;
+  int low_bits;  // bucket bits sorted per bin in shared memory
+};
+
+// SCATTER == false: blk[bin * nblocks + block] = number of this block's digits in the bin.
+// SCATTER == true : blk holds the scanned counts; pairs go to their reserved slots.
+template <bool SCATTER>
+__global__ void __launch_bounds__(MSM_PART_THREADS) msm_part_kernel(MsmPartArgs a, uint32_t* __restrict__ blk,
+                                                                      uint2* __restrict__ pairs) {
+  extern __shared__ uint32_t part_h[];
+  for (uint32_t k = threadIdx.x; k < a.nbins; k += MSM_PART_THREADS)
+    part_h[k] = SCATTER ? blk[(uint64_t)k * a.nblocks + blockIdx.x] : 0u;
+  __syncthreads();
+  const uint64_t i0 = (uint64_t)blockIdx.x * a.pts_per_block;
+  uint64_t i1 = i0 + a.pts_per_block;
+  if (i1 > a.n) i1 = a.n;
+  for (uint64_t i = i0 + threadIdx.x; i < i1; i += MSM_PART_THREADS) {
+    uint32_t s[9];
+    msm_load_scalar(a.scalars, i, s);
+    uint32_t carry = 0;
+    for (int w = 0; w < a.W; w++) {
+      uint32_t code = msm_digit_code(s, w, a.c, a.B, a.wstride, carry);
+      if (code == MSM_INVALID) continue;
+      uint32_t bucket = code >> 1;
+      uint32_t pos = atomicAdd(&part_h[bucket >> a.low_bits], 1u);
+      if (SCATTER) {
+        uint32_t e = (uint32_t)i;
+        if (a.pre_stride) e += (uint32_t)w * a.pre_stride + a.pre_offset;
+        pairs[pos] = make_uint2(((bucket & ((1u << a.low_bits) - 1)) << 1) | (code & 1u), e);
+      }
+    }
+  }
+  if (!SCATTER) {
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < a.nbins; k += MSM_PART_THREADS) blk[(uint64_t)k * a.nblocks + blockIdx.x] = part_h[k];
+  }
+}
+
+// One block per bin.  blk_off: scanned per-(bin, block) counts, so bin k owns pairs
+// [blk_off[k * nblocks], blk_off[(k + 1) * nblocks]) (the scan's grand total closes the last bin).
+template <int LOW>
+__global__ void __launch_bounds__(1 << LOW) msm_part_sort_kernel(const uint2* __restrict__ pairs,
+                                                                 const uint32_t* __restrict__ blk_off, uint32_t nblocks,
+                                                                 uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
+  constexpr uint32_t L = 1u << LOW;  // == blockDim.x: one low-bits counter per thread
+  __shared__ uint32_t h[L];
+  __shared__ uint32_t total;
+  const uint32_t bin = blockIdx.x;
+  const uint32_t beg = blk_off[(uint64_t)bin * nblocks], end = blk_off[(uint64_t)(bin + 1) * nblocks];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t k = beg + threadIdx.x; k < end; k += L) atomicAdd(&h[pairs[k].x >> 1], 1u);
+  __syncthreads();
+  uint32_t cnt = h[threadIdx.x];
+  uint32_t ex = block_exclusive_scan(cnt, &total) + beg;
+  offsets[(uint64_t)bin * L + threadIdx.x] = ex;
+  if (bin == gridDim.x - 1 && threadIdx.x == 0) offsets[(uint64_t)gridDim.x * L] = end;
+  h[threadIdx.x] = ex;
+  __syncthreads();
+  for (uint32_t k = beg + threadIdx.x; k < end; k += L) {
+    uint2 e = pairs[k];
+    uint32_t pos = atomicAdd(&h[e.x >> 1], 1u);
+    sorted[pos] = e.y | ((e.x & 1u) << 31);
+  }
+}
+
+static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, int c, int W, uint32_t B,
+                                  uint32_t wstride, uint32_t* __restrict__ codes, uint32_t* __restrict__ hist) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[9];
+  msm_load_scalar(scalars, i, s);
+  uint32_t carry = 0;
+  for (int w = 0; w < W; w++) {
+    uint32_t code = msm_digit_code(s, w, c, B, wstride, carry);
+    codes[(uint64_t)w * n + i] = code;
+    if (code != MSM_INVALID) atomicAdd(&hist[code >> 1], 1u);
+  }
 }
 
 // ---------------------------------------------------------------- stage 3: bucket accumulation
@@ -379,61 +479,6 @@ __global__ void __launch_bounds__(128) msm_bucket_fold_heavy_kernel(const XYZZ<F
     }
     if (threadIdx.x == 0) buckets[b] = acc;
     __syncthreads();
-  }
-}
-
-// EXPERIMENT: pairwise affine additions with a shared inversion (see zkp_dbg_affine_pairs).
-// Thread t owns outputs t, t + T, ... (B of them).  Pass 1 multiplies the denominators up, one inversion,
-// pass 2 walks back: lambda = num / den, x3 = lambda^2 - x1 - x2, y3 = lambda (x1 - x3) - y1.
-// den = x2 - x1, or 2 y1 when the points are equal (num = 3 x1^2), or 1 when the sum is trivial.
-template <class F, int B>
-__global__ void __launch_bounds__(128) affine_pair_add_kernel(const Affine<F>* __restrict__ in, uint32_t n_out,
-                                                               Affine<F>* __restrict__ out) {
-  const uint32_t T = gridDim.x * blockDim.x;
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  F pre[B];
-  F acc = F::one();
-#pragma unroll 1
-  for (int k = 0; k < B; k++) {
-    uint32_t i = t + (uint32_t)k * T;
-    pre[k] = acc;
-    if (i < n_out) {
-      F x1 = in[2 * i].x, x2 = in[2 * i + 1].x;
-      F d = x2 - x1;
-      if (d.is_zero()) {
-        F y1 = in[2 * i].y, y2 = in[2 * i + 1].y;
-        d = (y1 == y2 && !y1.is_zero()) ? y1.dbl() : F::one();
-      }
-      if (in[2 * i].is_inf() || in[2 * i + 1].is_inf()) d = F::one();
-      acc = acc * d;
-    }
-  }
-  F inv = acc.inv();
-#pragma unroll 1
-  for (int k = B - 1; k >= 0; k--) {
-    uint32_t i = t + (uint32_t)k * T;
-    if (i >= n_out) continue;
-    Affine<F> p = in[2 * i], q = in[2 * i + 1];
-    Affine<F> r;
-    if (p.is_inf()) { out[i] = q; continue; }
-    if (q.is_inf()) { out[i] = p; continue; }
-    F d = q.x - p.x, num = q.y - p.y;
-    if (d.is_zero()) {
-      if (num.is_zero() && !p.y.is_zero()) {
-        d = p.y.dbl();
-        F xx = p.x.sqr();
-        num = xx.dbl() + xx;
-      } else {
-        out[i] = Affine<F>::inf();
-        continue;
-      }
-    }
-    F dinv = inv * pre[k];
-    inv = inv * d;
-    F lam = num * dinv;
-    r.x = lam.sqr() - p.x - q.x;
-    r.y = lam * (p.x - r.x) - p.y;
-    out[i] = r;
   }
 }
 
@@ -639,24 +684,89 @@ __global__ void fe_from_mont_kernel(FE* __restrict__ v, uint64_t n) {
   if (i < n) v[i] = v[i].from_mont();
 }
 
+// Result of an MSM whose single bucket set (window-precomputed table) was reduced in `count` bucket-range
+// parts: part p covers buckets [off_p, off_p + m_p) and its recursion ends with E_p = sum_j (j + 1) B_(off_p + j)
+// and A_p = m_p * sum_j B_(off_p + j), so the whole weighted sum is sum_p (E_p + (off_p / m_p) * A_p).
+struct MsmPartsFinal {
+  const void* A[8];
+  const void* E[8];
+  uint32_t k[8];  // off_p / m_p (parts are power-of-two sized and sorted by decreasing size, so this is an integer)
+  int count;
+};
+template <class F>
+__global__ void msm_final_parts_kernel(MsmPartsFinal f, Affine<F>* __restrict__ out, int* __restrict__ inf_flag,
+                                       XYZZ<F>* __restrict__ out_xyzz) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  XYZZ<F> r = XYZZ<F>::inf();
+  for (int p = 0; p < f.count; p++) {
+    r.add(*reinterpret_cast<const XYZZ<F>*>(f.E[p]));
+    uint32_t k = f.k[p];
+    if (k) {  // k * A_p, k < 2^8: double-and-add from the top bit
+      XYZZ<F> a = *reinterpret_cast<const XYZZ<F>*>(f.A[p]);
+      XYZZ<F> t = XYZZ<F>::inf();
+      for (int b = 31 - __clz(k); b >= 0; b--) {
+        t = t.dbl();
+        if ((k >> b) & 1u) t.add(a);
+      }
+      r.add(t);
+    }
+  }
+  if (out_xyzz) *out_xyzz = r;
+  if (out) {
+    Affine<F> a = r.to_affine();
+    *inf_flag = r.is_inf() ? 1 : 0;
+    a.x = a.x.from_mont();
+    a.y = a.y.from_mont();
+    *out = a;
+  }
+}
+
 // ---------------------------------------------------------------- host driver
+// Tunables (zkp_msm_set_option; 0 = automatic everywhere).
+struct MsmOptions {
+  int window_bits = 0;  // plain tables: window width override
+  int sort = 0;         // 1 = counting sort with global atomics, 2 = radix partition
+  int split = 0;        // bucket-range parts of a precomputed-table MSM: 1 = none, 2 / 3 / 4 = that many
+};
+MsmOptions& msm_options();  // defined in msm_g1.cu
+
+static constexpr int MSM_MAX_PARTS = 4;
+
 template <class F>
 struct MsmEngine {
   using FC = typename CompactOf<F>::type;  // same layout, out-of-line products (small code)
-  DevBuf codes, sorted, hist, offsets, cursor, tile_sums, buckets, lvlA[2], lvlE[2], result, flag;
-  DevBuf ntask, task_base, len_bins, tasks, partials, folded, heavy;
+  DevBuf codes, sorted, hist, offsets, cursor, tile_sums, buckets, result, flag, pairs, blk_hist, blk_off;
+  // per bucket-range part: task lists, partial sums, reduction levels
+  struct PartWs {
+    DevBuf ntask, task_base, len_bins, tasks, partials, heavy, lvlA[2], lvlE[2];
+    uint32_t off = 0, m = 0;
+    const void* A_final = nullptr;
+    const void* E_final = nullptr;
+  } part[MSM_MAX_PARTS];
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev_acc[MSM_MAX_PARTS] = {}, ev_red[MSM_MAX_PARTS] = {};
   int reduce_L = 8;
   uint32_t wide_threshold = 1u << 17;  // items (all windows) above which a level is throughput bound
   uint32_t quad_threshold = 1u << 12;  // radix-2 outputs (all windows) below which a level is latency bound
 
-  // pts: device, affine Montgomery; scalars: device, canonical.  Leaves the affine canonical result
-  // in `result` (and the infinity flag in `flag`), or the XYZZ Montgomery partial sum when
-  // want_xyzz (multi-GPU shards).  Returns the number of kernels launched.
+  void ensure_streams() {
+    if (aux[0]) return;
+    int lo = 0, hi = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    // the reductions that run beside a later part's accumulation are latency bound: their (few, small)
+    // blocks take the SM slots that free up first
+    for (int k = 0; k < 2; k++) CUDA_CHECK(cudaStreamCreateWithPriority(&aux[k], cudaStreamNonBlocking, hi));
+    for (int k = 0; k < MSM_MAX_PARTS; k++) {
+      CUDA_CHECK(cudaEventCreateWithFlags(&ev_acc[k], cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ev_red[k], cudaEventDisableTiming));
+    }
+  }
+
   // Builds the window-precomputed table T[w][i] = 2^(c*w) * P_i (w < W, affine Montgomery) from the n
   // plain points in `src`.  `dst` must hold W*n points; dst[0..n) may alias src.
   int precompute(const Affine<F>* src, uint64_t n, int c, Affine<F>* dst, cudaStream_t st) {
     MsmPlan pl = msm_plan(n, c);
-    DevBuf cur;
+    ScopedDevBuf cur;
     cur.reserve((size_t)n * sizeof(XYZZ<F>));
     int launches = 0;
     if (dst != src) CUDA_CHECK(cudaMemcpyAsync(dst, src, n * sizeof(Affine<F>), cudaMemcpyDeviceToDevice, st));
@@ -672,10 +782,195 @@ struct MsmEngine {
       launches += 2;
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
-    cur.release();
     return launches;
   }
 
+  int scan_u32(const uint32_t* in, uint32_t count, uint32_t* out, cudaStream_t st) {
+    uint32_t ntiles = ceil_div(count, SCAN_TILE);
+    tile_sums.reserve((size_t)ntiles * 4);
+    scan_tile_sums_kernel<<<ntiles, SCAN_BLOCK, 0, st>>>(in, count, tile_sums.as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    scan_tile_offsets_kernel<<<1, SCAN_BLOCK, 0, st>>>(tile_sums.as<uint32_t>(), ntiles);
+    CUDA_CHECK_LAUNCH();
+    scan_apply_kernel<<<ntiles, SCAN_BLOCK, 0, st>>>(in, count, tile_sums.as<uint32_t>(), out);
+    CUDA_CHECK_LAUNCH();
+    return 3;
+  }
+
+  // ---- stages 1 + 2: `sorted` (entry | sign << 31, grouped by bucket) and `offsets` (nbuckets + 1)
+  int sort_entries(const uint32_t* scalars, uint64_t n, const MsmPlan& pl, uint32_t wstride, uint32_t pre_stride,
+                   uint32_t pre_offset, cudaStream_t st, StageTrace& tr) {
+    const uint64_t total = (uint64_t)pl.W * n;
+    int launches = 0;
+    sorted.reserve(total * 4);
+    offsets.reserve(((size_t)pl.nbuckets + 1) * 4);
+    int mode = msm_options().sort;
+    // the partition wants whole bins of 2^low consecutive buckets and enough bins to spread over the SMs
+    const int low = pl.nbuckets >= (1u << 18) ? 10 : 8;
+    const bool can_radix = pl.c >= 16 && (pl.nbuckets >> low) <= 4096;
+    if (mode == 0) mode = (can_radix && total >= (1u << 21)) ? 2 : 1;
+    if (mode == 2 && !can_radix) mode = 1;
+    if (mode == 2) {
+      MsmPartArgs a;
+      a.scalars = scalars;
+      a.n = n;
+      a.c = pl.c;
+      a.W = pl.W;
+      a.B = pl.B;
+      a.wstride = wstride;
+      a.low_bits = low;
+      a.nbins = pl.nbuckets >> low;
+      a.pts_per_block = 1024;
+      while (ceil_div(n, a.pts_per_block) > 4096) a.pts_per_block *= 2;
+      a.nblocks = ceil_div(n, a.pts_per_block);
+      a.pre_stride = pre_stride;
+      a.pre_offset = pre_offset;
+      const uint32_t cells = a.nbins * a.nblocks;
+      blk_hist.reserve((size_t)cells * 4);
+      blk_off.reserve(((size_t)cells + 1) * 4);
+      pairs.reserve(total * sizeof(uint2));
+      msm_part_kernel<false><<<a.nblocks, MSM_PART_THREADS, a.nbins * 4, st>>>(a, blk_hist.as<uint32_t>(), nullptr);
+      CUDA_CHECK_LAUNCH();
+      launches += 1 + scan_u32(blk_hist.as<uint32_t>(), cells, blk_off.as<uint32_t>(), st);
+      tr.mark("digits+scan");
+      msm_part_kernel<true><<<a.nblocks, MSM_PART_THREADS, a.nbins * 4, st>>>(a, blk_off.as<uint32_t>(), pairs.as<uint2>());
+      CUDA_CHECK_LAUNCH();
+      if (low == 10)
+        msm_part_sort_kernel<10><<<a.nbins, 1024, 0, st>>>(pairs.as<uint2>(), blk_off.as<uint32_t>(), a.nblocks,
+                                                          offsets.as<uint32_t>(), sorted.as<uint32_t>());
+      else
+        msm_part_sort_kernel<8><<<a.nbins, 256, 0, st>>>(pairs.as<uint2>(), blk_off.as<uint32_t>(), a.nblocks,
+                                                        offsets.as<uint32_t>(), sorted.as<uint32_t>());
+      CUDA_CHECK_LAUNCH();
+      launches += 2;
+      tr.mark("scatter");
+      return launches;
+    }
+    codes.reserve(total * 4);
+    hist.reserve((size_t)pl.nbuckets * 4);
+    cursor.reserve(((size_t)pl.nbuckets + 1) * 4);
+    CUDA_CHECK(cudaMemsetAsync(hist.p, 0, (size_t)pl.nbuckets * 4, st));
+    msm_digits_kernel<<<ceil_div(n, 256), 256, 0, st>>>(scalars, n, pl.c, pl.W, pl.B, wstride, codes.as<uint32_t>(),
+                                                       hist.as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    launches += 1 + scan_u32(hist.as<uint32_t>(), pl.nbuckets, offsets.as<uint32_t>(), st);
+    tr.mark("digits+scan");
+    CUDA_CHECK(cudaMemcpyAsync(cursor.p, offsets.p, ((size_t)pl.nbuckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    msm_scatter_kernel<<<ceil_div(total, 256), 256, 0, st>>>(codes.as<uint32_t>(), total, n, cursor.as<uint32_t>(),
+                                                            sorted.as<uint32_t>(), pre_stride, pre_offset);
+    CUDA_CHECK_LAUNCH();
+    launches++;
+    tr.mark("scatter");
+    return launches;
+  }
+
+  // ---- stage 3a: tasks of the buckets [pw.off, pw.off + pw.m): count -> scan -> length histogram -> emit
+  // sorted by length.  `max_tasks` bounds the data-dependent task count.
+  int build_tasks(PartWs& pw, uint32_t max_tasks, cudaStream_t st) {
+    const uint32_t* off = offsets.as<uint32_t>() + pw.off;
+    pw.ntask.reserve(((size_t)pw.m + 1) * 4);
+    pw.task_base.reserve(((size_t)pw.m + 1) * 4);
+    pw.len_bins.reserve((MSM_TASK_LEN + 1) * 4);
+    pw.tasks.reserve((size_t)max_tasks * sizeof(uint4));
+    pw.partials.reserve((size_t)max_tasks * sizeof(XYZZ<F>));
+    msm_task_count_kernel<<<ceil_div(pw.m, 256), 256, 0, st>>>(off, pw.m, pw.ntask.template as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    int launches = 1 + scan_u32(pw.ntask.template as<uint32_t>(), pw.m, pw.task_base.template as<uint32_t>(), st);
+    CUDA_CHECK(cudaMemsetAsync(pw.len_bins.p, 0, (MSM_TASK_LEN + 1) * 4, st));
+    msm_task_hist_kernel<<<ceil_div(pw.m, 256), 256, 0, st>>>(off, pw.m, pw.len_bins.template as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    msm_task_bins_kernel<<<1, 32, 0, st>>>(pw.len_bins.template as<uint32_t>());
+    CUDA_CHECK_LAUNCH();
+    msm_task_emit_kernel<<<ceil_div(pw.m, 256), 256, 0, st>>>(off, pw.task_base.template as<uint32_t>(), pw.m,
+                                                             pw.len_bins.template as<uint32_t>(), pw.tasks.template as<uint4>());
+    CUDA_CHECK_LAUNCH();
+    return launches + 3;
+  }
+
+  // ---- stage 3b + 4: fold the partial sums of the part's buckets, then the weighted-sum recursion down
+  // to one item per window.  `overlapped`: the part runs beside a later part's accumulation, so its fused
+  // blocks are kept small enough (128 threads) to take the SM slot of a single retiring accumulate block.
+  int reduce_part(PartWs& pw, int n_windows, uint64_t entries_hint, bool overlapped, cudaStream_t st, StageTrace* tr) {
+    int launches = 0;
+    XYZZ<FC>* bk = buckets.as<XYZZ<FC>>() + pw.off;
+    pw.heavy.reserve(((size_t)pw.m + 1) * 4);
+    CUDA_CHECK(cudaMemsetAsync(pw.heavy.p, 0, 4, st));
+    msm_bucket_fold_kernel<FC><<<ceil_div(pw.m, 128), 128, 0, st>>>(
+        pw.partials.template as<XYZZ<FC>>(), pw.task_base.template as<uint32_t>(), pw.m, bk, pw.heavy.template as<uint32_t>(),
+        pw.heavy.template as<uint32_t>() + 1,
+        // "heavy" is relative to the average bucket: every bucket of a dense MSM (many entries per
+        // bucket) folds serially in parallel with the others; only outliers get a whole block
+        MSM_FOLD_SERIAL + 3 * (uint32_t)(entries_hint / MSM_TASK_LEN));
+    CUDA_CHECK_LAUNCH();
+    msm_bucket_fold_heavy_kernel<FC><<<296, 128, 0, st>>>(pw.partials.template as<XYZZ<FC>>(), pw.task_base.template as<uint32_t>(),
+                                                          pw.heavy.template as<uint32_t>(), pw.heavy.template as<uint32_t>() + 1, bk);
+    CUDA_CHECK_LAUNCH();
+    launches += 2;
+    if (tr) tr->mark("fold");
+    uint32_t n_in = pw.m / n_windows;  // buckets per window
+    const XYZZ<FC>* A = bk;
+    const XYZZ<FC>* E = nullptr;
+    int pp = 0;
+    const uint32_t seg_max = overlapped ? 32u : (uint32_t)WsFused<FC>::SEG;
+    while (n_in > 1) {
+      // wide levels (many items): radix reduce_L running sums, fewest group operations per bucket;
+      // middle levels: radix 2, one thread per output (still throughput bound);
+      // narrow levels: fused segments on quads of lanes, shortest dependency chain.
+      bool wide = (uint64_t)n_in * n_windows >= (uint64_t)wide_threshold && n_in >= (uint32_t)reduce_L;
+      bool fused = !wide && (uint64_t)(n_in / 2) * n_windows <= (uint64_t)quad_threshold;
+      uint32_t L = wide ? (uint32_t)reduce_L : 2u;
+      if (fused) L = n_in < seg_max ? n_in : seg_max;
+      int logL = 0;
+      while ((1u << logL) < L) logL++;
+      uint32_t T = n_in / L;
+      size_t bytes = (size_t)T * n_windows * sizeof(XYZZ<F>);
+      pw.lvlA[pp].reserve(bytes);
+      pw.lvlE[pp].reserve(bytes);
+      XYZZ<FC>* Ao = pw.lvlA[pp].template as<XYZZ<FC>>();
+      XYZZ<FC>* Eo = pw.lvlE[pp].template as<XYZZ<FC>>();
+      if (wide)
+        msm_ws_level_kernel<FC><<<ceil_div((uint64_t)T * n_windows, 64), 64, 0, st>>>(A, E, n_in, L, logL, n_windows, Ao, Eo);
+      else if (fused)
+        // a role-0 and a role-1 warp per 8 chunks of the first level, never less than one pair of whole warps
+        msm_ws2_fused_kernel<FC><<<T * n_windows, L * 4 < 64 ? 64 : L * 4, 2 * WsFused<FC>::SEG * sizeof(XYZZ<FC>), st>>>(A, E, L, Ao, Eo);
+      else
+        msm_ws2_kernel<FC><<<ceil_div((uint64_t)ceil_div((uint64_t)T * n_windows, 32) * 64, 64), 64, 0, st>>>(A, E, n_in, n_windows, Ao, Eo);
+      CUDA_CHECK_LAUNCH();
+      launches++;
+      A = Ao;
+      E = Eo;
+      n_in = T;
+      pp ^= 1;
+      if (tr) tr->mark(wide ? "ws wide" : fused ? "ws fused" : "ws2");
+    }
+    pw.A_final = A;
+    pw.E_final = E ? E : A;  // no level ran (one bucket per window): the bucket has weight 1 = itself
+    return launches;
+  }
+
+  // Bucket-range parts of a single-bucket-set MSM (window-precomputed table), largest first and every
+  // offset a multiple of its part's size: {1/2, 1/2}, {1/2, 1/4, 1/4} or {1/2, 1/4, 1/8, 1/8}.  The
+  // reduction of part p (a few hundred microseconds, mostly dependent group operations on a handful of
+  // warps) runs on a side stream while the accumulation of part p + 1 keeps the integer pipe full; only
+  // the LAST -- smallest -- part's reduction is left exposed.
+  int plan_parts(uint32_t nbuckets, bool single_set) {
+    int want = msm_options().split;
+    if (want == 0) want = nbuckets >= (1u << 18) ? 4 : nbuckets >= (1u << 16) ? 2 : 1;
+    if (!single_set || nbuckets < (1u << 14)) want = 1;
+    if (want > MSM_MAX_PARTS) want = MSM_MAX_PARTS;
+    uint32_t off = 0;
+    for (int p = 0; p < want; p++) {
+      uint32_t m = p + 1 < want ? nbuckets >> (p + 1) : nbuckets - off;
+      part[p].off = off;
+      part[p].m = m;
+      off += m;
+    }
+    return want;
+  }
+
+  // pts: device, affine Montgomery; scalars: device, canonical.  Leaves the affine canonical result
+  // in `result` (and the infinity flag in `flag`), or the XYZZ Montgomery partial sum when
+  // want_xyzz (multi-GPU shards).  Returns the number of kernels launched.
   // pre_stride != 0: `pts` is the base of a window-precomputed table [w][i] built with window width
   // force_c; the MSM covers points [pre_offset, pre_offset + n) of it.
   int run(const Affine<F>* pts, const uint32_t* scalars, uint64_t n, cudaStream_t st, bool want_xyzz = false,
@@ -696,131 +991,60 @@ struct MsmEngine {
     MsmPlan pl = msm_plan(n, force_c);
     uint64_t total = (uint64_t)pl.W * n;
     if (total >= (1ull << 32)) throw std::runtime_error("msm: W*n must be < 2^32");
+    if (pre_stride && (uint64_t)pl.W * pre_stride >= (1ull << 31))
+      throw std::runtime_error("msm: precomputed table too large for 31-bit entry indices");
     const uint32_t wstride = pre_stride ? 0u : pl.B;
     if (pre_stride) pl.nbuckets = pl.B;  // precomputed windows: every digit of every window lands in one bucket set
-    codes.reserve(total * 4);
-    sorted.reserve(total * 4);
-    hist.reserve((size_t)pl.nbuckets * 4);
-    offsets.reserve(((size_t)pl.nbuckets + 1) * 4);
-    cursor.reserve(((size_t)pl.nbuckets + 1) * 4);
-    uint32_t ntiles = ceil_div(pl.nbuckets, SCAN_TILE);
-    tile_sums.reserve((size_t)ntiles * 4);
+    const int n_windows = pre_stride ? 1 : pl.W;
     buckets.reserve((size_t)pl.nbuckets * sizeof(XYZZ<F>));
 
     StageTrace tr(st);
-    CUDA_CHECK(cudaMemsetAsync(hist.p, 0, (size_t)pl.nbuckets * 4, st));
-    msm_digits_kernel<<<ceil_div(n, 256), 256, 0, st>>>(scalars, n, pl.c, pl.W, pl.B, wstride, codes.as<uint32_t>(),
-                                                       hist.as<uint32_t>());
-    CUDA_CHECK_LAUNCH();
-    scan_tile_sums_kernel<<<ntiles, SCAN_BLOCK, 0, st>>>(hist.as<uint32_t>(), pl.nbuckets, tile_sums.as<uint32_t>());
-    CUDA_CHECK_LAUNCH();
-    scan_tile_offsets_kernel<<<1, SCAN_BLOCK, 0, st>>>(tile_sums.as<uint32_t>(), ntiles);
-    CUDA_CHECK_LAUNCH();
-    scan_apply_kernel<<<ntiles, SCAN_BLOCK, 0, st>>>(hist.as<uint32_t>(), pl.nbuckets, tile_sums.as<uint32_t>(),
-                                                    offsets.as<uint32_t>());
-    CUDA_CHECK_LAUNCH();
-    tr.mark("digits+scan");
-    CUDA_CHECK(cudaMemcpyAsync(cursor.p, offsets.p, ((size_t)pl.nbuckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
-    if (pre_stride && (uint64_t)pl.W * pre_stride >= (1ull << 31))
-      throw std::runtime_error("msm: precomputed table too large for 31-bit entry indices");
-    msm_scatter_kernel<<<ceil_div(total, 256), 256, 0, st>>>(codes.as<uint32_t>(), total, n, cursor.as<uint32_t>(),
-                                                            sorted.as<uint32_t>(), pre_stride, pre_offset);
-    CUDA_CHECK_LAUNCH();
-    tr.mark("scatter");
-    // tasks: count per bucket -> scan -> length histogram -> emit sorted by length
-    ntask.reserve(((size_t)pl.nbuckets + 1) * 4);
-    task_base.reserve(((size_t)pl.nbuckets + 1) * 4);
-    len_bins.reserve((MSM_TASK_LEN + 1) * 4);
-    uint32_t max_tasks = (uint32_t)(total / MSM_TASK_LEN) + pl.nbuckets + 1;
-    tasks.reserve((size_t)max_tasks * sizeof(uint4));
-    partials.reserve((size_t)max_tasks * sizeof(XYZZ<F>));
-    msm_task_count_kernel<<<ceil_div(pl.nbuckets, 256), 256, 0, st>>>(offsets.as<uint32_t>(), pl.nbuckets,
-                                                                     ntask.as<uint32_t>());
-    CUDA_CHECK_LAUNCH();
-    scan_tile_sums_kernel<<<ntiles, SCAN_BLOCK, 0, st>>>(ntask.as<uint32_t>(), pl.nbuckets, tile_sums.as<uint32_t>());
-    CUDA_CHECK_LAUNCH();
-    scan_tile_offsets_kernel<<<1, SCAN_BLOCK, 0, st>>>(tile_sums.as<uint32_t>(), ntiles);
-    CUDA_CHECK_LAUNCH();
-    scan_apply_kernel<<<ntiles, SCAN_BLOCK, 0, st>>>(ntask.as<uint32_t>(), pl.nbuckets, tile_sums.as<uint32_t>(),
-                                                    task_base.as<uint32_t>());
-    CUDA_CHECK_LAUNCH();
-    CUDA_CHECK(cudaMemsetAsync(len_bins.p, 0, (MSM_TASK_LEN + 1) * 4, st));
-    msm_task_hist_kernel<<<ceil_div(pl.nbuckets, 256), 256, 0, st>>>(offsets.as<uint32_t>(), pl.nbuckets,
-                                                                    len_bins.as<uint32_t>());
-    CUDA_CHECK_LAUNCH();
-    msm_task_bins_kernel<<<1, 32, 0, st>>>(len_bins.as<uint32_t>());
-    CUDA_CHECK_LAUNCH();
-    msm_task_emit_kernel<<<ceil_div(pl.nbuckets, 256), 256, 0, st>>>(offsets.as<uint32_t>(), task_base.as<uint32_t>(),
-                                                                    pl.nbuckets, len_bins.as<uint32_t>(),
-                                                                    tasks.as<uint4>());
-    CUDA_CHECK_LAUNCH();
-    // the task count is data dependent: launch for the upper bound, threads past
-    // task_base[nbuckets] exit at once (no host round trip in the middle of the pipeline)
-    tr.mark("tasks");
-    const uint32_t* d_ntasks = task_base.as<uint32_t>() + pl.nbuckets;
-    // fully inlined field arithmetic here (an out-of-line-product build of this kernel measured 4 % slower)
-    msm_accumulate_kernel<F><<<ceil_div(max_tasks, 128), 128, 0, st>>>(pts, sorted.as<uint32_t>(), tasks.as<uint4>(),
-                                                                      d_ntasks, partials.as<XYZZ<F>>());
-    CUDA_CHECK_LAUNCH();
-    tr.mark("accumulate");
-    heavy.reserve(((size_t)pl.nbuckets + 1) * 4);
-    CUDA_CHECK(cudaMemsetAsync(heavy.p, 0, 4, st));
-    msm_bucket_fold_kernel<FC><<<ceil_div(pl.nbuckets, 128), 128, 0, st>>>(
-        partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(), pl.nbuckets, buckets.as<XYZZ<FC>>(), heavy.as<uint32_t>(),
-        heavy.as<uint32_t>() + 1,
-        // "heavy" is relative to the average bucket: every bucket of a dense MSM (many entries per
-        // bucket) folds serially in parallel with the others; only outliers get a whole block
-        MSM_FOLD_SERIAL + 3 * (uint32_t)(total / pl.nbuckets / MSM_TASK_LEN));
-    CUDA_CHECK_LAUNCH();
-    msm_bucket_fold_heavy_kernel<FC><<<296, 128, 0, st>>>(partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(),
-                                                          heavy.as<uint32_t>(), heavy.as<uint32_t>() + 1,
-                                                          buckets.as<XYZZ<FC>>());
-    CUDA_CHECK_LAUNCH();
-    launches += 16;
+    launches += sort_entries(scalars, n, pl, wstride, pre_stride, pre_offset, st, tr);
 
-    // weighted-sum recursion down to one item per window
-    uint32_t n_in = pl.B;
-    const XYZZ<FC>* A = buckets.as<XYZZ<FC>>();
-    const XYZZ<FC>* E = nullptr;
-    int pp = 0;
-    tr.mark("fold");
-    if (pre_stride) pl.W = 1;  // one shared bucket set: reduce a single "window", no Horner
-    while (n_in > 1) {
-      // wide levels (many items): radix reduce_L running sums, fewest group operations per bucket;
-      // middle levels: radix 2, one thread per output (still throughput bound);
-      // narrow levels: fused segments on quads of lanes, shortest dependency chain.
-      bool wide = (uint64_t)n_in * pl.W >= (uint64_t)wide_threshold && n_in >= (uint32_t)reduce_L;
-      bool fused = !wide && (uint64_t)(n_in / 2) * pl.W <= (uint64_t)quad_threshold;
-      uint32_t L = wide ? (uint32_t)reduce_L : 2u;
-      if (fused) L = n_in < (uint32_t)WsFused<FC>::SEG ? n_in : (uint32_t)WsFused<FC>::SEG;
-      int logL = 0;
-      while ((1u << logL) < L) logL++;
-      uint32_t T = n_in / L;
-      size_t bytes = (size_t)T * pl.W * sizeof(XYZZ<F>);
-      lvlA[pp].reserve(bytes);
-      lvlE[pp].reserve(bytes);
-      if (wide)
-        msm_ws_level_kernel<FC><<<ceil_div((uint64_t)T * pl.W, 64), 64, 0, st>>>(
-            A, E, n_in, L, logL, pl.W, lvlA[pp].template as<XYZZ<FC>>(), lvlE[pp].template as<XYZZ<FC>>());
-      else if (fused)
-        msm_ws2_fused_kernel<FC><<<T * pl.W, WsFused<FC>::SEG * 4, 2 * WsFused<FC>::SEG * sizeof(XYZZ<FC>), st>>>(
-            A, E, L, lvlA[pp].template as<XYZZ<FC>>(), lvlE[pp].template as<XYZZ<FC>>());
-      else
-        msm_ws2_kernel<FC><<<ceil_div((uint64_t)ceil_div((uint64_t)T * pl.W, 32) * 64, 64), 64, 0, st>>>(
-            A, E, n_in, pl.W, lvlA[pp].template as<XYZZ<FC>>(), lvlE[pp].template as<XYZZ<FC>>());
+    const int nparts = plan_parts(pl.nbuckets, pre_stride != 0);
+    if (nparts > 1) ensure_streams();
+    // the task count of a part is data dependent (all entries may fall into it): launch for the upper
+    // bound, threads past task_base[m] exit at once (no host round trip in the middle of the pipeline)
+    uint32_t max_tasks[MSM_MAX_PARTS];
+    for (int p = 0; p < nparts; p++) {
+      max_tasks[p] = (uint32_t)(total / MSM_TASK_LEN) + part[p].m + 1;
+      launches += build_tasks(part[p], max_tasks[p], st);
+    }
+    tr.mark("tasks");
+    for (int p = 0; p < nparts; p++) {
+      PartWs& pw = part[p];
+      // fully inlined field arithmetic here (an out-of-line-product build of this kernel measured 4 % slower)
+      msm_accumulate_kernel<F><<<ceil_div(max_tasks[p], 128), 128, 0, st>>>(
+          pts, sorted.as<uint32_t>(), pw.tasks.template as<uint4>(), pw.task_base.template as<uint32_t>() + pw.m,
+          pw.partials.template as<XYZZ<F>>());
       CUDA_CHECK_LAUNCH();
       launches++;
-      A = lvlA[pp].template as<XYZZ<FC>>();
-      E = lvlE[pp].template as<XYZZ<FC>>();
-      n_in = T;
-      pp ^= 1;
-      tr.mark(wide ? "ws wide" : fused ? "ws fused" : "ws2");
+      if (nparts > 1 && p + 1 < nparts) {
+        CUDA_CHECK(cudaEventRecord(ev_acc[p], st));
+        cudaStream_t side = aux[p & 1];
+        CUDA_CHECK(cudaStreamWaitEvent(side, ev_acc[p], 0));
+        launches += reduce_part(pw, n_windows, total / pl.nbuckets, true, side, nullptr);
+        CUDA_CHECK(cudaEventRecord(ev_red[p], side));
+      }
     }
-    // n_in == 1: V_w = E_w (c == 1 never happens; for B == 1 the single bucket has weight 1 = itself)
-    const XYZZ<FC>* wsum = E ? E : A;
-    msm_final_kernel<FC><<<1, 32, 0, st>>>(wsum, pl.W, pl.c, nullptr, 0,
-                                          want_xyzz ? nullptr : reinterpret_cast<Affine<FC>*>(out_aff), flag.as<int>(),
-                                          want_xyzz ? reinterpret_cast<XYZZ<FC>*>(out_xyzz) : nullptr);
+    tr.mark("accumulate");
+    launches += reduce_part(part[nparts - 1], n_windows, total / pl.nbuckets, false, st, &tr);
+    for (int p = 0; p + 1 < nparts; p++) CUDA_CHECK(cudaStreamWaitEvent(st, ev_red[p], 0));
+    if (nparts == 1) {
+      msm_final_kernel<FC><<<1, 32, 0, st>>>(reinterpret_cast<const XYZZ<FC>*>(part[0].E_final), n_windows, pl.c, nullptr, 0,
+                                            want_xyzz ? nullptr : reinterpret_cast<Affine<FC>*>(out_aff), flag.as<int>(),
+                                            want_xyzz ? reinterpret_cast<XYZZ<FC>*>(out_xyzz) : nullptr);
+    } else {
+      MsmPartsFinal f;
+      f.count = nparts;
+      for (int p = 0; p < nparts; p++) {
+        f.A[p] = part[p].A_final;
+        f.E[p] = part[p].E_final;
+        f.k[p] = part[p].off / part[p].m;
+      }
+      msm_final_parts_kernel<FC><<<1, 32, 0, st>>>(f, want_xyzz ? nullptr : reinterpret_cast<Affine<FC>*>(out_aff),
+                                                  flag.as<int>(), want_xyzz ? reinterpret_cast<XYZZ<FC>*>(out_xyzz) : nullptr);
+    }
     CUDA_CHECK_LAUNCH();
     launches++;
     tr.mark("horner+affine");

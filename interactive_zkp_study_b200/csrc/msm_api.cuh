@@ -1,12 +1,12 @@
 // Group-generic implementation of the MSM / table entry points; instantiated for G1 (msm_g1.cu)
 // and G2 (msm_g2.cu).  See include/zkp_b200.h for the contract of each function.
 #pragma once
+#include "comm.cuh"
 #include "msm.cuh"
 #include "registry.cuh"
 
 namespace zkp {
 
-extern int g_force_window_bits;  // defined in msm_g1.cu
 
 // out[i] = scalars[i] * base: MSB-first double-and-add in XYZZ with mixed additions, one thread per
 // scalar, then one inversion per point.  Replaces the n sequential Python scalar-muls of
@@ -148,7 +148,7 @@ struct GroupApi {
     if (t->pre_c)
       return engine(slot).run(t->buf.as<Affine<F>>(), dscalars, n, st, partial, t->pre_c, (uint32_t)t->n,
                               (uint32_t)offset);
-    return engine(slot).run(t->buf.as<Affine<F>>() + offset, dscalars, n, st, partial, g_force_window_bits);
+    return engine(slot).run(t->buf.as<Affine<F>>() + offset, dscalars, n, st, partial, msm_options().window_bits);
   }
 
   // `count` independent MSMs on one table, alternating between two streams (each with its own
@@ -163,7 +163,7 @@ struct GroupApi {
       std::vector<Resource*> sv(count);
       for (uint32_t k = 0; k < count; k++) {
         sv[k] = need(scalars[k], HandleKind::Scalars, "msm_batch");
-        if (offsets[k] + lens[k] > t->n || sc_off[k] + lens[k] > sv[k]->n) throw InvalidArgument("msm_batch: range out of bounds");
+        if (!range_ok(offsets[k], lens[k], t->n) || !range_ok(sc_off[k], lens[k], sv[k]->n)) throw InvalidArgument("msm_batch: range out of bounds");
       }
       if (!count) return;
       static DevBuf res;
@@ -203,13 +203,11 @@ struct GroupApi {
       if (t->n == 0) return;
       MsmPlan pl = msm_plan(t->n, window_bits);
       if ((uint64_t)pl.W * t->n >= (1ull << 31)) throw InvalidArgument("table_precompute: W*n must be < 2^31");
-      DevBuf big;
+      ScopedDevBuf big;  // several GiB: must not leak if the precomputation runs out of memory half way
       big.reserve((size_t)pl.W * t->n * PT);
       c.launches += engine().precompute(t->buf.as<Affine<F>>(), t->n, window_bits, big.as<Affine<F>>(), c.stream);
       t->buf.release();
-      t->buf = big;
-      big.p = nullptr;
-      big.cap = 0;
+      t->buf = big.detach();
       t->pre_c = window_bits;
     });
   }
@@ -238,7 +236,7 @@ struct GroupApi {
         upload_points(c, pts, n, dp.p);
         CUDA_CHECK(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
       }
-      c.launches += engine().run(dp.as<Affine<F>>(), ds.as<uint32_t>(), n, c.stream, false, g_force_window_bits);
+      c.launches += engine().run(dp.as<Affine<F>>(), ds.as<uint32_t>(), n, c.stream, false, msm_options().window_bits);
       fetch_result(c, out_xy, out_is_inf);
     });
   }
@@ -248,7 +246,7 @@ struct GroupApi {
     return guarded([&](Context& c) {
       Resource* t = need(table, KIND, "msm_table");
       if (!out_xy || (n && !scalars)) throw InvalidArgument("msm_table: null argument");
-      if (offset + n > t->n) throw InvalidArgument("msm_table: point range exceeds the table");
+      if (!range_ok(offset, n, t->n)) throw InvalidArgument("msm_table: point range exceeds the table");
       DevBuf& ds = scratch_scalars();
       if (n) {
         ds.reserve(n * 32);
@@ -265,7 +263,7 @@ struct GroupApi {
       Resource* t = need(table, KIND, "msm_dev");
       Resource* s = need(scalars, HandleKind::Scalars, "msm_dev");
       if (!out) throw InvalidArgument("msm_dev: null output");
-      if (offset + n > t->n || sc_offset + n > s->n) throw InvalidArgument("msm_dev: range out of bounds");
+      if (!range_ok(offset, n, t->n) || !range_ok(sc_offset, n, s->n)) throw InvalidArgument("msm_dev: range out of bounds");
       MsmEngine<F>& e = engine();
       c.launches += run_on_table(c, t, offset, s->buf.as<uint32_t>() + 8 * sc_offset, n, partial);
       if (partial) {
@@ -277,6 +275,54 @@ struct GroupApi {
       } else {
         fetch_result(c, out, out_is_inf);
       }
+    });
+  }
+
+  // Sharded MSM, one rank's call: local Pippenger over this rank's point range -> XYZZ partial
+  // -> all-gather of one partial per rank -> fold + affine, all enqueued on the library stream back to
+  // back; the host only waits for the final 64 / 128 bytes.  Every rank returns the full result.
+  static void multi_tail(Context& c, uint8_t* out_xy, int* out_is_inf) {
+    MsmEngine<F>& e = engine();
+    CommState& cs = comm_state();
+    const size_t PB = sizeof(XYZZ<F>);
+    cs.gathered.reserve((size_t)cs.world * PB);
+    comm_all_gather(e.result.template as<char>() + PT, cs.gathered.p, PB, c.stream);
+    using FC = typename CompactOf<F>::type;
+    combine_partials_kernel<FC><<<1, 32, 0, c.stream>>>(cs.gathered.template as<XYZZ<FC>>(), (uint32_t)cs.world,
+                                                      e.result.template as<Affine<FC>>(), e.flag.template as<int>());
+    CUDA_CHECK_LAUNCH();
+    c.launches++;
+    fetch_result(c, out_xy, out_is_inf);
+  }
+
+  static int msm_multi(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n, uint8_t* out_xy,
+                       int* out_is_inf) {
+    return guarded([&](Context& c) {
+      Resource* t = need(table, KIND, "msm_multi");
+      Resource* s = need(scalars, HandleKind::Scalars, "msm_multi");
+      if (!out_xy) throw InvalidArgument("msm_multi: null output");
+      if (!range_ok(offset, n, t->n) || !range_ok(sc_offset, n, s->n)) throw InvalidArgument("msm_multi: range out of bounds");
+      if (!comm_state().ready) throw InvalidArgument("msm_multi: zkp_comm_init has not been called on this rank");
+      c.launches += run_on_table(c, t, offset, s->buf.as<uint32_t>() + 8 * sc_offset, n, true);
+      multi_tail(c, out_xy, out_is_inf);
+    });
+  }
+
+  // the same with this rank's scalars in host memory (the end-to-end form of the sharded commit)
+  static int msm_multi_host(uint64_t table, uint64_t offset, const uint8_t* scalars, uint64_t n, uint8_t* out_xy,
+                            int* out_is_inf) {
+    return guarded([&](Context& c) {
+      Resource* t = need(table, KIND, "msm_multi_table");
+      if (!out_xy || (n && !scalars)) throw InvalidArgument("msm_multi_table: null argument");
+      if (!range_ok(offset, n, t->n)) throw InvalidArgument("msm_multi_table: point range exceeds the table");
+      if (!comm_state().ready) throw InvalidArgument("msm_multi_table: zkp_comm_init has not been called on this rank");
+      DevBuf& ds = scratch_scalars();
+      if (n) {
+        ds.reserve(n * 32);
+        CUDA_CHECK(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
+      }
+      c.launches += run_on_table(c, t, offset, ds.as<uint32_t>(), n, true);
+      multi_tail(c, out_xy, out_is_inf);
     });
   }
 
@@ -308,7 +354,7 @@ struct GroupApi {
     r->n = n;
     r->buf.reserve_pooled(n ? n * PT : PT);
     if (n >= 4096) {
-      DevBuf tsc, tab;
+      PooledDevBuf tsc, tab;
       tsc.reserve_pooled(8192 * 32);
       tab.reserve_pooled(8192 * PT);
       fixed_base_table_scalars_kernel<<<32, 256, 0, c.stream>>>(tsc.as<uint32_t>());
@@ -320,8 +366,6 @@ struct GroupApi {
       CUDA_CHECK_LAUNCH();
       c.launches += 3;
       CUDA_CHECK(cudaStreamSynchronize(c.stream));
-      tsc.recycle();
-      tab.recycle();
     } else if (n) {
       fixed_base_mul_kernel<F><<<ceil_div(n, 128), 128, 0, c.stream>>>(base, dscalars, n, r->buf.as<Affine<F>>());
       CUDA_CHECK_LAUNCH();
@@ -353,7 +397,7 @@ struct GroupApi {
   }
 
   static void download(Context& c, Resource* t, uint64_t offset, uint64_t n, uint8_t* out_pts) {
-    if (offset + n > t->n) throw InvalidArgument("table_download: range out of bounds");
+    if (!range_ok(offset, n, t->n)) throw InvalidArgument("table_download: range out of bounds");
     if (!n) return;
     DevBuf& dp = scratch_pts();
     dp.reserve(n * PT);

@@ -2,8 +2,9 @@
 #include "msm_api.cuh"
 
 namespace zkp {
-int g_force_window_bits = 0;
-}
+static MsmOptions g_msm_options;
+MsmOptions& msm_options() { return g_msm_options; }
+}  // namespace zkp
 namespace zkp {
 int g2_msm_enqueue(Context& c, uint64_t table, uint64_t scalars, uint64_t n, int slot, char* dev_out);  // msm_g2.cu
 }
@@ -17,8 +18,29 @@ int zkp_msm_set_window_bits(int c) {
     set_last_error("zkp_msm_set_window_bits: c must be 0 or in [2,20]");
     return ZKP_ERR_INVALID_ARGUMENT;
   }
-  g_force_window_bits = c;
+  msm_options().window_bits = c;
   return ZKP_OK;
+}
+
+int zkp_msm_set_option(const char* name, int value) {
+  std::string n = name ? name : "";
+  if (n == "sort" && value >= 0 && value <= 2) msm_options().sort = value;
+  else if (n == "split" && value >= 0 && value <= MSM_MAX_PARTS) msm_options().split = value;
+  else if (n == "window_bits") return zkp_msm_set_window_bits(value);
+  else {
+    set_last_error("zkp_msm_set_option: unknown option or value out of range (sort 0..2, split 0..4, window_bits)");
+    return ZKP_ERR_INVALID_ARGUMENT;
+  }
+  return ZKP_OK;
+}
+
+int zkp_g1_msm_multi(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n,
+                     uint8_t out_xy[64], int* out_is_inf) {
+  return Api::msm_multi(table, offset, scalars, sc_offset, n, out_xy, out_is_inf);
+}
+int zkp_g1_msm_multi_table(uint64_t table, uint64_t offset, const uint8_t* scalars, uint64_t n, uint8_t out_xy[64],
+                           int* out_is_inf) {
+  return Api::msm_multi_host(table, offset, scalars, n, out_xy, out_is_inf);
 }
 
 int zkp_g1_msm(const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t out_xy[64], int* out_is_inf) {
@@ -107,48 +129,6 @@ int zkp_groth16_msms_dev(uint64_t ta, uint64_t sa, uint64_t na, uint64_t tb2, ui
     if (fc) memset(out_c, 0, 64); else memcpy(out_c, host + 128, 64);
     if (fb) memset(out_b, 0, 128); else memcpy(out_b, host + 256, 128);
     if (out_is_inf) { out_is_inf[0] = fa; out_is_inf[1] = fb; out_is_inf[2] = fc; }
-  });
-}
-
-// EXPERIMENT (not on any product path): out[i] = P[2i] + P[2i+1] in affine coordinates with one shared
-// inversion per `batch` additions per thread (Montgomery's trick), to measure what a batched-affine
-// bucket accumulation could reach against the XYZZ mixed addition.  ms: kernel time; out_first: the
-// first `n_check` sums (canonical) for a correctness check.
-int zkp_dbg_affine_pairs(uint64_t table, int batch, double* ms, uint8_t* out_first, uint32_t n_check) {
-  return guarded([&](Context& c) {
-    Resource* t = need(table, HandleKind::G1Table, "zkp_dbg_affine_pairs");
-    if (t->pre_c || !ms) throw InvalidArgument("zkp_dbg_affine_pairs: needs a plain table");
-    uint32_t n_out = (uint32_t)(t->n / 2);
-    DevBuf out;
-    out.reserve((size_t)n_out * sizeof(Affine<Fp>));
-    cudaEvent_t e0, e1;
-    CUDA_CHECK(cudaEventCreate(&e0));
-    CUDA_CHECK(cudaEventCreate(&e1));
-    float best = 1e30f;
-    for (int rep = 0; rep < 4; rep++) {
-      CUDA_CHECK(cudaEventRecord(e0, c.stream));
-      uint32_t threads = ceil_div(n_out, (uint32_t)batch);
-      if (batch == 8) affine_pair_add_kernel<Fp, 8><<<ceil_div(threads, 128), 128, 0, c.stream>>>(t->buf.as<Affine<Fp>>(), n_out, out.as<Affine<Fp>>());
-      else if (batch == 16) affine_pair_add_kernel<Fp, 16><<<ceil_div(threads, 128), 128, 0, c.stream>>>(t->buf.as<Affine<Fp>>(), n_out, out.as<Affine<Fp>>());
-      else if (batch == 32) affine_pair_add_kernel<Fp, 32><<<ceil_div(threads, 128), 128, 0, c.stream>>>(t->buf.as<Affine<Fp>>(), n_out, out.as<Affine<Fp>>());
-      else throw InvalidArgument("zkp_dbg_affine_pairs: batch must be 8, 16 or 32");
-      CUDA_CHECK_LAUNCH();
-      CUDA_CHECK(cudaEventRecord(e1, c.stream));
-      CUDA_CHECK(cudaEventSynchronize(e1));
-      float m;
-      CUDA_CHECK(cudaEventElapsedTime(&m, e0, e1));
-      if (m < best) best = m;
-    }
-    *ms = best;
-    if (out_first && n_check) {
-      if (n_check > n_out) n_check = n_out;
-      fe_from_mont_kernel<Fp><<<ceil_div(n_check * 2, 256), 256, 0, c.stream>>>(out.as<Fp>(), (uint64_t)n_check * 2);
-      CUDA_CHECK(cudaMemcpyAsync(out_first, out.p, (size_t)n_check * 64, cudaMemcpyDeviceToHost, c.stream));
-      CUDA_CHECK(cudaStreamSynchronize(c.stream));
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    out.release();
   });
 }
 

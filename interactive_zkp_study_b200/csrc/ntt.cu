@@ -413,7 +413,7 @@ int zkp_fr_ntt_dev(uint64_t scalars, uint64_t offset, uint32_t log_n, const uint
     if (!omega) throw InvalidArgument("zkp_fr_ntt_dev: null omega");
     if (log_n > 28) throw InvalidArgument("zkp_fr_ntt_dev: log_n must be <= 28");
     uint64_t n = uint64_t(1) << log_n;
-    if (offset + n > s->n) throw InvalidArgument("zkp_fr_ntt_dev: range out of bounds");
+    if (!range_ok(offset, n, s->n)) throw InvalidArgument("zkp_fr_ntt_dev: range out of bounds");
     g_ntt_scratch.reserve(n * 32);
     FrBytes w, cs;
     memcpy(w.b, omega, 32);

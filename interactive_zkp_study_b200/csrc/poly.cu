@@ -131,6 +131,36 @@ __global__ void fr_scale_by_dev_kernel(const Fr* __restrict__ a, const Fr* __res
 // Batch inversion, Montgomery's trick on strided chunks: thread t owns elements t, t+T, t+2T, ...
 // (coalesced), one Fermat inversion per BATCH_INV_CHUNK elements.  Zeros map to zero (py_ecc inv(0)=0).
 // Input and output in the same form F: canonical (mont == 0) or Montgomery (mont == 1).
+// sum_i a[i] * b[i] over canonical vectors: every product is a Montgomery product of two canonical values
+// (= a*b/R); the partial sums stay in that form and the last step multiplies by R^2 (mont: * R) once.
+static constexpr int DOT_THREADS = 256;
+__device__ __forceinline__ Fr dot_block_reduce(Fr acc, Fr* sm) {
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = DOT_THREADS / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sm[threadIdx.x] = sm[threadIdx.x] + sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  return sm[0];
+}
+__global__ void __launch_bounds__(DOT_THREADS) fr_dot_partial_kernel(const Fr* __restrict__ a, const Fr* __restrict__ b,
+                                                                      uint64_t n, Fr* __restrict__ partial) {
+  __shared__ Fr sm[DOT_THREADS];
+  Fr acc = Fr::zero();
+  for (uint64_t i = (uint64_t)blockIdx.x * DOT_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * DOT_THREADS)
+    acc = acc + a[i] * b[i];
+  Fr tot = dot_block_reduce(acc, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(DOT_THREADS) fr_dot_final_kernel(const Fr* __restrict__ partial, uint32_t count,
+                                                                    Fr* __restrict__ out) {
+  __shared__ Fr sm[DOT_THREADS];
+  Fr acc = Fr::zero();
+  for (uint32_t i = threadIdx.x; i < count; i += DOT_THREADS) acc = acc + partial[i];
+  Fr tot = dot_block_reduce(acc, sm);
+  if (threadIdx.x == 0) *out = tot * Fr::r2();
+}
+
 static constexpr int BATCH_INV_CHUNK = 32;
 __global__ void __launch_bounds__(128) fr_batch_inverse_kernel(const Fr* __restrict__ in, uint64_t n, uint64_t T, int mont,
                                                                 Fr* __restrict__ out) {
@@ -845,7 +875,7 @@ int zkp_scalars_copy(uint64_t dst, uint64_t dst_off, uint64_t src, uint64_t src_
   return guarded([&](Context& c) {
     Resource* d = need(dst, HandleKind::Scalars, "zkp_scalars_copy");
     Resource* s = need(src, HandleKind::Scalars, "zkp_scalars_copy");
-    if (dst_off + n > d->n || src_off + n > s->n) throw InvalidArgument("zkp_scalars_copy: range out of bounds");
+    if (!range_ok(dst_off, n, d->n) || !range_ok(src_off, n, s->n)) throw InvalidArgument("zkp_scalars_copy: range out of bounds");
     if (n) CUDA_CHECK(cudaMemcpyAsync(d->buf.as<Fr>() + dst_off, s->buf.as<Fr>() + src_off, n * 32,
                                      cudaMemcpyDeviceToDevice, c.stream));
   });
@@ -854,7 +884,7 @@ int zkp_scalars_copy(uint64_t dst, uint64_t dst_off, uint64_t src, uint64_t src_
 int zkp_scalars_upload(uint64_t dst, uint64_t dst_off, const uint8_t* host, uint64_t n) {
   return guarded([&](Context& c) {
     Resource* d = need(dst, HandleKind::Scalars, "zkp_scalars_upload");
-    if (dst_off + n > d->n || (n && !host)) throw InvalidArgument("zkp_scalars_upload: bad range or null source");
+    if (!range_ok(dst_off, n, d->n) || (n && !host)) throw InvalidArgument("zkp_scalars_upload: bad range or null source");
     if (n) CUDA_CHECK(cudaMemcpyAsync(d->buf.as<Fr>() + dst_off, host, n * 32, cudaMemcpyHostToDevice, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
   });
@@ -863,7 +893,7 @@ int zkp_scalars_upload(uint64_t dst, uint64_t dst_off, const uint8_t* host, uint
 int zkp_scalars_scale(uint64_t h, uint64_t off, uint64_t n, const uint8_t k[32]) {
   return guarded([&](Context& c) {
     Resource* d = need(h, HandleKind::Scalars, "zkp_scalars_scale");
-    if (off + n > d->n || !k) throw InvalidArgument("zkp_scalars_scale: bad range or null factor");
+    if (!range_ok(off, n, d->n) || !k) throw InvalidArgument("zkp_scalars_scale: bad range or null factor");
     if (!n) return;
     ArenaScope scope;
     Fr* dk = g_arena.alloc(1);
@@ -877,7 +907,7 @@ int zkp_scalars_scale(uint64_t h, uint64_t off, uint64_t n, const uint8_t k[32])
 int zkp_fr_poly_eval_dev(uint64_t h, uint64_t off, uint64_t n, const uint8_t x[32], uint8_t out[32]) {
   return guarded([&](Context& c) {
     Resource* d = need(h, HandleKind::Scalars, "zkp_fr_poly_eval_dev");
-    if (off + n > d->n || !x || !out) throw InvalidArgument("zkp_fr_poly_eval_dev: bad argument");
+    if (!range_ok(off, n, d->n) || !x || !out) throw InvalidArgument("zkp_fr_poly_eval_dev: bad argument");
     if (!n) {
       memset(out, 0, 32);
       return;
@@ -970,7 +1000,7 @@ static Fr fr_from_bytes(const uint8_t* b) {
 }
 static Fr* hptr(uint64_t h, uint64_t off, uint64_t n, const char* what) {
   Resource* r = need(h, HandleKind::Scalars, what);
-  if (off + n > r->n) throw InvalidArgument(std::string(what) + ": range out of bounds");
+  if (!range_ok(off, n, r->n)) throw InvalidArgument(std::string(what) + ": range out of bounds");
   return r->buf.as<Fr>() + off;
 }
 // canonical constant -> Montgomery on the device (one tiny kernel + 32-byte read back)
@@ -1165,6 +1195,33 @@ int zkp_fr_lincomb_dev(uint64_t dst, uint64_t dst_off, uint64_t n, uint32_t coun
     fr_lincomb_kernel<<<GRID_1D(n)>>>(a, n, d);
     CUDA_CHECK_LAUNCH();
     c.launches++;
+  });
+}
+
+// <a, b> = sum_i a[i] * b[i] mod r of two device-resident canonical vectors.  The O(1)-host verification
+// of an MSM over points with known discrete logs, sum_i k_i (s_i G) == (<k, s>) G, at any size;
+// also sum_i c_i x^i style evaluations against a powers vector.
+int zkp_fr_dot_dev(uint64_t a, uint64_t a_off, uint64_t b, uint64_t b_off, uint64_t n, uint8_t out[32]) {
+  return guarded([&](Context& c) {
+    if (!out) throw InvalidArgument("zkp_fr_dot_dev: null output");
+    if (!n) {
+      memset(out, 0, 32);
+      return;
+    }
+    ArenaScope scope;
+    Fr* pa = hptr(a, a_off, n, "zkp_fr_dot_dev");
+    Fr* pb = hptr(b, b_off, n, "zkp_fr_dot_dev");
+    uint32_t blocks = ceil_div(n, DOT_THREADS);
+    uint32_t cap = (uint32_t)c.sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    Fr* partial = g_arena.alloc(blocks + 1);
+    fr_dot_partial_kernel<<<blocks, DOT_THREADS, 0, c.stream>>>(pa, pb, n, partial);
+    CUDA_CHECK_LAUNCH();
+    fr_dot_final_kernel<<<1, DOT_THREADS, 0, c.stream>>>(partial, blocks, partial + blocks);
+    CUDA_CHECK_LAUNCH();
+    c.launches += 2;
+    CUDA_CHECK(cudaMemcpyAsync(out, partial + blocks, 32, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
   });
 }
 

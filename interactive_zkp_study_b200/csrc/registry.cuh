@@ -19,6 +19,16 @@ struct Resource {
   // sparse matrices (CSR): n rows; buf = values (Montgomery), aux[0] = row_ptr, aux[1] = column indices
   uint64_t cols = 0, nnz = 0;
   DevBuf aux[2];
+  Resource() = default;
+  Resource(const Resource&) = delete;
+  Resource& operator=(const Resource&) = delete;
+  // a half-built resource dropped by an exception, or a handle erased from the registry, gives its
+  // buffers back to the pool (recycle() is a no-op on an empty buffer)
+  ~Resource() {
+    buf.recycle();
+    aux[0].recycle();
+    aux[1].recycle();
+  }
 };
 
 struct Registry {

@@ -153,6 +153,11 @@ def set_window_bits(c):
     check(_lib.lib().zkp_msm_set_window_bits(int(c)))
 
 
+def msm_set_option(name, value):
+    """Engine tunables for measurements ("sort", "split", "window_bits"; 0 = automatic)."""
+    check(_lib.lib().zkp_msm_set_option(name.encode(), int(value)))
+
+
 # ------------------------------------------------------------------ handles
 class DeviceHandle:
     """Owns a device-resident table or scalar vector; freed on garbage collection."""
@@ -347,13 +352,64 @@ def g1_msm_dev_batch(table, items):
 
 def g1_msm_dev_partial(table, offset, scalars, sc_offset, n, out_addr=None):
     """XYZZ partial sum (128 B, Montgomery) of one rank's point range.  With `out_addr` (a host or
-    device address, e.g. a torch tensor's data_ptr()) the partial is written there and None returned."""
+    device address on this GPU) the partial is written there and None returned."""
     if out_addr is not None:
         check(_lib.lib().zkp_g1_msm_dev_partial(table.handle, offset, scalars.handle, sc_offset, n, buf(int(out_addr))))
         return None
     out = bytearray(128)
     check(_lib.lib().zkp_g1_msm_dev_partial(table.handle, offset, scalars.handle, sc_offset, n, buf(out)))
     return bytes(out)
+
+
+# ------------------------------------------------------------------ multi-GPU (one process per GPU)
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """Rank 0: the 128-byte NCCL id every rank passes to comm_init."""
+    out = bytearray(COMM_ID_BYTES)
+    check(_lib.lib().zkp_comm_unique_id(buf(out)))
+    return bytes(out)
+
+
+def comm_init(rank, world, comm_id):
+    if len(comm_id) != COMM_ID_BYTES:
+        raise ValueError("a communicator id is %d bytes" % COMM_ID_BYTES)
+    check(_lib.lib().zkp_comm_init(int(rank), int(world), buf(bytes(comm_id))))
+
+
+def comm_info():
+    r, w, v = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(_lib.lib().zkp_comm_info(ctypes.byref(r), ctypes.byref(w), ctypes.byref(v)))
+    return {"rank": r.value, "world": w.value, "nccl_version": v.value}
+
+
+def comm_barrier():
+    check(_lib.lib().zkp_comm_barrier())
+
+
+def comm_destroy():
+    check(_lib.lib().zkp_comm_destroy())
+
+
+def g1_msm_multi(table, offset, scalars, sc_offset, n):
+    """Collective: this rank's shard of a sharded G1 MSM; every rank gets the affine result."""
+    out, inf = _msm_out(1)
+    check(_lib.lib().zkp_g1_msm_multi(table.handle, offset, scalars.handle, sc_offset, n, buf(out), ctypes.byref(inf)))
+    return g1_from_bytes(bytes(out), bool(inf.value))
+
+
+def g1_msm_multi_table(table, offset, sc_bytes, n):
+    """The same with this rank's scalars in host memory (bytes or a pinned address)."""
+    out, inf = _msm_out(1)
+    check(_lib.lib().zkp_g1_msm_multi_table(table.handle, offset, buf(sc_bytes), n, buf(out), ctypes.byref(inf)))
+    return g1_from_bytes(bytes(out), bool(inf.value))
+
+
+def g2_msm_multi(table, offset, scalars, sc_offset, n):
+    out, inf = _msm_out(2)
+    check(_lib.lib().zkp_g2_msm_multi(table.handle, offset, scalars.handle, sc_offset, n, buf(out), ctypes.byref(inf)))
+    return g2_from_bytes(bytes(out), bool(inf.value))
 
 
 def g1_combine_partials(partials_bytes, count):
@@ -490,6 +546,13 @@ def batch_inverse_dev(h, off, n, montgomery=False):
 
 def scan_dev(op, dst, dst_off, src, src_off, n):
     check(_lib.lib().zkp_fr_scan_dev(op, dst.handle, dst_off, src.handle, src_off, n))
+
+
+def fr_dot_dev(a, a_off, b, b_off, n):
+    """sum_i a[a_off + i] * b[b_off + i] mod r of two device-resident canonical vectors."""
+    out = bytearray(32)
+    check(_lib.lib().zkp_fr_dot_dev(a.handle, a_off, b.handle, b_off, n, buf(out)))
+    return int.from_bytes(out, "little")
 
 
 def div_linear_dev(src, src_off, n, zeta, dst, dst_off):

@@ -2,21 +2,26 @@
 
 sum_i k_i P_i is a sum of independent per-range partial sums, so every rank runs the full single-GPU
 Pippenger on its own range of the static table (resident on its GPU) and emits ONE un-normalised XYZZ
-point.  The only exchange step of the path is an all-gather of world x 128 bytes; rank 0 folds the
-partials and converts to affine.  There is no other collective: the NTT / quotient / PLONK rounds are
-single-GPU work ("replicas only").
+point.  The only exchange step of the path is an all-gather of world x 128 bytes, and it lives INSIDE
+the library: ``zkp_g1_msm_multi`` enqueues local MSM -> ``ncclAllGather`` -> fold -> affine on the
+library's stream with no host synchronisation in between (csrc/comm.cu, csrc/msm_api.cuh).  There is no
+other collective: the NTT / quotient / PLONK rounds are single-GPU work ("replicas only").
 
-Process-group plumbing is torch.distributed (NCCL over NVLink on the GPU box, gloo in the CPU tests).
-Under NCCL the partial is written by the library directly into the CUDA send buffer of the gather and
-folded directly out of its receive buffer (no host staging); under gloo the same buffers live in host
-memory.  The reference has no multi-device path; the call it scales is kzg.commit
+This module is the host side of that: the shard arithmetic and the bootstrap of the library's NCCL
+communicator.  The 128-byte communicator id travels from rank 0 to the other ranks over a plain TCP
+rendezvous (standard library sockets) -- or over any channel the caller already has (``exchange_id``).
+The reference has no multi-device path; the call being scaled is kzg.commit
 (/root/reference/zkp/plonk/kzg.py:32-67) / the proof-element sums of proving.py:23-75.
 
 Partial wire format (G1): x | y | zz | zzz, each 32 bytes little-endian, Montgomery form (x * 2^256 mod p);
 the point is (x/zz, y/zzz); zz == 0 encodes the point at infinity.
 """
+import os
+import socket
+import time
 
 PARTIAL_BYTES = 128
+ID_BYTES = 128
 
 
 def shard_range(total, rank, world):
@@ -29,59 +34,99 @@ def shard_range(total, rank, world):
     return start, base + (1 if rank < extra else 0)
 
 
-class PartialExchange:
-    """The gather of one 128-byte partial per rank.  Buffers are allocated once and reused by every
-    MSM (a CUDA tensor pair under NCCL, host tensors under gloo)."""
-
-    def __init__(self, group=None):
-        import torch
-        import torch.distributed as dist
-        if not dist.is_initialized():
-            raise RuntimeError("PartialExchange needs an initialised torch.distributed process group")
-        self._torch, self._dist, self.group = torch, dist, group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
-        self.on_device = "nccl" in str(dist.get_backend(group)).lower()
-        device = torch.device("cuda", torch.cuda.current_device()) if self.on_device else torch.device("cpu")
-        self.send = torch.zeros(PARTIAL_BYTES, dtype=torch.uint8, device=device)
-        self.recv = torch.zeros(PARTIAL_BYTES * self.world, dtype=torch.uint8, device=device)
-
-    @property
-    def send_addr(self):
-        """Where this rank's partial goes (device address under NCCL, host address under gloo)."""
-        return self.send.data_ptr()
-
-    @property
-    def recv_addr(self):
-        return self.recv.data_ptr()
-
-    def write_partial(self, partial):
-        """Host-side fill of the send buffer (tests and callers that hold the partial as bytes)."""
-        if len(partial) != PARTIAL_BYTES:
-            raise ValueError("a G1 partial is %d bytes" % PARTIAL_BYTES)
-        t = self._torch.frombuffer(bytearray(partial), dtype=self._torch.uint8)
-        self.send.copy_(t)
-
-    def all_gather(self):
-        """The exchange step.  On return every rank's receive buffer holds the world partials in rank
-        order and (NCCL) the collective has completed on the device, so another stream may read it."""
-        self._dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
-        if self.on_device:
-            # device-wide: the receive buffer is read next by the library's own stream, which knows nothing
-            # about torch's streams
-            self._torch.cuda.synchronize()
-
-    def gathered_bytes(self):
-        return bytes(self.recv.cpu().numpy().tobytes())
+def _recv_exact(conn, n):
+    out = bytearray()
+    while len(out) < n:
+        chunk = conn.recv(n - len(out))
+        if not chunk:
+            raise ConnectionError("rendezvous peer closed the connection")
+        out += chunk
+    return bytes(out)
 
 
-def g1_msm_sharded(exchange, table, scalars, n_local, offset=0, sc_offset=0):
+def tcp_broadcast(payload, rank, world, addr="127.0.0.1", port=29617, timeout=120.0):
+    """Rank 0 hands `payload` (bytes) to the world - 1 other ranks; every rank returns it.
+
+    Rank 0 listens on (addr, port) until each peer has connected, announced its rank and been served;
+    peers retry the connection until rank 0 is up.  One-shot, no daemon, standard library only."""
+    if world == 1:
+        return bytes(payload)
+    deadline = time.monotonic() + timeout
+    if rank == 0:
+        payload = bytes(payload)
+        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        srv.bind((addr, port))
+        srv.listen(world)
+        srv.settimeout(timeout)
+        served = set()
+        try:
+            while len(served) < world - 1:
+                conn, _ = srv.accept()
+                with conn:
+                    conn.settimeout(timeout)
+                    peer = int.from_bytes(_recv_exact(conn, 4), "little")
+                    if not 1 <= peer < world:
+                        raise ValueError("rendezvous: unexpected peer rank %d" % peer)
+                    conn.sendall(len(payload).to_bytes(4, "little") + payload)
+                    served.add(peer)
+        finally:
+            srv.close()
+        return payload
+    while True:
+        try:
+            with socket.create_connection((addr, port), timeout=5.0) as conn:
+                conn.settimeout(timeout)
+                conn.sendall(int(rank).to_bytes(4, "little"))
+                size = int.from_bytes(_recv_exact(conn, 4), "little")
+                return _recv_exact(conn, size)
+        except (ConnectionRefusedError, ConnectionResetError, socket.timeout, OSError):
+            if time.monotonic() > deadline:
+                raise TimeoutError("rendezvous: rank 0 did not answer on %s:%d" % (addr, port))
+            time.sleep(0.05)
+
+
+class Communicator:
+    """The library's NCCL communicator for this process (one per process, as one GPU per process)."""
+
+    def __init__(self, rank, world, exchange_id=None, addr=None, port=None):
+        """Collective over all ranks.  `exchange_id(id_or_None) -> id` may replace the TCP rendezvous
+        (rank 0 passes the id, the others None; all get the id back)."""
+        from . import native
+        if world <= 0 or not 0 <= rank < world:
+            raise ValueError("Communicator: need 0 <= rank < world")
+        self.rank, self.world = rank, world
+        mine = native.comm_unique_id() if rank == 0 else None
+        if exchange_id is not None:
+            comm_id = exchange_id(mine)
+        else:
+            addr = addr or os.environ.get("MASTER_ADDR", "127.0.0.1")
+            port = int(port or os.environ.get("ZKP_B200_RDZV_PORT", 0) or int(os.environ.get("MASTER_PORT", "29500")) + 117)
+            comm_id = tcp_broadcast(mine, rank, world, addr, port)
+        native.comm_init(rank, world, comm_id)
+        self.info = native.comm_info()
+
+    @classmethod
+    def from_env(cls, **kw):
+        """RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT from the environment, as one-process-per-GPU launchers set them."""
+        return cls(int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), **kw)
+
+    def barrier(self):
+        from . import native
+        native.comm_barrier()
+
+    def close(self):
+        from . import native
+        native.comm_destroy()
+
+
+def g1_msm_sharded(comm, table, scalars, n_local, offset=0, sc_offset=0):
     """This rank's share of a sharded G1 MSM: `table` / `scalars` are device handles of the LOCAL point
-    and scalar ranges (shard_range of the global ones).  Returns the affine result on rank 0 and None on
-    the other ranks."""
+    and scalar ranges (shard_range of the global ones).  Collective; every rank returns the affine
+    result.  `scalars` may also be host bytes / a pinned address (uploaded inside the call)."""
     from . import native
-    native.g1_msm_dev_partial(table, offset, scalars, sc_offset, n_local, out_addr=exchange.send_addr)
-    exchange.all_gather()
-    if exchange.rank != 0:
-        return None
-    return native.g1_combine_partials(exchange.recv_addr, exchange.world)
+    if comm is None:
+        raise ValueError("g1_msm_sharded needs a Communicator")
+    if isinstance(scalars, native.DeviceHandle):
+        return native.g1_msm_multi(table, offset, scalars, sc_offset, n_local)
+    return native.g1_msm_multi_table(table, offset, scalars, n_local)

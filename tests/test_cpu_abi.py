@@ -9,8 +9,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    src = open(os.path.join(ROOT, "include", "zkp_b200.h")).read()
+def _declared(header="zkp_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(zkp_[a-z0-9_]+)\s*\(", src)))
 
@@ -18,11 +18,13 @@ def _declared():
 def test_library_exports_every_declared_symbol():
     from interactive_zkp_study_b200 import _lib
     lib = _lib.load_library()
-    names = _declared()
-    assert len(names) >= 40
-    for name in names:
+    product, diag = _declared(), _declared("zkp_b200_diag.h")
+    assert len(product) >= 40
+    for name in product + diag:
         assert hasattr(lib, name), name
-    assert sorted(_lib.PROTOTYPES) == names  # the ctypes table and the header agree
+    assert sorted(_lib.PROTOTYPES) == sorted(product + diag)  # the ctypes table and the two headers agree
+    # experiments and self-test hooks stay out of the product header
+    assert not [n for n in product if n.startswith("zkp_dbg_") or n in ("zkp_latency_probe", "zkp_imad_peak")]
 
 
 def test_header_cites_the_reference_interface():

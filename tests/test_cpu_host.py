@@ -108,22 +108,27 @@ def _decode_partial(b):
 
 
 def _gloo_worker(rank, world, port, q):
+    import torch
     import torch.distributed as dist
     from oracle import bn254, synthetic
     from interactive_zkp_study_b200 import sharded
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the product's bootstrap channel: rank 0's 128-byte communicator id reaches every rank
+    ident = bytes(range(128)) if rank == 0 else None
+    got_id = sharded.tcp_broadcast(ident, rank, world, "127.0.0.1", port + 1)
     total = 49                               # odd on purpose: ranks own 25 and 24 points
     start, count = sharded.shard_range(total, rank, world)
     s = synthetic.scalars(0x5EED0002, total)[start:start + count]
     k = synthetic.scalars(0x5EED0001, total)[start:start + count]
     pts = [bn254.g1_mul(bn254.G1, x) for x in s]
     part = bn254.g1_msm(pts, k)             # the per-rank partial sum (CPU stand-in for the GPU shard)
-    ex = sharded.PartialExchange()          # the product's exchange step, on the gloo backend
-    assert (ex.rank, ex.world, ex.on_device) == (rank, world, False)
-    ex.write_partial(_encode_partial(part, scale=7 + rank))
-    ex.all_gather()
-    blob = ex.gathered_bytes()
+    # the exchange step of the sharded MSM (ncclAllGather inside the library on a GPU box), here over gloo
+    # with oracle-made partials in the library's 128-byte wire format
+    send = torch.frombuffer(bytearray(_encode_partial(part, scale=7 + rank)), dtype=torch.uint8)
+    recv = torch.zeros(sharded.PARTIAL_BYTES * world, dtype=torch.uint8)
+    dist.all_gather_into_tensor(recv, send)
+    blob = bytes(recv.numpy().tobytes())
     if rank == 0:
         acc = None
         for r in range(world):
@@ -131,9 +136,20 @@ def _gloo_worker(rank, world, port, q):
         s_all = synthetic.scalars(0x5EED0002, total)
         k_all = synthetic.scalars(0x5EED0001, total)
         want = bn254.g1_mul(bn254.G1, sum(a * b for a, b in zip(s_all, k_all)) % bn254.R)
-        q.put(acc == want)
+        q.put(acc == want and got_id == bytes(range(128)))
+    else:
+        assert got_id == bytes(range(128))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def test_tcp_rendezvous_world1_and_bad_arguments():
+    from interactive_zkp_study_b200 import sharded
+    assert sharded.tcp_broadcast(b"abc", 0, 1) == b"abc"          # a single rank needs no socket
+    with pytest.raises(ValueError):
+        sharded.Communicator(2, 2)
+    with pytest.raises(ValueError):
+        sharded.g1_msm_sharded(None, None, None, 0)
 
 
 def test_shard_range_tiles_the_index_space():
@@ -151,9 +167,9 @@ def test_shard_range_tiles_the_index_space():
 
 
 def test_sharded_msm_partition_and_combine_world2_gloo():
-    """N>1 path on CPU (gloo, world_size 2): the product's shard_range + PartialExchange (the one
-    exchange step of the sharded MSM) with oracle-made partials in the 128-byte wire format; the fold
-    on rank 0 == the unsharded MSM."""
+    """N>1 path on CPU (gloo, world_size 2): the product's shard_range and communicator-id rendezvous,
+    and the one exchange step of the sharded MSM (an all-gather of 128-byte partials; inside the library
+    it is ncclAllGather) with oracle-made partials in the wire format; the fold == the unsharded MSM."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
