@@ -483,8 +483,8 @@ def run_ours(args):
         sampler.start()
     peak = {}
     if rank == 0:
-        peak = {"imad_wide_u32": nat.imad_peak(0), "imad_wide_u32_dependent_multiplicand": nat.imad_peak(4),
-                "imad_lo": nat.imad_peak(1), "imad_hi_u32": nat.imad_peak(2), "fp_mul_chain": nat.imad_peak(3)}
+        peak = {"imad_wide_u32": nat.imad_peak(0), "imad_lo": nat.imad_peak(1), "imad_hi_u32": nat.imad_peak(2),
+                "fp_mul_chain": nat.imad_peak(3), "mad_wide_u32_register_factors": nat.imad_peak(4)}
 
     # ---- resident-input timing (value)
     for i in range(warmup):
@@ -508,18 +508,6 @@ def run_ours(args):
     total_points = n * world
     value = total_points * steps / (ms * 1e-3) / 1e6
 
-    # the accumulation kernel alone (no bucket-range parts: nothing overlaps it), same table and vectors
-    iso_acc_us = iso_msm_us = None
-    if rank == 0 and world == 1:
-        nat.msm_set_option("split", 1)
-        nat.g1_msm_dev(table, 0, k_h[0], 0, n)
-        iso_acc_us = iso_msm_us = 0.0
-        reps = 5
-        for i in range(reps):
-            nat.g1_msm_dev(table, 0, k_h[(i + 1) % n_vec], 0, n)
-            iso_acc_us += nat.msm_last_profile("accumulate") / reps
-            iso_msm_us += nat.msm_last_profile(None) / reps
-        nat.msm_set_option("split", 0)
     nat.msm_profile(False)
 
     # for the record: the same MSMs submitted as ONE pipelined batch call (two streams: the tail of MSM k
@@ -631,14 +619,10 @@ def run_ours(args):
         "algorithmic_note": "%d windows x (8 products x 136 + 2 squarings x 108 = 1304 limb-MAC per XYZZ mixed addition) per point; "
                             "with squarings counted as products (SURVEY 8d) the figure is x %.4f" % (W_actual, 1360.0 / MADD_MACS),
         "kernel_ms": acc_s * 1e3, "kernel_share_of_step": acc_us / max(msm_us, 1e-9),
-        "kernel_timing": "CUDA events on the library stream around the accumulate launches of every timed step "
-                         "(the bucket-range parts run back to back; earlier parts' reductions overlap them on side streams)",
-        "isolated": None if iso_acc_us is None else {
-            "kernel_ms": iso_acc_us * 1e-3, "achieved": acc_macs / (iso_acc_us * 1e-6) / 1e12,
-            "frac": acc_macs / (iso_acc_us * 1e-6) / 1e12 / peak_t, "msm_ms": iso_msm_us * 1e-3,
-            "note": "same MSM with one bucket-range part (nothing overlaps the kernel)"},
-        "peak_source": "measured live on this GPU by zkp_imad_peak(0): IMAD.WIDE.U32, 12 independent accumulators per thread, "
-                       "shared multiplicand, immediate multiplier; MEASURED_PEAKS.json has no integer peak",
+        "kernel_timing": "CUDA events on the library stream around the accumulate launch of every timed step",
+        "peak_source": "measured live on this GPU by zkp_imad_peak(0): IMAD.WIDE.U32[.X] in the carry-chain form the field "
+                       "arithmetic issues (mad.lo.cc / madc.hi.cc pairs), 4 independent 4-lane chains per thread, 1024 threads per SM, "
+                       "no loop-invariant operand (checked in SASS); MEASURED_PEAKS.json has no integer peak",
         "peaks_gmacs": peak,
         "whole_msm": {"macs_per_point_model": msm_macs_per_point(n),
                       "frac": (n * msm_macs_per_point(n) / (msm_us / steps * 1e-6) / 1e12) / peak_t,

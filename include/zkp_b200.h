@@ -102,10 +102,7 @@ int zkp_g1_msm_dev_partial(uint64_t table, uint64_t offset, uint64_t scalars, ui
 int zkp_g1_combine_partials(const uint8_t* partials, uint32_t count, uint8_t out_xy[64], int* out_is_inf);
 /* Window-width override for experiments (0 = automatic). */
 int zkp_msm_set_window_bits(int c);
-/* Engine tunables for measurements (0 = automatic): "sort" 1 = counting sort with global atomics, 2 = radix
- * partition through shared memory; "split" 1..4 = bucket-range parts of an MSM on a precomputed table
- * (the reduction of one part overlaps the accumulation of the next); "window_bits" as above.  Results are
- * identical under every setting. */
+/* Engine tunables for measurements by name (0 = automatic); today: "window_bits" as above. */
 int zkp_msm_set_option(const char* name, int value);
 
 /* ---- multi-GPU: points sharded by contiguous range, one process per GPU -----------------

@@ -14,10 +14,12 @@
 extern "C" {
 #endif
 
-/* Integer-MAD microbenchmarks, G(limb-MAC)/s over the whole chip.  variant 0 = IMAD.WIDE.U32 peak (the
- * roofline unit: 12 independent accumulators per thread, shared multiplicand, immediate multiplier);
- * 1 = IMAD (32-bit lo); 2 = IMAD.HI; 3 = chains of whole Fp Montgomery products (136 limb-MACs each);
- * 4 = IMAD.WIDE.U32 with a dependent multiplicand and four register operands (reads below variant 0). */
+/* Integer-MAD microbenchmarks, G(limb-MAC)/s over the whole chip.  variant 0 = IMAD.WIDE.U32 peak in the
+ * carry-chain form the field arithmetic issues (mad.lo.cc / madc.hi.cc pairs -> IMAD.WIDE.U32[.X]), four
+ * independent 4-lane chains per thread: the roofline denominator; 1 = IMAD (32-bit lo); 2 = IMAD.HI;
+ * 3 = chains of whole Fp Montgomery products (136 limb-MACs each); 4 = plain mad.wide.u32 with register
+ * factors (ptxas adds separate 64-bit additions: reads below variant 0); 5 = variant 4 interleaved with
+ * 64-bit shift-and-add steps on the integer ALU. */
 int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effective);
 /* Single-thread latency of one operation (ns): mode 0/1/2 = 1/2/4 independent Fp products per step,
  * 3 = XYZZ add (inlined products), 4 = XYZZ add (out-of-line products), 5 = mixed add, 6 = double;

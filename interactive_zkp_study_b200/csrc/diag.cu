@@ -22,7 +22,6 @@ static void diag_events() {
 // Independent accumulator chains per thread, 256 threads x 4-8 blocks per SM: the issue rate of the
 // integer-multiply pipe is the only limit (asm volatile keeps every instruction; see the variants below).
 static constexpr int PEAK_UNROLL = 16;
-static constexpr int PEAK_CHAINS_WIDE = 12;  // independent accumulators per thread in the IMAD.WIDE peak loop
 
 // One thread, dependent chains: the latency a lone thread pays per operation (what bounds the MSM's
 // reduction tail).  mode 0/1/2: 1/2/4 independent Fp product chains per iteration (time per iteration);
@@ -89,15 +88,17 @@ __global__ void latency_probe_kernel(int mode, int iters, uint32_t* out) {
   }
   out[0] = s;
 }
-// VARIANT 0: IMAD.WIDE.U32 peak.  CHAINS independent 64-bit accumulators per thread, every instruction
-//            acc_k += x * IMMEDIATE with one shared multiplicand register: two register-file reads per
-//            instruction (x is served by the operand-reuse cache), the operand mix of a CIOS row, whose
-//            multiplier limb is shared along the row and whose modulus limbs are immediates.  Nothing but
-//            the issue rate of the pipe IMAD.WIDE runs on limits it.
-//         1: mad.lo.u32 (IMAD), 2: mad.hi.u32 (IMAD.HI): one dependent chain per accumulator
-//         3: Fp Montgomery multiplication chains (136 limb-MACs each): the practical ceiling
-//         4: IMAD.WIDE.U32 whose multiplicand is the low half of its own accumulator (round 1's form:
-//            four register reads per instruction and a dependent multiplicand; reads BELOW variant 0)
+// Variants of zkp_imad_peak (G limb-MAC/s over the chip; every kernel checked in SASS for the instruction named):
+//   0: IMAD.WIDE.U32 peak in the form the field arithmetic issues it -- mad.lo.cc / madc.hi.cc pairs, four
+//      64-bit lanes deep (ptxas: 1 IMAD.WIDE.U32 + 3 IMAD.WIDE.U32.X + 1 IADD3.X per 4 limb-MACs), 4
+//      independent chains per thread per step, multiplicands taken from another chain's limbs so nothing is
+//      loop invariant (a loop-invariant product is strength-reduced to additions by ptxas).  This is the
+//      roofline denominator: 9.14 T limb-MAC/s measured = 31.4 lanes/clk/SM, the rate of IMAD.HI.
+//   1: mad.lo.u32 (IMAD), 2: mad.hi.u32 (IMAD.HI): 8 dependent chains per thread
+//   3: chains of whole Fp Montgomery products (136 limb-MACs each): the practical ceiling of a product loop
+//   4: plain mad.wide.u32 with both factors in registers, 12 accumulators (ptxas splits the 64-bit accumulate
+//      into IMAD.WIDE.U32 ..., RZ + IADD3 / IADD3.X: reads BELOW variant 0, it is bound by the extra additions)
+//   5: variant 4 interleaved one-to-one with 64-bit shift-and-add steps on the integer ALU
 template <int VARIANT>
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters, uint32_t m0) {
   uint32_t seed = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
@@ -121,35 +122,85 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     return;
   }
-  constexpr int CHAINS = VARIANT == 0 ? PEAK_CHAINS_WIDE : 8;
-  unsigned long long acc[CHAINS];
+  if (VARIANT == 0) {
+    uint32_t a[4][8];
 #pragma unroll
-  for (int k = 0; k < CHAINS; k++) acc[k] = ((unsigned long long)(seed + k) << 32) | (seed * (k + 3));
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) a[k][j] = seed + 17 * k + j;
+    uint32_t cs = 0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < PEAK_UNROLL; u++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          uint32_t c;
+          asm volatile("mad.lo.cc.u32   %0, %9,  %13, %0;\n\t"
+                       "madc.hi.cc.u32  %1, %9,  %13, %1;\n\t"
+                       "madc.lo.cc.u32  %2, %10, %13, %2;\n\t"
+                       "madc.hi.cc.u32  %3, %10, %13, %3;\n\t"
+                       "madc.lo.cc.u32  %4, %11, %13, %4;\n\t"
+                       "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
+                       "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
+                       "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
+                       "addc.u32        %8, 0, 0;"
+                       : "+r"(a[k][0]), "+r"(a[k][1]), "+r"(a[k][2]), "+r"(a[k][3]), "+r"(a[k][4]), "+r"(a[k][5]),
+                         "+r"(a[k][6]), "+r"(a[k][7]), "=r"(c)
+                       : "r"(a[(k + 1) & 3][0]), "r"(a[(k + 1) & 3][2]), "r"(a[(k + 1) & 3][4]), "r"(a[(k + 1) & 3][6]), "r"(b));
+          cs += c;
+        }
+      }
+    }
+    uint32_t s = cs;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) s ^= a[k][j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    return;
+  }
+  if (VARIANT == 1 || VARIANT == 2) {
+    uint32_t acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = seed * (k + 3);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < PEAK_UNROLL; u++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          if (VARIANT == 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(acc[k]) : "r"(b), "r"(seed));
+          else asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(acc[k]) : "r"(b), "r"(seed));
+        }
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= acc[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    return;
+  }
+  // 4 / 5
   const uint32_t x = seed | 1u;
+  unsigned long long acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) acc[k] = ((unsigned long long)(seed + k) << 32) | (seed * (k + 3));
+  unsigned long long carry[4] = {seed, seed + 1, seed + 2, seed + 3};
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int u = 0; u < PEAK_UNROLL; u++) {
 #pragma unroll
-      for (int k = 0; k < CHAINS; k++) {
-        if (VARIANT == 0) {
-          asm volatile("mad.wide.u32 %0, %1, 0x9e3779b1, %0;" : "+l"(acc[k]) : "r"(x));
-        } else if (VARIANT == 4) {
-          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"((uint32_t)acc[k]), "r"(b));
-        } else if (VARIANT == 1) {
-          uint32_t v = (uint32_t)acc[k];
-          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v) : "r"(b), "r"(seed));
-          acc[k] = v;
-        } else {
-          uint32_t v = (uint32_t)acc[k];
-          asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(v) : "r"(b), "r"(seed));
-          acc[k] = v;
-        }
+      for (int k = 0; k < 12; k++) {
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"((uint32_t)acc[(k + 7) % 12] ^ x), "r"(b));
+        if (VARIANT == 5)
+          asm volatile("{\n\t.reg .u64 t;\n\tshr.u64 t, %0, 29;\n\tadd.u64 %0, t, %1;\n\t}" : "+l"(carry[k & 3]) : "l"(acc[(k + 3) % 12]));
       }
     }
   }
   uint32_t s = 0;
 #pragma unroll
-  for (int k = 0; k < CHAINS; k++) s ^= (uint32_t)acc[k] ^ (uint32_t)(acc[k] >> 32);
+  for (int k = 0; k < 12; k++) s ^= (uint32_t)acc[k] ^ (uint32_t)(acc[k] >> 32);
+#pragma unroll
+  for (int k = 0; k < 4; k++) s ^= (uint32_t)carry[k] ^ (uint32_t)(carry[k] >> 32);
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
@@ -239,8 +290,8 @@ int zkp_latency_probe(int mode, double* ns_per_op) {
 int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effective) {
   return guarded([&](Context& c) {
     diag_events();
-    if (variant < 0 || variant > 4 || !gmacs_per_s) throw InvalidArgument("zkp_imad_peak: bad variant");
-    const int blocks = c.sm_count * (variant == 0 ? 4 : 8), threads = 256;
+    if (variant < 0 || variant > 5 || !gmacs_per_s) throw InvalidArgument("zkp_imad_peak: bad variant");
+    const int blocks = c.sm_count * ((variant == 1 || variant == 2) ? 8 : 4), threads = 256;
     const int iters = variant == 3 ? 2000 : 4000;
     ScopedDevBuf out;
     out.reserve((size_t)blocks * threads * 4);
@@ -250,7 +301,8 @@ int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effecti
         case 1: imad_peak_kernel<1><<<blocks, threads, 0, c.stream>>>(out.as<uint32_t>(), it, 0x12345677u); break;
         case 2: imad_peak_kernel<2><<<blocks, threads, 0, c.stream>>>(out.as<uint32_t>(), it, 0x12345677u); break;
         case 3: imad_peak_kernel<3><<<blocks, threads, 0, c.stream>>>(out.as<uint32_t>(), it, 0x12345677u); break;
-        default: imad_peak_kernel<4><<<blocks, threads, 0, c.stream>>>(out.as<uint32_t>(), it, 0x12345677u); break;
+        case 4: imad_peak_kernel<4><<<blocks, threads, 0, c.stream>>>(out.as<uint32_t>(), it, 0x12345677u); break;
+        default: imad_peak_kernel<5><<<blocks, threads, 0, c.stream>>>(out.as<uint32_t>(), it, 0x12345677u); break;
       }
       CUDA_CHECK_LAUNCH();
       c.launches++;
@@ -266,9 +318,8 @@ int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effecti
       CUDA_CHECK(cudaEventElapsedTime(&ms, d_ev0, d_ev1));
       if (ms < best) best = ms;
     }
-    double per_thread = variant == 3 ? (double)iters * 2 * 136
-                                     : (double)iters * PEAK_UNROLL * (variant == 0 ? PEAK_CHAINS_WIDE : 8);
-    double macs = per_thread * blocks * threads;
+    double per_iter = variant == 3 ? 2.0 * 136 : variant == 0 ? PEAK_UNROLL * 16.0 : variant >= 4 ? PEAK_UNROLL * 12.0 : PEAK_UNROLL * 8.0;
+    double macs = per_iter * iters * blocks * threads;
     *gmacs_per_s = macs / (best * 1e-3) / 1e9;
     if (sm_clock_mhz_effective) *sm_clock_mhz_effective = 0.0;  // clocks are sampled by bench.py via nvidia-smi
   });

@@ -179,22 +179,7 @@ static __global__ void msm_scatter_kernel(const uint32_t* __restrict__ codes, ui
   sorted[pos] = i | ((code & 1u) << 31);
 }
 
-// ---------------------------------------------------------------- stage 2 (large inputs): radix partition
-// The counting sort above pays one global atomic per digit in each of its two passes (13.6 M + 13.6 M
-// at 2^20 points, c = 20: 80 + 168 us, atomic bound).  For large inputs the (bucket, entry) pairs are
-// instead partitioned on the HIGH bits of the bucket with block-local shared-memory histograms, then
-// every bin -- 2^low_bits consecutive buckets, low_bits = 10 or 8 -- is sorted by one block entirely in shared memory:
-//   P1a  count   : a block walks its contiguous range of scalars, recodes them and histograms the bins
-//                  of its digits in shared memory; per-block counts go out as blk_hist[bin][block];
-//   scan         : exclusive scan of blk_hist (bin-major) = where block b's share of bin k starts;
-//   P1b  scatter : the same blocks recode again (cheaper than storing and re-reading the digits) and
-//                  write {low bucket bits | sign, entry} pairs to their reserved slots;
-//   P2   sort    : one block per bin: histogram of the low bits, scan (this IS the bucket offsets
-//                  array of the bin), scatter of the entries to their final places.
-// No global atomics; every global access is a coalesced stream except the pair writes of P1b (runs of
-// a few hundred bytes) and the final scatter (inside one bin's 100 KB, L2-resident).
-static constexpr int MSM_PART_THREADS = 256;   // P1 block size; P2 runs 2^low_bits threads (one scan item each)
-
+// ---------------------------------------------------------------- digit recoding helpers
 // Canonical scalar i reduced mod r into s[0..8] (s[8] = 0): the group has order r, so
 // k*P == (k mod r)*P (field.py:88).  2^256 / r < 6.
 __device__ __forceinline__ void msm_load_scalar(const uint32_t* __restrict__ scalars, uint64_t i, uint32_t (&s)[9]) {
@@ -239,78 +224,6 @@ __device__ __forceinline__ uint32_t msm_digit_code(const uint32_t (&s)[9], int w
   return v ? (((uint32_t)w * wstride + (v - 1)) << 1) : MSM_INVALID;
 }
 
-struct MsmPartArgs {
-  const uint32_t* scalars;
-  uint64_t n;
-  int c, W;
-  uint32_t B, wstride;
-  uint32_t nbins, nblocks, pts_per_block;
-  uint32_t pre_stride, pre_offset;
-  int low_bits;  // bucket bits sorted per bin in shared memory
-};
-
-// SCATTER == false: blk[bin * nblocks + block] = number of this block's digits in the bin.
-// SCATTER == true : blk holds the scanned counts; pairs go to their reserved slots.
-template <bool SCATTER>
-__global__ void __launch_bounds__(MSM_PART_THREADS) msm_part_kernel(MsmPartArgs a, uint32_t* __restrict__ blk,
-                                                                      uint2* __restrict__ pairs) {
-  extern __shared__ uint32_t part_h[];
-  for (uint32_t k = threadIdx.x; k < a.nbins; k += MSM_PART_THREADS)
-    part_h[k] = SCATTER ? blk[(uint64_t)k * a.nblocks + blockIdx.x] : 0u;
-  __syncthreads();
-  const uint64_t i0 = (uint64_t)blockIdx.x * a.pts_per_block;
-  uint64_t i1 = i0 + a.pts_per_block;
-  if (i1 > a.n) i1 = a.n;
-  for (uint64_t i = i0 + threadIdx.x; i < i1; i += MSM_PART_THREADS) {
-    uint32_t s[9];
-    msm_load_scalar(a.scalars, i, s);
-    uint32_t carry = 0;
-    for (int w = 0; w < a.W; w++) {
-      uint32_t code = msm_digit_code(s, w, a.c, a.B, a.wstride, carry);
-      if (code == MSM_INVALID) continue;
-      uint32_t bucket = code >> 1;
-      uint32_t pos = atomicAdd(&part_h[bucket >> a.low_bits], 1u);
-      if (SCATTER) {
-        uint32_t e = (uint32_t)i;
-        if (a.pre_stride) e += (uint32_t)w * a.pre_stride + a.pre_offset;
-        pairs[pos] = make_uint2(((bucket & ((1u << a.low_bits) - 1)) << 1) | (code & 1u), e);
-      }
-    }
-  }
-  if (!SCATTER) {
-    __syncthreads();
-    for (uint32_t k = threadIdx.x; k < a.nbins; k += MSM_PART_THREADS) blk[(uint64_t)k * a.nblocks + blockIdx.x] = part_h[k];
-  }
-}
-
-// One block per bin.  blk_off: scanned per-(bin, block) counts, so bin k owns pairs
-// [blk_off[k * nblocks], blk_off[(k + 1) * nblocks]) (the scan's grand total closes the last bin).
-template <int LOW>
-__global__ void __launch_bounds__(1 << LOW) msm_part_sort_kernel(const uint2* __restrict__ pairs,
-                                                                 const uint32_t* __restrict__ blk_off, uint32_t nblocks,
-                                                                 uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
-  constexpr uint32_t L = 1u << LOW;  // == blockDim.x: one low-bits counter per thread
-  __shared__ uint32_t h[L];
-  __shared__ uint32_t total;
-  const uint32_t bin = blockIdx.x;
-  const uint32_t beg = blk_off[(uint64_t)bin * nblocks], end = blk_off[(uint64_t)(bin + 1) * nblocks];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  for (uint32_t k = beg + threadIdx.x; k < end; k += L) atomicAdd(&h[pairs[k].x >> 1], 1u);
-  __syncthreads();
-  uint32_t cnt = h[threadIdx.x];
-  uint32_t ex = block_exclusive_scan(cnt, &total) + beg;
-  offsets[(uint64_t)bin * L + threadIdx.x] = ex;
-  if (bin == gridDim.x - 1 && threadIdx.x == 0) offsets[(uint64_t)gridDim.x * L] = end;
-  h[threadIdx.x] = ex;
-  __syncthreads();
-  for (uint32_t k = beg + threadIdx.x; k < end; k += L) {
-    uint2 e = pairs[k];
-    uint32_t pos = atomicAdd(&h[e.x >> 1], 1u);
-    sorted[pos] = e.y | ((e.x & 1u) << 31);
-  }
-}
-
 static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, int c, int W, uint32_t B,
                                   uint32_t wstride, uint32_t* __restrict__ codes, uint32_t* __restrict__ hist) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -332,6 +245,7 @@ static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, u
 // structured inputs: a few huge buckets).  One thread per task; buckets with several tasks are
 // folded afterwards.
 static constexpr uint32_t MSM_TASK_LEN = 64;
+static constexpr uint32_t MSM_DIRECT = 0x80000000u;
 #ifndef MSM_ACC_MIN_BLOCKS
 #define MSM_ACC_MIN_BLOCKS 4  // resident 128-thread blocks per SM the G1 accumulate kernel is compiled for
 #endif
@@ -383,7 +297,9 @@ static __global__ void msm_task_bins_kernel(uint32_t* __restrict__ len_hist) {
   }
 }
 
-// task record: x = bucket, y = first entry, z = length, w = slot in the partial-sum array
+// task record: x = bucket, y = first entry, z = length, w = slot in the partial-sum array, or
+// MSM_DIRECT | bucket when the task is the bucket's only one: its sum then IS the bucket and the
+// accumulate kernel stores it there (no copy through the partial array, nothing left for the fold)
 static __global__ void msm_task_emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_base,
                                             uint32_t nbuckets, uint32_t* __restrict__ len_cursor,
                                             uint4* __restrict__ tasks) {
@@ -407,9 +323,11 @@ static __global__ void msm_task_emit_kernel(const uint32_t* __restrict__ offsets
   __syncthreads();
   if (b < nbuckets) {
     uint32_t tb = task_base[b];
+    const bool single = full + (rem ? 1u : 0u) == 1u;
     for (uint32_t k = 0; k < full; k++)
-      tasks[base[0] + r_full + k] = make_uint4(b, beg + k * MSM_TASK_LEN, MSM_TASK_LEN, tb + k);
-    if (rem) tasks[base[MSM_TASK_LEN - rem] + r_rem] = make_uint4(b, beg + full * MSM_TASK_LEN, rem, tb + full);
+      tasks[base[0] + r_full + k] = make_uint4(b, beg + k * MSM_TASK_LEN, MSM_TASK_LEN, single ? (MSM_DIRECT | b) : tb + k);
+    if (rem)
+      tasks[base[MSM_TASK_LEN - rem] + r_rem] = make_uint4(b, beg + full * MSM_TASK_LEN, rem, single ? (MSM_DIRECT | b) : tb + full);
   }
 }
 
@@ -418,7 +336,8 @@ __global__ void __launch_bounds__(128, AccMinBlocks<F>::value) msm_accumulate_ke
                                                               const uint32_t* __restrict__ sorted,
                                                               const uint4* __restrict__ tasks,
                                                               const uint32_t* __restrict__ ntasks_ptr,
-                                                              XYZZ<F>* __restrict__ partials) {
+                                                              XYZZ<F>* __restrict__ partials,
+                                                              XYZZ<F>* __restrict__ buckets) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= *ntasks_ptr) return;  // the task count is data dependent and stays on the device
   uint4 task = tasks[t];
@@ -430,10 +349,12 @@ __global__ void __launch_bounds__(128, AccMinBlocks<F>::value) msm_accumulate_ke
     if (e >> 31) p.y = p.y.neg();
     acc.madd(p);
   }
-  partials[task.w] = acc;
+  if (task.w & MSM_DIRECT) buckets[task.w & ~MSM_DIRECT] = acc;
+  else partials[task.w] = acc;
 }
 
-// buckets[b] = sum of its tasks' partial sums (usually exactly one).  Buckets with more than
+// buckets[b] = sum of its tasks' partial sums; empty buckets become infinity, single-task buckets were
+// already written by the accumulate kernel.  Buckets with more than
 // MSM_FOLD_SERIAL partials (skewed scalars, or a top window that only uses a few buckets) are queued
 // for the block-per-bucket kernel below so that no single thread walks thousands of partials.
 static constexpr uint32_t MSM_FOLD_SERIAL = 24;
@@ -445,6 +366,7 @@ __global__ void __launch_bounds__(128) msm_bucket_fold_kernel(const XYZZ<F>* __r
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbuckets) return;
   uint32_t t0 = task_base[b], t1 = task_base[b + 1];
+  if (t1 - t0 == 1) return;  // a single task: the accumulate kernel wrote the bucket itself
   if (t1 - t0 > serial_limit) {
     heavy_list[atomicAdd(heavy_count, 1u)] = b;
     return;
@@ -684,83 +606,21 @@ __global__ void fe_from_mont_kernel(FE* __restrict__ v, uint64_t n) {
   if (i < n) v[i] = v[i].from_mont();
 }
 
-// Result of an MSM whose single bucket set (window-precomputed table) was reduced in `count` bucket-range
-// parts: part p covers buckets [off_p, off_p + m_p) and its recursion ends with E_p = sum_j (j + 1) B_(off_p + j)
-// and A_p = m_p * sum_j B_(off_p + j), so the whole weighted sum is sum_p (E_p + (off_p / m_p) * A_p).
-struct MsmPartsFinal {
-  const void* A[8];
-  const void* E[8];
-  uint32_t k[8];  // off_p / m_p (parts are power-of-two sized and sorted by decreasing size, so this is an integer)
-  int count;
-};
-template <class F>
-__global__ void msm_final_parts_kernel(MsmPartsFinal f, Affine<F>* __restrict__ out, int* __restrict__ inf_flag,
-                                       XYZZ<F>* __restrict__ out_xyzz) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  XYZZ<F> r = XYZZ<F>::inf();
-  for (int p = 0; p < f.count; p++) {
-    r.add(*reinterpret_cast<const XYZZ<F>*>(f.E[p]));
-    uint32_t k = f.k[p];
-    if (k) {  // k * A_p, k < 2^8: double-and-add from the top bit
-      XYZZ<F> a = *reinterpret_cast<const XYZZ<F>*>(f.A[p]);
-      XYZZ<F> t = XYZZ<F>::inf();
-      for (int b = 31 - __clz(k); b >= 0; b--) {
-        t = t.dbl();
-        if ((k >> b) & 1u) t.add(a);
-      }
-      r.add(t);
-    }
-  }
-  if (out_xyzz) *out_xyzz = r;
-  if (out) {
-    Affine<F> a = r.to_affine();
-    *inf_flag = r.is_inf() ? 1 : 0;
-    a.x = a.x.from_mont();
-    a.y = a.y.from_mont();
-    *out = a;
-  }
-}
-
 // ---------------------------------------------------------------- host driver
-// Tunables (zkp_msm_set_option; 0 = automatic everywhere).
+// Tunables (zkp_msm_set_option; 0 = automatic).
 struct MsmOptions {
   int window_bits = 0;  // plain tables: window width override
-  int sort = 0;         // 1 = counting sort with global atomics, 2 = radix partition
-  int split = 0;        // bucket-range parts of a precomputed-table MSM: 1 = none, 2 / 3 / 4 = that many
 };
 MsmOptions& msm_options();  // defined in msm_g1.cu
-
-static constexpr int MSM_MAX_PARTS = 4;
 
 template <class F>
 struct MsmEngine {
   using FC = typename CompactOf<F>::type;  // same layout, out-of-line products (small code)
-  DevBuf codes, sorted, hist, offsets, cursor, tile_sums, buckets, result, flag, pairs, blk_hist, blk_off;
-  // per bucket-range part: task lists, partial sums, reduction levels
-  struct PartWs {
-    DevBuf ntask, task_base, len_bins, tasks, partials, heavy, lvlA[2], lvlE[2];
-    uint32_t off = 0, m = 0;
-    const void* A_final = nullptr;
-    const void* E_final = nullptr;
-  } part[MSM_MAX_PARTS];
-  cudaStream_t aux[2] = {nullptr, nullptr};
-  cudaEvent_t ev_acc[MSM_MAX_PARTS] = {}, ev_red[MSM_MAX_PARTS] = {};
+  DevBuf codes, sorted, hist, offsets, cursor, tile_sums, buckets, lvlA[2], lvlE[2], result, flag;
+  DevBuf ntask, task_base, len_bins, tasks, partials, heavy;
   int reduce_L = 8;
   uint32_t wide_threshold = 1u << 17;  // items (all windows) above which a level is throughput bound
   uint32_t quad_threshold = 1u << 12;  // radix-2 outputs (all windows) below which a level is latency bound
-
-  void ensure_streams() {
-    if (aux[0]) return;
-    int lo = 0, hi = 0;
-    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    // the reductions that run beside a later part's accumulation are latency bound: their (few, small)
-    // blocks take the SM slots that free up first
-    for (int k = 0; k < 2; k++) CUDA_CHECK(cudaStreamCreateWithPriority(&aux[k], cudaStreamNonBlocking, hi));
-    for (int k = 0; k < MSM_MAX_PARTS; k++) {
-      CUDA_CHECK(cudaEventCreateWithFlags(&ev_acc[k], cudaEventDisableTiming));
-      CUDA_CHECK(cudaEventCreateWithFlags(&ev_red[k], cudaEventDisableTiming));
-    }
-  }
 
   // Builds the window-precomputed table T[w][i] = 2^(c*w) * P_i (w < W, affine Montgomery) from the n
   // plain points in `src`.  `dst` must hold W*n points; dst[0..n) may alias src.
@@ -797,121 +657,78 @@ struct MsmEngine {
     return 3;
   }
 
-  // ---- stages 1 + 2: `sorted` (entry | sign << 31, grouped by bucket) and `offsets` (nbuckets + 1)
+  // ---- stages 1 + 2: `sorted` (entry | sign << 31, grouped by bucket) and `offsets` (nbuckets + 1).
+  // Counting sort with one global atomic per digit in each pass.  A radix partition through shared-memory
+  // histograms (block-local bins, then one block per bin) was built and measured in round 2: 417 us against
+  // 289 us at 2^20 points -- it trades 27 M L2 atomics for 54 M shared-memory ones, which are no faster on
+  // this part -- and was removed.
   int sort_entries(const uint32_t* scalars, uint64_t n, const MsmPlan& pl, uint32_t wstride, uint32_t pre_stride,
                    uint32_t pre_offset, cudaStream_t st, StageTrace& tr) {
     const uint64_t total = (uint64_t)pl.W * n;
-    int launches = 0;
-    sorted.reserve(total * 4);
-    offsets.reserve(((size_t)pl.nbuckets + 1) * 4);
-    int mode = msm_options().sort;
-    // the partition wants whole bins of 2^low consecutive buckets and enough bins to spread over the SMs
-    const int low = pl.nbuckets >= (1u << 18) ? 10 : 8;
-    const bool can_radix = pl.c >= 16 && (pl.nbuckets >> low) <= 4096;
-    if (mode == 0) mode = (can_radix && total >= (1u << 21)) ? 2 : 1;
-    if (mode == 2 && !can_radix) mode = 1;
-    if (mode == 2) {
-      MsmPartArgs a;
-      a.scalars = scalars;
-      a.n = n;
-      a.c = pl.c;
-      a.W = pl.W;
-      a.B = pl.B;
-      a.wstride = wstride;
-      a.low_bits = low;
-      a.nbins = pl.nbuckets >> low;
-      a.pts_per_block = 1024;
-      while (ceil_div(n, a.pts_per_block) > 4096) a.pts_per_block *= 2;
-      a.nblocks = ceil_div(n, a.pts_per_block);
-      a.pre_stride = pre_stride;
-      a.pre_offset = pre_offset;
-      const uint32_t cells = a.nbins * a.nblocks;
-      blk_hist.reserve((size_t)cells * 4);
-      blk_off.reserve(((size_t)cells + 1) * 4);
-      pairs.reserve(total * sizeof(uint2));
-      msm_part_kernel<false><<<a.nblocks, MSM_PART_THREADS, a.nbins * 4, st>>>(a, blk_hist.as<uint32_t>(), nullptr);
-      CUDA_CHECK_LAUNCH();
-      launches += 1 + scan_u32(blk_hist.as<uint32_t>(), cells, blk_off.as<uint32_t>(), st);
-      tr.mark("digits+scan");
-      msm_part_kernel<true><<<a.nblocks, MSM_PART_THREADS, a.nbins * 4, st>>>(a, blk_off.as<uint32_t>(), pairs.as<uint2>());
-      CUDA_CHECK_LAUNCH();
-      if (low == 10)
-        msm_part_sort_kernel<10><<<a.nbins, 1024, 0, st>>>(pairs.as<uint2>(), blk_off.as<uint32_t>(), a.nblocks,
-                                                          offsets.as<uint32_t>(), sorted.as<uint32_t>());
-      else
-        msm_part_sort_kernel<8><<<a.nbins, 256, 0, st>>>(pairs.as<uint2>(), blk_off.as<uint32_t>(), a.nblocks,
-                                                        offsets.as<uint32_t>(), sorted.as<uint32_t>());
-      CUDA_CHECK_LAUNCH();
-      launches += 2;
-      tr.mark("scatter");
-      return launches;
-    }
     codes.reserve(total * 4);
+    sorted.reserve(total * 4);
     hist.reserve((size_t)pl.nbuckets * 4);
+    offsets.reserve(((size_t)pl.nbuckets + 1) * 4);
     cursor.reserve(((size_t)pl.nbuckets + 1) * 4);
     CUDA_CHECK(cudaMemsetAsync(hist.p, 0, (size_t)pl.nbuckets * 4, st));
     msm_digits_kernel<<<ceil_div(n, 256), 256, 0, st>>>(scalars, n, pl.c, pl.W, pl.B, wstride, codes.as<uint32_t>(),
                                                        hist.as<uint32_t>());
     CUDA_CHECK_LAUNCH();
-    launches += 1 + scan_u32(hist.as<uint32_t>(), pl.nbuckets, offsets.as<uint32_t>(), st);
+    int launches = 1 + scan_u32(hist.as<uint32_t>(), pl.nbuckets, offsets.as<uint32_t>(), st);
     tr.mark("digits+scan");
     CUDA_CHECK(cudaMemcpyAsync(cursor.p, offsets.p, ((size_t)pl.nbuckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
     msm_scatter_kernel<<<ceil_div(total, 256), 256, 0, st>>>(codes.as<uint32_t>(), total, n, cursor.as<uint32_t>(),
                                                             sorted.as<uint32_t>(), pre_stride, pre_offset);
     CUDA_CHECK_LAUNCH();
-    launches++;
     tr.mark("scatter");
-    return launches;
+    return launches + 1;
   }
 
-  // ---- stage 3a: tasks of the buckets [pw.off, pw.off + pw.m): count -> scan -> length histogram -> emit
-  // sorted by length.  `max_tasks` bounds the data-dependent task count.
-  int build_tasks(PartWs& pw, uint32_t max_tasks, cudaStream_t st) {
-    const uint32_t* off = offsets.as<uint32_t>() + pw.off;
-    pw.ntask.reserve(((size_t)pw.m + 1) * 4);
-    pw.task_base.reserve(((size_t)pw.m + 1) * 4);
-    pw.len_bins.reserve((MSM_TASK_LEN + 1) * 4);
-    pw.tasks.reserve((size_t)max_tasks * sizeof(uint4));
-    pw.partials.reserve((size_t)max_tasks * sizeof(XYZZ<F>));
-    msm_task_count_kernel<<<ceil_div(pw.m, 256), 256, 0, st>>>(off, pw.m, pw.ntask.template as<uint32_t>());
+  // ---- stage 3a: tasks: count per bucket -> scan -> length histogram -> emit sorted by length
+  int build_tasks(uint32_t nbuckets, uint32_t max_tasks, cudaStream_t st) {
+    const uint32_t* off = offsets.as<uint32_t>();
+    ntask.reserve(((size_t)nbuckets + 1) * 4);
+    task_base.reserve(((size_t)nbuckets + 1) * 4);
+    len_bins.reserve((MSM_TASK_LEN + 1) * 4);
+    tasks.reserve((size_t)max_tasks * sizeof(uint4));
+    partials.reserve((size_t)max_tasks * sizeof(XYZZ<F>));
+    msm_task_count_kernel<<<ceil_div(nbuckets, 256), 256, 0, st>>>(off, nbuckets, ntask.as<uint32_t>());
     CUDA_CHECK_LAUNCH();
-    int launches = 1 + scan_u32(pw.ntask.template as<uint32_t>(), pw.m, pw.task_base.template as<uint32_t>(), st);
-    CUDA_CHECK(cudaMemsetAsync(pw.len_bins.p, 0, (MSM_TASK_LEN + 1) * 4, st));
-    msm_task_hist_kernel<<<ceil_div(pw.m, 256), 256, 0, st>>>(off, pw.m, pw.len_bins.template as<uint32_t>());
+    int launches = 1 + scan_u32(ntask.as<uint32_t>(), nbuckets, task_base.as<uint32_t>(), st);
+    CUDA_CHECK(cudaMemsetAsync(len_bins.p, 0, (MSM_TASK_LEN + 1) * 4, st));
+    msm_task_hist_kernel<<<ceil_div(nbuckets, 256), 256, 0, st>>>(off, nbuckets, len_bins.as<uint32_t>());
     CUDA_CHECK_LAUNCH();
-    msm_task_bins_kernel<<<1, 32, 0, st>>>(pw.len_bins.template as<uint32_t>());
+    msm_task_bins_kernel<<<1, 32, 0, st>>>(len_bins.as<uint32_t>());
     CUDA_CHECK_LAUNCH();
-    msm_task_emit_kernel<<<ceil_div(pw.m, 256), 256, 0, st>>>(off, pw.task_base.template as<uint32_t>(), pw.m,
-                                                             pw.len_bins.template as<uint32_t>(), pw.tasks.template as<uint4>());
+    msm_task_emit_kernel<<<ceil_div(nbuckets, 256), 256, 0, st>>>(off, task_base.as<uint32_t>(), nbuckets,
+                                                                 len_bins.as<uint32_t>(), tasks.as<uint4>());
     CUDA_CHECK_LAUNCH();
     return launches + 3;
   }
 
-  // ---- stage 3b + 4: fold the partial sums of the part's buckets, then the weighted-sum recursion down
-  // to one item per window.  `overlapped`: the part runs beside a later part's accumulation, so its fused
-  // blocks are kept small enough (128 threads) to take the SM slot of a single retiring accumulate block.
-  int reduce_part(PartWs& pw, int n_windows, uint64_t entries_hint, bool overlapped, cudaStream_t st, StageTrace* tr) {
+  // ---- stage 3b + 4: fold the buckets that were cut into several tasks, then the weighted-sum recursion
+  // down to one item per window.  Returns the window sums through `wsum`.
+  int reduce_buckets(uint32_t nbuckets, int n_windows, uint64_t avg_entries, cudaStream_t st, StageTrace& tr,
+                     const XYZZ<FC>** wsum) {
     int launches = 0;
-    XYZZ<FC>* bk = buckets.as<XYZZ<FC>>() + pw.off;
-    pw.heavy.reserve(((size_t)pw.m + 1) * 4);
-    CUDA_CHECK(cudaMemsetAsync(pw.heavy.p, 0, 4, st));
-    msm_bucket_fold_kernel<FC><<<ceil_div(pw.m, 128), 128, 0, st>>>(
-        pw.partials.template as<XYZZ<FC>>(), pw.task_base.template as<uint32_t>(), pw.m, bk, pw.heavy.template as<uint32_t>(),
-        pw.heavy.template as<uint32_t>() + 1,
+    XYZZ<FC>* bk = buckets.as<XYZZ<FC>>();
+    heavy.reserve(((size_t)nbuckets + 1) * 4);
+    CUDA_CHECK(cudaMemsetAsync(heavy.p, 0, 4, st));
+    msm_bucket_fold_kernel<FC><<<ceil_div(nbuckets, 128), 128, 0, st>>>(
+        partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(), nbuckets, bk, heavy.as<uint32_t>(), heavy.as<uint32_t>() + 1,
         // "heavy" is relative to the average bucket: every bucket of a dense MSM (many entries per
         // bucket) folds serially in parallel with the others; only outliers get a whole block
-        MSM_FOLD_SERIAL + 3 * (uint32_t)(entries_hint / MSM_TASK_LEN));
+        MSM_FOLD_SERIAL + 3 * (uint32_t)(avg_entries / MSM_TASK_LEN));
     CUDA_CHECK_LAUNCH();
-    msm_bucket_fold_heavy_kernel<FC><<<296, 128, 0, st>>>(pw.partials.template as<XYZZ<FC>>(), pw.task_base.template as<uint32_t>(),
-                                                          pw.heavy.template as<uint32_t>(), pw.heavy.template as<uint32_t>() + 1, bk);
+    msm_bucket_fold_heavy_kernel<FC><<<296, 128, 0, st>>>(partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(),
+                                                          heavy.as<uint32_t>(), heavy.as<uint32_t>() + 1, bk);
     CUDA_CHECK_LAUNCH();
     launches += 2;
-    if (tr) tr->mark("fold");
-    uint32_t n_in = pw.m / n_windows;  // buckets per window
+    tr.mark("fold");
+    uint32_t n_in = nbuckets / n_windows;  // buckets per window
     const XYZZ<FC>* A = bk;
     const XYZZ<FC>* E = nullptr;
     int pp = 0;
-    const uint32_t seg_max = overlapped ? 32u : (uint32_t)WsFused<FC>::SEG;
     while (n_in > 1) {
       // wide levels (many items): radix reduce_L running sums, fewest group operations per bucket;
       // middle levels: radix 2, one thread per output (still throughput bound);
@@ -919,20 +736,19 @@ struct MsmEngine {
       bool wide = (uint64_t)n_in * n_windows >= (uint64_t)wide_threshold && n_in >= (uint32_t)reduce_L;
       bool fused = !wide && (uint64_t)(n_in / 2) * n_windows <= (uint64_t)quad_threshold;
       uint32_t L = wide ? (uint32_t)reduce_L : 2u;
-      if (fused) L = n_in < seg_max ? n_in : seg_max;
+      if (fused) L = n_in < (uint32_t)WsFused<FC>::SEG ? n_in : (uint32_t)WsFused<FC>::SEG;
       int logL = 0;
       while ((1u << logL) < L) logL++;
       uint32_t T = n_in / L;
       size_t bytes = (size_t)T * n_windows * sizeof(XYZZ<F>);
-      pw.lvlA[pp].reserve(bytes);
-      pw.lvlE[pp].reserve(bytes);
-      XYZZ<FC>* Ao = pw.lvlA[pp].template as<XYZZ<FC>>();
-      XYZZ<FC>* Eo = pw.lvlE[pp].template as<XYZZ<FC>>();
+      lvlA[pp].reserve(bytes);
+      lvlE[pp].reserve(bytes);
+      XYZZ<FC>* Ao = lvlA[pp].template as<XYZZ<FC>>();
+      XYZZ<FC>* Eo = lvlE[pp].template as<XYZZ<FC>>();
       if (wide)
         msm_ws_level_kernel<FC><<<ceil_div((uint64_t)T * n_windows, 64), 64, 0, st>>>(A, E, n_in, L, logL, n_windows, Ao, Eo);
       else if (fused)
-        // a role-0 and a role-1 warp per 8 chunks of the first level, never less than one pair of whole warps
-        msm_ws2_fused_kernel<FC><<<T * n_windows, L * 4 < 64 ? 64 : L * 4, 2 * WsFused<FC>::SEG * sizeof(XYZZ<FC>), st>>>(A, E, L, Ao, Eo);
+        msm_ws2_fused_kernel<FC><<<T * n_windows, WsFused<FC>::SEG * 4, 2 * WsFused<FC>::SEG * sizeof(XYZZ<FC>), st>>>(A, E, L, Ao, Eo);
       else
         msm_ws2_kernel<FC><<<ceil_div((uint64_t)ceil_div((uint64_t)T * n_windows, 32) * 64, 64), 64, 0, st>>>(A, E, n_in, n_windows, Ao, Eo);
       CUDA_CHECK_LAUNCH();
@@ -941,31 +757,11 @@ struct MsmEngine {
       E = Eo;
       n_in = T;
       pp ^= 1;
-      if (tr) tr->mark(wide ? "ws wide" : fused ? "ws fused" : "ws2");
+      tr.mark(wide ? "ws wide" : fused ? "ws fused" : "ws2");
     }
-    pw.A_final = A;
-    pw.E_final = E ? E : A;  // no level ran (one bucket per window): the bucket has weight 1 = itself
+    // n_in == 1: V_w = E_w (for B == 1 the single bucket has weight 1 = itself)
+    *wsum = E ? E : A;
     return launches;
-  }
-
-  // Bucket-range parts of a single-bucket-set MSM (window-precomputed table), largest first and every
-  // offset a multiple of its part's size: {1/2, 1/2}, {1/2, 1/4, 1/4} or {1/2, 1/4, 1/8, 1/8}.  The
-  // reduction of part p (a few hundred microseconds, mostly dependent group operations on a handful of
-  // warps) runs on a side stream while the accumulation of part p + 1 keeps the integer pipe full; only
-  // the LAST -- smallest -- part's reduction is left exposed.
-  int plan_parts(uint32_t nbuckets, bool single_set) {
-    int want = msm_options().split;
-    if (want == 0) want = nbuckets >= (1u << 18) ? 4 : nbuckets >= (1u << 16) ? 2 : 1;
-    if (!single_set || nbuckets < (1u << 14)) want = 1;
-    if (want > MSM_MAX_PARTS) want = MSM_MAX_PARTS;
-    uint32_t off = 0;
-    for (int p = 0; p < want; p++) {
-      uint32_t m = p + 1 < want ? nbuckets >> (p + 1) : nbuckets - off;
-      part[p].off = off;
-      part[p].m = m;
-      off += m;
-    }
-    return want;
   }
 
   // pts: device, affine Montgomery; scalars: device, canonical.  Leaves the affine canonical result
@@ -973,6 +769,12 @@ struct MsmEngine {
   // want_xyzz (multi-GPU shards).  Returns the number of kernels launched.
   // pre_stride != 0: `pts` is the base of a window-precomputed table [w][i] built with window width
   // force_c; the MSM covers points [pre_offset, pre_offset + n) of it.
+  //
+  // Measured and not kept (round 2): cutting the single bucket set of a precomputed-table MSM into
+  // bucket-range parts so that one part's reduction overlaps the next part's accumulation.  Accumulation
+  // blocks live ~0.3 ms (a 26-entry task at 1/512 of an SM's product rate), so every extra accumulate launch
+  // costs most of a block lifetime in under-filled waves (+0.1 ms per part at 2^20) while the exposed
+  // reduction of the last part is still log2(buckets) dependent levels long.
   int run(const Affine<F>* pts, const uint32_t* scalars, uint64_t n, cudaStream_t st, bool want_xyzz = false,
           int force_c = 0, uint32_t pre_stride = 0, uint32_t pre_offset = 0) {
     int launches = 0;
@@ -1000,51 +802,23 @@ struct MsmEngine {
 
     StageTrace tr(st);
     launches += sort_entries(scalars, n, pl, wstride, pre_stride, pre_offset, st, tr);
-
-    const int nparts = plan_parts(pl.nbuckets, pre_stride != 0);
-    if (nparts > 1) ensure_streams();
-    // the task count of a part is data dependent (all entries may fall into it): launch for the upper
-    // bound, threads past task_base[m] exit at once (no host round trip in the middle of the pipeline)
-    uint32_t max_tasks[MSM_MAX_PARTS];
-    for (int p = 0; p < nparts; p++) {
-      max_tasks[p] = (uint32_t)(total / MSM_TASK_LEN) + part[p].m + 1;
-      launches += build_tasks(part[p], max_tasks[p], st);
-    }
+    // the task count is data dependent: launch for the upper bound, threads past
+    // task_base[nbuckets] exit at once (no host round trip in the middle of the pipeline)
+    const uint32_t max_tasks = (uint32_t)(total / MSM_TASK_LEN) + pl.nbuckets + 1;
+    launches += build_tasks(pl.nbuckets, max_tasks, st);
     tr.mark("tasks");
-    for (int p = 0; p < nparts; p++) {
-      PartWs& pw = part[p];
-      // fully inlined field arithmetic here (an out-of-line-product build of this kernel measured 4 % slower)
-      msm_accumulate_kernel<F><<<ceil_div(max_tasks[p], 128), 128, 0, st>>>(
-          pts, sorted.as<uint32_t>(), pw.tasks.template as<uint4>(), pw.task_base.template as<uint32_t>() + pw.m,
-          pw.partials.template as<XYZZ<F>>());
-      CUDA_CHECK_LAUNCH();
-      launches++;
-      if (nparts > 1 && p + 1 < nparts) {
-        CUDA_CHECK(cudaEventRecord(ev_acc[p], st));
-        cudaStream_t side = aux[p & 1];
-        CUDA_CHECK(cudaStreamWaitEvent(side, ev_acc[p], 0));
-        launches += reduce_part(pw, n_windows, total / pl.nbuckets, true, side, nullptr);
-        CUDA_CHECK(cudaEventRecord(ev_red[p], side));
-      }
-    }
+    // fully inlined field arithmetic here (an out-of-line-product build of this kernel measured 4 % slower)
+    msm_accumulate_kernel<F><<<ceil_div(max_tasks, 128), 128, 0, st>>>(pts, sorted.as<uint32_t>(), tasks.as<uint4>(),
+                                                                      task_base.as<uint32_t>() + pl.nbuckets,
+                                                                      partials.as<XYZZ<F>>(), buckets.as<XYZZ<F>>());
+    CUDA_CHECK_LAUNCH();
+    launches++;
     tr.mark("accumulate");
-    launches += reduce_part(part[nparts - 1], n_windows, total / pl.nbuckets, false, st, &tr);
-    for (int p = 0; p + 1 < nparts; p++) CUDA_CHECK(cudaStreamWaitEvent(st, ev_red[p], 0));
-    if (nparts == 1) {
-      msm_final_kernel<FC><<<1, 32, 0, st>>>(reinterpret_cast<const XYZZ<FC>*>(part[0].E_final), n_windows, pl.c, nullptr, 0,
-                                            want_xyzz ? nullptr : reinterpret_cast<Affine<FC>*>(out_aff), flag.as<int>(),
-                                            want_xyzz ? reinterpret_cast<XYZZ<FC>*>(out_xyzz) : nullptr);
-    } else {
-      MsmPartsFinal f;
-      f.count = nparts;
-      for (int p = 0; p < nparts; p++) {
-        f.A[p] = part[p].A_final;
-        f.E[p] = part[p].E_final;
-        f.k[p] = part[p].off / part[p].m;
-      }
-      msm_final_parts_kernel<FC><<<1, 32, 0, st>>>(f, want_xyzz ? nullptr : reinterpret_cast<Affine<FC>*>(out_aff),
-                                                  flag.as<int>(), want_xyzz ? reinterpret_cast<XYZZ<FC>*>(out_xyzz) : nullptr);
-    }
+    const XYZZ<FC>* wsum = nullptr;
+    launches += reduce_buckets(pl.nbuckets, n_windows, total / pl.nbuckets, st, tr, &wsum);
+    msm_final_kernel<FC><<<1, 32, 0, st>>>(wsum, n_windows, pl.c, nullptr, 0,
+                                          want_xyzz ? nullptr : reinterpret_cast<Affine<FC>*>(out_aff), flag.as<int>(),
+                                          want_xyzz ? reinterpret_cast<XYZZ<FC>*>(out_xyzz) : nullptr);
     CUDA_CHECK_LAUNCH();
     launches++;
     tr.mark("horner+affine");

@@ -24,14 +24,9 @@ int zkp_msm_set_window_bits(int c) {
 
 int zkp_msm_set_option(const char* name, int value) {
   std::string n = name ? name : "";
-  if (n == "sort" && value >= 0 && value <= 2) msm_options().sort = value;
-  else if (n == "split" && value >= 0 && value <= MSM_MAX_PARTS) msm_options().split = value;
-  else if (n == "window_bits") return zkp_msm_set_window_bits(value);
-  else {
-    set_last_error("zkp_msm_set_option: unknown option or value out of range (sort 0..2, split 0..4, window_bits)");
-    return ZKP_ERR_INVALID_ARGUMENT;
-  }
-  return ZKP_OK;
+  if (n == "window_bits") return zkp_msm_set_window_bits(value);
+  set_last_error("zkp_msm_set_option: unknown option (window_bits)");
+  return ZKP_ERR_INVALID_ARGUMENT;
 }
 
 int zkp_g1_msm_multi(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n,

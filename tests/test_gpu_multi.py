@@ -1,6 +1,6 @@
-"""-m gpu: the multi-GPU entry points of the C ABI (zkp_comm_*, zkp_g1_msm_multi, zkp_g2_msm_multi) and the
-engine variants behind them (radix-partition sort, bucket-range parts), verified at sizes the CPU cannot
-reach through the device-side identity  sum_i k_i (s_i G) == <k, s> G  (zkp_fr_dot_dev).
+"""-m gpu: the multi-GPU entry points of the C ABI (zkp_comm_*, zkp_g1_msm_multi, zkp_g2_msm_multi), verified
+at sizes the CPU cannot reach through the device-side identity  sum_i k_i (s_i G) == <k, s> G
+(zkp_fr_dot_dev).
 
 The communicator of the calling process is a one-rank NCCL world (the driver's GPU tier has one GPU):
 local MSM -> ncclAllGather -> fold runs through exactly the code the 8-GPU runs use.  When two or more
@@ -130,34 +130,24 @@ def test_msm_multi_2p22_device_verified(native, comm):
 
 
 @pytest.mark.parametrize("log_n,pre_c", [(17, 17), (18, 20), (20, 0), (20, 20)])
-def test_sort_and_split_variants_agree(native, log_n, pre_c):
-    """Every engine variant (counting sort / radix partition, 1-4 bucket-range parts) returns the same point
-    as <k, s> G, on a precomputed table (pre_c) or a plain one (pre_c = 0)."""
+def test_large_msm_device_verified(native, log_n, pre_c):
+    """Whole-table and offset sub-range MSMs at sizes the CPU cannot reach: result == <k, s> G with the dot
+    product taken on the device, on a precomputed table (pre_c) or a plain one (pre_c = 0)."""
     n = 1 << log_n
     table, s_h, k_h = _known_dlog_table(native, n, 0x5EED0002 + log_n, 0x5EED0001 + log_n)
-    want = bn254.g1_mul(bn254.G1, native.fr_dot_dev(k_h, 0, s_h, 0, n))
     if pre_c:
         native.table_precompute(table, pre_c)
-    try:
-        for sort in (1, 2):
-            for split in ((1, 2, 3, 4) if pre_c else (1,)):
-                native.msm_set_option("sort", sort)
-                native.msm_set_option("split", split)
-                assert native.g1_msm_dev(table, 0, k_h, 0, n) == want, (sort, split)
-        # a sub-range with an offset into both vectors, automatic settings
-        native.msm_set_option("sort", 0)
-        native.msm_set_option("split", 0)
-        m = n // 2 + 3
-        want_sub = bn254.g1_mul(bn254.G1, native.fr_dot_dev(k_h, 5, s_h, 7, m))
-        assert native.g1_msm_dev(table, 7, k_h, 5, m) == want_sub
-    finally:
-        native.msm_set_option("sort", 0)
-        native.msm_set_option("split", 0)
+    assert native.g1_msm_dev(table, 0, k_h, 0, n) == bn254.g1_mul(bn254.G1, native.fr_dot_dev(k_h, 0, s_h, 0, n))
+    m = n // 2 + 3
+    assert native.g1_msm_dev(table, 7, k_h, 5, m) == bn254.g1_mul(bn254.G1, native.fr_dot_dev(k_h, 5, s_h, 7, m))
+    assert native.msm_set_option("window_bits", 0) is None
+    with pytest.raises(native.ZkpB200Error):
+        native.msm_set_option("no such option", 1)
 
 
-def test_radix_sort_skewed_scalars(native):
-    """Skewed digit distributions through the radix partition and the bucket-range parts: all scalars equal
-    (every window's digits land in one bucket), half of them zero, tiny scalars (only the lowest window used)."""
+def test_skewed_scalars_at_2p17(native):
+    """Skewed digit distributions at a size where buckets are cut into many tasks: all scalars equal (every
+    window's digits land in one bucket), half of them zero, tiny scalars (only the lowest window used), r - 1."""
     n = 1 << 17
     table, s_h, _ = _known_dlog_table(native, n, 0x5EED0102)
     native.table_precompute(table, 17)
@@ -169,18 +159,11 @@ def test_radix_sort_skewed_scalars(native):
         "tiny": [rng.randrange(1, 1000) for _ in range(n)],
         "r - 1": [R - 1] * n,
     }
-    try:
-        native.msm_set_option("sort", 2)
-        for name, k in cases.items():
-            k_h = native.scalars_load(native.fr_vec_bytes(k), n)
-            want = bn254.g1_mul(bn254.G1, native.fr_dot_dev(k_h, 0, s_h, 0, n))
-            for split in (1, 4):
-                native.msm_set_option("split", split)
-                assert native.g1_msm_dev(table, 0, k_h, 0, n) == want, (name, split)
-            k_h.free()
-    finally:
-        native.msm_set_option("sort", 0)
-        native.msm_set_option("split", 0)
+    for name, k in cases.items():
+        k_h = native.scalars_load(native.fr_vec_bytes(k), n)
+        want = bn254.g1_mul(bn254.G1, native.fr_dot_dev(k_h, 0, s_h, 0, n))
+        assert native.g1_msm_dev(table, 0, k_h, 0, n) == want, name
+        k_h.free()
 
 
 _WORKER = r'''
