@@ -123,6 +123,9 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters
     return;
   }
   if (VARIANT == 0) {
+    // the multiplier is a per-thread register, as the limb b_i of a CIOS row is (with a kernel-uniform multiplier
+    // ptxas feeds it from a uniform register and the same loop reads 10 % lower)
+    const uint32_t y = (seed * 3u) | b;
     uint32_t a[4][8];
 #pragma unroll
     for (int k = 0; k < 4; k++)
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters
                        "addc.u32        %8, 0, 0;"
                        : "+r"(a[k][0]), "+r"(a[k][1]), "+r"(a[k][2]), "+r"(a[k][3]), "+r"(a[k][4]), "+r"(a[k][5]),
                          "+r"(a[k][6]), "+r"(a[k][7]), "=r"(c)
-                       : "r"(a[(k + 1) & 3][0]), "r"(a[(k + 1) & 3][2]), "r"(a[(k + 1) & 3][4]), "r"(a[(k + 1) & 3][6]), "r"(b));
+                       : "r"(a[(k + 1) & 3][0]), "r"(a[(k + 1) & 3][2]), "r"(a[(k + 1) & 3][4]), "r"(a[(k + 1) & 3][6]), "r"(y));
           cs += c;
         }
       }
