@@ -8,8 +8,12 @@
 // (32-byte elements = one DRAM sector each) and writes contiguous 32 KB tiles; later passes work on
 // tiles of 2^S strided rows x 2^(10-S) contiguous elements.  A 32-byte element is exactly one sector, so
 // even a run of one element wastes no bandwidth: taking all 10 stages per pass (2^20 = 10 + 10, two
-// passes) measured 4 % faster than insisting on 256-byte runs (10 + 7 + 3, three passes).  Shared memory is
-// limb-major (SoA) so consecutive threads hit consecutive banks.  Twiddles omega^i, i < n/2, are
+// passes) measured 4 % faster than insisting on 256-byte runs (10 + 7 + 3, three passes).  Shared memory holds
+// the tile as swizzled 128-bit halves (conflict-free LDS.128 / STS.128).  A radix-8 variant (three stages per
+// round in registers, first / last round straight from / to global memory) was built and measured in round 2:
+// 0.27 - 0.32 ms at 2^20 against 0.24 ms for the radix-4 rounds below (its 8 scattered loads + 7 twiddle
+// loads per thread stall on the load queue, ncu: lg_throttle 0.9, long_scoreboard 2.1, no_instruction 1.1 per
+// issue) and was not kept.  Twiddles omega^i, i < n/2, are
 // precomputed on the device in Montgomery form and cached per (omega, n); because they are
 // Montgomery constants, the data keeps whatever form it came in (canonical host data needs no
 // conversion).  The n^-1 factor of the inverse and the coset scalings are fused into the
@@ -73,19 +77,33 @@ struct NttPassArgs {
   Fr n_inv;             // Montgomery
 };
 
-__device__ __forceinline__ Fr lds_elem(const uint32_t* sm, uint32_t tile, uint32_t idx) {
+// Shared-memory tile: element `slot` is kept as two 16-byte halves, half h at uint4 index (h << log_tile) +
+// swz(slot): every access is a 128-bit LDS / STS (two per element instead of eight 32-bit ones).  swz XORs
+// the low three slot bits with parities of the higher ones so that the eight lanes of a quarter-warp fall
+// into eight different 16-byte bank groups for every index pattern of the radix-4 / radix-2 rounds and of
+// the load / store phases (all (S, log_g) splits of a 1024-element tile, checked exhaustively; the
+// limb-major 32-bit layout of round 1 took 3.7 M bank conflicts per pass).
+__device__ __forceinline__ uint32_t ntt_swz(uint32_t slot) {
+  const uint32_t hb = slot >> 3;
+  const uint32_t p = __popc(hb & 23u) & 1u, q = __popc(hb & 42u) & 1u;
+  return slot ^ (p * 5u) ^ (q << 1);
+}
+__device__ __forceinline__ Fr lds_elem(const uint4* sm, uint32_t tile, uint32_t slot) {
+  const uint32_t i = ntt_swz(slot);
+  uint4 lo = sm[i], hi = sm[tile + i];
   Fr r;
-#pragma unroll
-  for (int l = 0; l < 8; l++) r.v[l] = sm[l * tile + idx];
+  r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+  r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
   return r;
 }
-__device__ __forceinline__ void sts_elem(uint32_t* sm, uint32_t tile, uint32_t idx, const Fr& x) {
-#pragma unroll
-  for (int l = 0; l < 8; l++) sm[l * tile + idx] = x.v[l];
+__device__ __forceinline__ void sts_elem(uint4* sm, uint32_t tile, uint32_t slot, const Fr& x) {
+  const uint32_t i = ntt_swz(slot);
+  sm[i] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  sm[tile + i] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
 }
 
 __global__ void __launch_bounds__(128, 4) ntt_pass_kernel(NttPassArgs a) {
-  extern __shared__ uint32_t sm[];
+  extern __shared__ uint4 sm[];
   const uint32_t log_tile = a.S + a.log_g;
   const uint32_t tile = 1u << log_tile;
   const uint32_t G = 1u << a.log_g;
@@ -350,8 +368,7 @@ int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes&
   if (S1 == log_n) a.dst = data;
   {
     uint32_t tile = 1u << (a.S + a.log_g);
-    uint32_t threads = tile >= 4 ? tile / 4 : 1;
-    if (tile >= 32u * NTT_ELEMS_PER_THREAD) threads = tile / NTT_ELEMS_PER_THREAD;
+    uint32_t threads = tile >= NTT_ELEMS_PER_THREAD ? tile / NTT_ELEMS_PER_THREAD : 1;
     ntt_pass_kernel<<<n / tile, threads, tile * 32, c.stream>>>(a);
     CUDA_CHECK_LAUNCH();
     launches++;
@@ -370,8 +387,7 @@ int ntt_device(Context& c, Fr* data, Fr* scratch, uint32_t log_n, const FrBytes&
     if (a.log_g > a.s0) a.log_g = a.s0;
     if (done + S == log_n) a.dst = data;  // the last pass lands in the caller's buffer (no extra copy)
     uint32_t tile = 1u << (a.S + a.log_g);
-    uint32_t threads = tile / 4;
-    if (tile >= 32u * NTT_ELEMS_PER_THREAD) threads = tile / NTT_ELEMS_PER_THREAD;
+    uint32_t threads = tile >= NTT_ELEMS_PER_THREAD ? tile / NTT_ELEMS_PER_THREAD : 1;
     ntt_pass_kernel<<<n / tile, threads, tile * 32, c.stream>>>(a);
     CUDA_CHECK_LAUNCH();
     launches++;
