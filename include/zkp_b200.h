@@ -44,6 +44,9 @@ int zkp_shutdown(void);
 const char* zkp_last_error(void);
 int zkp_device_info(char* name, int name_cap, int* sm_count, int* cc_major, int* cc_minor, int* sm_clock_khz);
 int zkp_device_mem_info(uint64_t* free_bytes, uint64_t* total_bytes);
+/* "domain:bus:device.function" of the library's GPU (e.g. to pin the calling process to the GPU's NUMA node
+ * before it allocates page-locked staging buffers: sharded.bind_to_gpu_numa_node) */
+int zkp_device_pci_bus_id(char* out, int cap);
 /* number of kernels this library has launched since zkp_init (bench.py "gpu_launches") */
 uint64_t zkp_launch_count(void);
 /* CUDA-event timer on the library's stream (the stream every kernel is launched on) */

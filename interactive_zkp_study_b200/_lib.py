@@ -37,6 +37,7 @@ PROTOTYPES = {
     "zkp_last_error": (ctypes.c_char_p, []),
     "zkp_device_info": (c_int, [ctypes.c_char_p, c_int, intp, intp, intp, intp]),
     "zkp_device_mem_info": (c_int, [u64p, u64p]),
+    "zkp_device_pci_bus_id": (c_int, [ctypes.c_char_p, c_int]),
     "zkp_launch_count": (u64, []),
     "zkp_timer_start": (c_int, []),
     "zkp_timer_stop": (c_int, [f32p]),

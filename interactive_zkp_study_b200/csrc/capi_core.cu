@@ -191,6 +191,13 @@ int zkp_device_info(char* name, int name_cap, int* sm_count, int* cc_major, int*
   });
 }
 
+int zkp_device_pci_bus_id(char* out, int cap) {
+  return guarded([&](Context& c) {
+    if (!out || cap < 16) throw InvalidArgument("zkp_device_pci_bus_id: need a buffer of at least 16 bytes");
+    CUDA_CHECK(cudaDeviceGetPCIBusId(out, cap, c.device));
+  });
+}
+
 int zkp_device_mem_info(uint64_t* free_bytes, uint64_t* total_bytes) {
   return guarded([&](Context&) {
     size_t f = 0, t = 0;

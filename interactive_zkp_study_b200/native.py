@@ -75,6 +75,12 @@ def device_info():
             "sm_clock_khz": khz.value}
 
 
+def device_pci_bus_id():
+    out = ctypes.create_string_buffer(32)
+    check(_lib.lib().zkp_device_pci_bus_id(out, 32))
+    return out.value.decode().lower()
+
+
 def device_mem_info():
     f, t = ctypes.c_uint64(), ctypes.c_uint64()
     check(_lib.lib().zkp_device_mem_info(ctypes.byref(f), ctypes.byref(t)))

@@ -49,14 +49,9 @@ def setup_from_toxic(k, alpha, beta, delta, x_val, zx_val, priv_vals, precompute
     return DeviceKey(k, m_priv, TA, TB2, TC)
 
 
-def prove(key, uA, uB, uC, Z, rx_priv, r, s, keep_quotient=False):
-    """uA, uB, uC: device scalar handles with k coefficients; Z: handle with k+1 coefficients (monic
-    divisor); rx_priv: handle with the private wires' witness values.  Returns (A, B, C) as the
-    reference's point types (and the quotient / remainder handles when keep_quotient)."""
+def _proof_scalars(key, uA, uB, hq, rx_priv, r, s):
+    """The three MSM scalar vectors of one proof, assembled on the device (see the table layout above)."""
     k, mp = key.k, key.m_priv
-    r, s = int(r) % R, int(s) % R
-    # H: k-1 coefficients; the remainder (k coefficients, zero for a satisfied instance) only on request
-    hq, hr = native.groth16_quotient_dev(uA, uB, uC, k, Z, k + 1, want_remainder=keep_quotient)
     one = native.fr_vec_bytes([1])
     scA = native.scalars_alloc(k + 2)
     native.scalars_copy(scA, 0, uA, 0, k)
@@ -73,9 +68,21 @@ def prove(key, uA, uB, uC, Z, rx_priv, r, s, keep_quotient=False):
         native.scalars_copy(scC, k + 1, rx_priv, 0, mp)
     if k > 1:
         native.scalars_copy(scC, k + 1 + mp, hq, 0, k - 1)
+    return scA, scB, scC, nC
+
+
+def prove(key, uA, uB, uC, Z, rx_priv, r, s, keep_quotient=False):
+    """uA, uB, uC: device scalar handles with k coefficients; Z: handle with k+1 coefficients (monic
+    divisor); rx_priv: handle with the private wires' witness values.  Returns (A, B, C) as the
+    reference's point types (and the quotient / remainder handles when keep_quotient)."""
+    k = key.k
+    r, s = int(r) % R, int(s) % R
+    # H: k-1 coefficients; the remainder (k coefficients, zero for a satisfied instance) only on request
+    hq, hr = native.groth16_quotient_dev(uA, uB, uC, k, Z, k + 1, want_remainder=keep_quotient)
+    scA, scB, scC, nC = _proof_scalars(key, uA, uB, hq, rx_priv, r, s)
     # A and X in G1 on one stream, B in G2 beside them on a second one
     A, B, X = native.groth16_msms_dev(key.TA, scA, k + 2, key.TB2, scB, k + 2, key.TC, scC, nC)
-    C = native.g1_msm(native.g1_bytes(A) + native.g1_bytes(X), native.fe_bytes(s) + one, 2)
+    C = native.g1_msm(native.g1_bytes(A) + native.g1_bytes(X), native.fe_bytes(s) + native.fr_vec_bytes([1]), 2)
     for h in (scA, scB, scC):
         h.free()
     out = (g1_from_ints(A), g2_from_ints(B), g1_from_ints(C))
@@ -83,3 +90,57 @@ def prove(key, uA, uB, uC, Z, rx_priv, r, s, keep_quotient=False):
         return out + (hq, hr)
     hq.free()
     return out
+
+
+# ------------------------------------------------------------------ the same proof over the GPUs of one box
+class ShardedDeviceKey:
+    """This rank's contiguous row range of each of the three CRS tables (sharded.shard_range of the
+    concatenated table), resident and window-precomputed on this rank's GPU."""
+
+    def __init__(self, k, m_priv, TA, TB2, TC, rA, rB, rC):
+        self.k, self.m_priv, self.TA, self.TB2, self.TC = k, m_priv, TA, TB2, TC
+        self.rA, self.rB, self.rC = rA, rB, rC        # (start, count) of this rank in each table
+
+
+def setup_from_toxic_sharded(comm, k, alpha, beta, delta, x_val, zx_val, priv_vals, precompute=True):
+    """setup_from_toxic with every table cut by point range over the ranks of `comm`: a rank
+    generates and keeps only its rows.  Same arguments on every rank."""
+    from ... import sharded
+    m_priv = len(priv_vals)
+    pw = _powers(x_val, k)
+    inv_delta = pow(delta % R, -1, R)
+    s15 = native.fr_vec_op(3, pw[:32 * (k - 1)], native.fe_bytes(zx_val % R * inv_delta % R), k - 1) if k > 1 else b""
+    enc = native.fr_vec_bytes
+    scA = pw + enc([alpha % R, delta % R])
+    scB = pw + enc([beta % R, delta % R])
+    scC = pw + enc([beta % R]) + enc([v % R for v in priv_vals]) + s15
+    out = []
+    for sc, g2 in ((scA, False), (scB, True), (scC, False)):
+        start, count = sharded.shard_range(len(sc) // 32, comm.rank, comm.world)
+        part = sc[32 * start:32 * (start + count)]
+        t = (native.g2_fixed_base_mul(native.g2_bytes(G2), part, count) if g2
+             else native.g1_fixed_base_mul(native.g1_bytes(G1), part, count))
+        if precompute and count >= 2:
+            native.table_precompute(t)
+        out.append((t, (start, count)))
+    (TA, rA), (TB2, rB), (TC, rC) = out
+    return ShardedDeviceKey(k, m_priv, TA, TB2, TC, rA, rB, rC)
+
+
+def prove_sharded(comm, key, uA, uB, uC, Z, rx_priv, r, s):
+    """prove() with each of the three multi-scalar multiplications sharded by point range over the ranks
+    (zkp_g1_msm_multi / zkp_g2_msm_multi: local Pippenger -> one all-gather of the partial sums -> fold, inside
+    the library).  Collective: every rank passes the same coefficient vectors and gets the same proof.  The
+    quotient -- NTT work, which stays on one GPU -- is computed by every rank for itself: that
+    costs no wall time and needs no 32 MiB broadcast of H."""
+    k = key.k
+    r, s = int(r) % R, int(s) % R
+    hq, _ = native.groth16_quotient_dev(uA, uB, uC, k, Z, k + 1, want_remainder=False)
+    scA, scB, scC, _ = _proof_scalars(key, uA, uB, hq, rx_priv, r, s)
+    A = native.g1_msm_multi(key.TA, 0, scA, key.rA[0], key.rA[1])
+    B = native.g2_msm_multi(key.TB2, 0, scB, key.rB[0], key.rB[1])
+    X = native.g1_msm_multi(key.TC, 0, scC, key.rC[0], key.rC[1])
+    C = native.g1_msm(native.g1_bytes(A) + native.g1_bytes(X), native.fe_bytes(s) + native.fr_vec_bytes([1]), 2)
+    for h in (scA, scB, scC, hq):
+        h.free()
+    return (g1_from_ints(A), g2_from_ints(B), g1_from_ints(C))

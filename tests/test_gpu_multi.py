@@ -166,6 +166,30 @@ def test_skewed_scalars_at_2p17(native):
         k_h.free()
 
 
+def test_groth16_prove_sharded_equals_single_gpu(native, comm):
+    """device_prover.prove_sharded (three MSMs through zkp_g1/g2_msm_multi on range-sharded CRS tables) returns
+    the proof of device_prover.prove on the unsharded key; k = 2^10 constraints, random coefficient vectors."""
+    from interactive_zkp_study_b200.zkp.groth16 import device_prover as dp
+    rng = random.Random(31)
+    k = 1 << 10
+    mp = k - 2
+    alpha, beta, delta, x = (rng.randrange(1, R) for _ in range(4))
+    Z = native.scalars_generate(0x5EED0300, k + 1)
+    native.scalars_upload(Z, k, native.fe_bytes(1), 1)
+    zx = native.fr_poly_eval_dev(Z, 0, k + 1, x)
+    priv = [rng.randrange(R) for _ in range(mp)]
+    uA, uB, uC = (native.scalars_generate(0x5EED0100 + i, k) for i in range(3))
+    rx = native.scalars_generate(0x5EED0200, mp)
+    r, s = rng.randrange(R), rng.randrange(R)
+    key = dp.setup_from_toxic(k, alpha, beta, delta, x, zx, priv)
+    skey = dp.setup_from_toxic_sharded(comm, k, alpha, beta, delta, x, zx, priv)
+    assert (skey.rA, skey.rB, skey.rC) == ((0, k + 2), (0, k + 2), (0, 3 * k - 2))
+    want = dp.prove(key, uA, uB, uC, Z, rx, r, s)
+    got = dp.prove_sharded(comm, skey, uA, uB, uC, Z, rx, r, s)
+    enc = lambda P: (native.g1_bytes(P[0]), native.g2_bytes(P[1]), native.g1_bytes(P[2]))
+    assert enc(got) == enc(want)
+
+
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, %(root)r)
