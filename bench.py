@@ -604,12 +604,21 @@ def run_ours(args):
             h.free()
 
     g16_sharded = None
-    if comm is not None and args.extras and args.log_n <= 20 and os.environ.get("ZKP_BENCH_G16_SHARDED", "0") == "1":
+    if comm is not None and args.extras and args.log_n <= 20 and os.environ.get("ZKP_BENCH_G16_SHARDED", "1") == "1":
         try:
             g16_sharded = groth16_record(args.log_n, None, comm=comm)
             g16_sharded["prove_ms"] = max_over_ranks(g16_sharded["prove_ms"])
         except Exception as e:  # never lose the headline line
             g16_sharded = {"error": repr(e)}
+    plonk_sharded = None
+    if comm is not None and args.extras and args.log_n <= 20 and os.environ.get("ZKP_BENCH_PLONK_SHARDED", "1") == "1":
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import plonk_large
+            plonk_sharded = plonk_large.run(args.log_n, 3, verify=(rank == 0), quiet=True, comm=comm)
+            plonk_sharded["prove_ms"] = max_over_ranks(plonk_sharded["prove_ms"])
+        except Exception as e:  # never lose the headline line
+            plonk_sharded = {"error": repr(e)}
     if comm is not None:
         comm.close()
     if rank != 0:
@@ -704,6 +713,8 @@ def run_ours(args):
                                        "frac": ach / (peak_t * world), "algorithmic_macs": macs,
                                        "algorithmic_note": "SURVEY 8d model (4 G1 MSMs + 1 G2 MSM x3 + quotient) against %d x the one-GPU peak" % world}
         sub["groth16_prove"] = g16_sharded
+    if plonk_sharded is not None:
+        sub["plonk_prove"] = plonk_sharded
     line.update(sub)
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -34,6 +34,7 @@ class DeviceKey:
 
     def __init__(self):
         self.coeffs, self.coset, self.comm = {}, {}, {}
+        self.ranks, self.srs_range = None, None     # sharded SRS: the communicator and this rank's row range
 
 
 def _alloc_from(src, n, total):
@@ -43,19 +44,33 @@ def _alloc_from(src, n, total):
 
 
 def _commit(key, h, off, length):
-    return native.g1_msm_dev(key.srs_table, 0, h, off, length)
+    """kzg.commit (kzg.py:32-67) of coefficients h[off : off + length] against SRS powers 0 .. length - 1."""
+    if key.ranks is None:
+        return native.g1_msm_dev(key.srs_table, 0, h, off, length)
+    # sharded SRS (SURVEY 8e): this rank holds powers [start, start + count); its share of the commitment is the
+    # MSM over the powers of its range that the polynomial reaches (possibly none), folded inside the library
+    start, count = key.srs_range
+    m = max(0, min(count, length - start))
+    return native.g1_msm_multi(key.srs_table, 0, h, off + start if m else 0, m)
 
 
 def _commit_many(key, items):
-    """Several commitments against the SRS in one pipelined call: items = [(handle, offset, length)]."""
+    """Several commitments against the SRS: items = [(handle, offset, length)].  On one GPU they go out as one
+    pipelined call (the tail of one MSM overlaps the accumulation of the next); sharded, each is a collective."""
+    if key.ranks is not None:
+        return [_commit(key, h, off, length) for h, off, length in items]
     return native.g1_msm_dev_batch(key.srs_table, [(h, off, 0, length) for h, off, length in items])
 
 
-def preprocess(n, selector_evals, sigma_evals, srs_table, srs_size):
+def preprocess(n, selector_evals, sigma_evals, srs_table, srs_size, comm=None, srs_range=None):
     """selector_evals: 5 handles (q_l, q_r, q_o, q_m, q_c evaluations on H, n each); sigma_evals: 3
     handles with the evaluations of S_sigma1..3 (permutation.py:44-86).  Mirrors
-    preprocessor.py:59-130: 8 iNTTs + 8 commitments, plus the static round-3 data."""
+    preprocessor.py:59-130: 8 iNTTs + 8 commitments, plus the static round-3 data.
+    comm / srs_range: a sharded.Communicator and the (start, count) row range of the SRS that `srs_table`
+    holds on this rank; every commitment of preprocess() and prove() is then a collective over the ranks,
+    while the NTT / quotient work is done by every rank for itself (it stays single-GPU work)."""
     key = DeviceKey()
+    key.ranks, key.srs_range = comm, srs_range
     key.n, key.log_n = n, n.bit_length() - 1
     key.omega = int(get_root_of_unity(n))
     # quotient coset: the smallest power-of-two multiple of n with at least 3n+6 points (deg t = 3n+5)

@@ -190,6 +190,24 @@ def test_groth16_prove_sharded_equals_single_gpu(native, comm):
     assert enc(got) == enc(want)
 
 
+def test_plonk_prove_with_sharded_srs_equals_single_gpu(native, comm):
+    """PLONK device prover with the SRS held as a row range and every commitment a collective MSM: same proof
+    as the unsharded prover for equal blinding scalars (n = 2^10 gates)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import plonk_synth
+    from interactive_zkp_study_b200.zkp.plonk import device_prover as dp
+    circ = plonk_synth.chain_circuit(1 << 10, seed=5)
+    key, wit, _ = plonk_synth.device_setup(circ)
+    skey, swit, _ = plonk_synth.device_setup(circ, comm=comm)
+    assert skey.srs_range == (0, (1 << 10) + 6) and skey.ranks is comm
+    assert {k: skey.comm[k] for k in dp.CIRCUIT_POLYS} == {k: key.comm[k] for k in dp.CIRCUIT_POLYS}
+    blinds = list(range(101, 110))
+    want = dp.prove(key, *wit, blinds=blinds)
+    got = dp.prove(skey, *swit, blinds=blinds)
+    flat = lambda pr: {k: (native.g1_bytes(v) if k.endswith("_comm") else int(v)) for k, v in vars(pr).items()}
+    assert flat(got) == flat(want)
+
+
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, %(root)r)

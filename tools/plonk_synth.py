@@ -53,22 +53,29 @@ def sigma_evals_bytes(sigma, n, omega):
     return out
 
 
-def device_setup(circ, srs_tau=None, precompute=True):
+def device_setup(circ, srs_tau=None, precompute=True, comm=None):
     """SRS on the device (tau^i G from a prefix-product + fixed-base kernel), the circuit uploaded, the
-    device key preprocessed.  Returns (key, witness handles, g2_powers as ints, tau)."""
+    device key preprocessed.  Returns (key, witness handles, tau).  comm: a sharded.Communicator -> every rank
+    keeps only its row range of the SRS and all commitments are collective (same arguments on every rank)."""
     from interactive_zkp_study_b200.zkp.plonk import device_prover as dp
     from interactive_zkp_study_b200.zkp.plonk.field import get_root_of_unity
     n = circ["n"]
     tau = srs_tau or 0x1d0c2e3f4a5b6c7d8e9fa0b1c2d3e4f5061728394a5b6c7d8e9f0011223344 % R
     size = n + 6
     powers = nat.fr_prefix_product(nat.fr_vec_bytes([tau] * size), size)
-    srs = nat.g1_fixed_base_mul(nat.g1_bytes((1, 2)), powers, size)
-    if precompute and size >= (1 << 12):
+    srs_range = None
+    if comm is not None:
+        from interactive_zkp_study_b200 import sharded
+        srs_range = sharded.shard_range(size, comm.rank, comm.world)
+        powers = powers[32 * srs_range[0]:32 * (srs_range[0] + srs_range[1])]
+    rows = size if srs_range is None else srs_range[1]
+    srs = nat.g1_fixed_base_mul(nat.g1_bytes((1, 2)), powers, rows)
+    if precompute and rows >= (1 << 12):
         nat.table_precompute(srs)
     omega = int(get_root_of_unity(n))
     enc = nat.fr_vec_bytes
     sel_h = [nat.scalars_load(enc(v), n) for v in circ["sel"]]
     sig_h = [nat.scalars_load(bts, n) for bts in sigma_evals_bytes(circ["sigma"], n, omega)]
-    key = dp.preprocess(n, sel_h, sig_h, srs, size)
+    key = dp.preprocess(n, sel_h, sig_h, srs, size, comm=comm, srs_range=srs_range)
     wit = [nat.scalars_load(enc(circ[k]), n) for k in "abc"]
     return key, wit, tau
