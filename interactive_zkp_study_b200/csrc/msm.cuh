@@ -81,8 +81,9 @@ inline int msm_auto_precomputed_c(uint64_t n) {
 // ---------------------------------------------------------------- stage 1: digits + histogram
 // wstride: distance between the bucket sets of consecutive windows (B for a plain table; 0 for a
 // window-precomputed table, where all windows share one bucket set).
-static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, int c, int W, uint32_t B,
-                                  uint32_t wstride, uint32_t* __restrict__ codes, uint32_t* __restrict__ hist);
+static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, uint64_t i0, uint64_t i1, int c,
+                                         int W, uint32_t B, uint32_t wstride, uint32_t* __restrict__ codes,
+                                         uint32_t* __restrict__ hist);
 
 // ---------------------------------------------------------------- exclusive scan (u32), 3 kernels
 static constexpr int SCAN_BLOCK = 1024;
@@ -224,10 +225,12 @@ __device__ __forceinline__ uint32_t msm_digit_code(const uint32_t (&s)[9], int w
   return v ? (((uint32_t)w * wstride + (v - 1)) << 1) : MSM_INVALID;
 }
 
-static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, int c, int W, uint32_t B,
-                                  uint32_t wstride, uint32_t* __restrict__ codes, uint32_t* __restrict__ hist) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// scalars [i0, i1) of the n of this MSM (the host-scalar entry points upload and recode in chunks)
+static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, uint64_t i0, uint64_t i1, int c,
+                                         int W, uint32_t B, uint32_t wstride, uint32_t* __restrict__ codes,
+                                         uint32_t* __restrict__ hist) {
+  uint64_t i = i0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= i1) return;
   uint32_t s[9];
   msm_load_scalar(scalars, i, s);
   uint32_t carry = 0;
@@ -618,6 +621,8 @@ struct MsmEngine {
   using FC = typename CompactOf<F>::type;  // same layout, out-of-line products (small code)
   DevBuf codes, sorted, hist, offsets, cursor, tile_sums, buckets, lvlA[2], lvlE[2], result, flag;
   DevBuf ntask, task_base, len_bins, tasks, partials, heavy;
+  static constexpr int UPLOAD_CHUNKS = 4;
+  cudaEvent_t ev_chunk[UPLOAD_CHUNKS] = {};
   int reduce_L = 8;
   uint32_t wide_threshold = 1u << 17;  // items (all windows) above which a level is throughput bound
   uint32_t quad_threshold = 1u << 12;  // radix-2 outputs (all windows) below which a level is latency bound
@@ -662,8 +667,12 @@ struct MsmEngine {
   // histograms (block-local bins, then one block per bin) was built and measured in round 2: 417 us against
   // 289 us at 2^20 points -- it trades 27 M L2 atomics for 54 M shared-memory ones, which are no faster on
   // this part -- and was removed.
+  // host_scalars != nullptr: the scalars still sit in host memory; they are copied to `scalars` in UPLOAD_CHUNKS
+  // pieces on `copy_st` and each piece is recoded as soon as it has landed, so the recoding (and the histogram
+  // atomics, the slow part of it) runs under the rest of the upload instead of after it.
   int sort_entries(const uint32_t* scalars, uint64_t n, const MsmPlan& pl, uint32_t wstride, uint32_t pre_stride,
-                   uint32_t pre_offset, cudaStream_t st, StageTrace& tr) {
+                   uint32_t pre_offset, cudaStream_t st, StageTrace& tr, const uint8_t* host_scalars = nullptr,
+                   cudaStream_t copy_st = nullptr) {
     const uint64_t total = (uint64_t)pl.W * n;
     codes.reserve(total * 4);
     sorted.reserve(total * 4);
@@ -671,10 +680,31 @@ struct MsmEngine {
     offsets.reserve(((size_t)pl.nbuckets + 1) * 4);
     cursor.reserve(((size_t)pl.nbuckets + 1) * 4);
     CUDA_CHECK(cudaMemsetAsync(hist.p, 0, (size_t)pl.nbuckets * 4, st));
-    msm_digits_kernel<<<ceil_div(n, 256), 256, 0, st>>>(scalars, n, pl.c, pl.W, pl.B, wstride, codes.as<uint32_t>(),
-                                                       hist.as<uint32_t>());
-    CUDA_CHECK_LAUNCH();
-    int launches = 1 + scan_u32(hist.as<uint32_t>(), pl.nbuckets, offsets.as<uint32_t>(), st);
+    int launches = 0;
+    const int chunks = (host_scalars && n >= (1u << 16)) ? UPLOAD_CHUNKS : 1;
+    for (int k = 0; k < chunks; k++) {
+      const uint64_t i0 = n * k / chunks, i1 = n * (k + 1) / chunks;
+      if (host_scalars) {
+        cudaStream_t cs = chunks > 1 ? copy_st : st;
+        if (chunks > 1 && k == 0) {  // the copy lane starts behind everything already queued on the main one
+          if (!ev_chunk[0])
+            for (auto& e : ev_chunk) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          CUDA_CHECK(cudaEventRecord(ev_chunk[0], st));
+          CUDA_CHECK(cudaStreamWaitEvent(cs, ev_chunk[0], 0));
+        }
+        CUDA_CHECK(cudaMemcpyAsync(const_cast<uint32_t*>(scalars) + 8 * i0, host_scalars + 32 * i0, (i1 - i0) * 32,
+                                   cudaMemcpyHostToDevice, cs));
+        if (chunks > 1) {
+          CUDA_CHECK(cudaEventRecord(ev_chunk[k], cs));
+          CUDA_CHECK(cudaStreamWaitEvent(st, ev_chunk[k], 0));
+        }
+      }
+      msm_digits_kernel<<<ceil_div(i1 - i0, 256), 256, 0, st>>>(scalars, n, i0, i1, pl.c, pl.W, pl.B, wstride,
+                                                               codes.as<uint32_t>(), hist.as<uint32_t>());
+      CUDA_CHECK_LAUNCH();
+      launches++;
+    }
+    launches += scan_u32(hist.as<uint32_t>(), pl.nbuckets, offsets.as<uint32_t>(), st);
     tr.mark("digits+scan");
     CUDA_CHECK(cudaMemcpyAsync(cursor.p, offsets.p, ((size_t)pl.nbuckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
     msm_scatter_kernel<<<ceil_div(total, 256), 256, 0, st>>>(codes.as<uint32_t>(), total, n, cursor.as<uint32_t>(),
@@ -776,7 +806,8 @@ struct MsmEngine {
   // costs most of a block lifetime in under-filled waves (+0.1 ms per part at 2^20) while the exposed
   // reduction of the last part is still log2(buckets) dependent levels long.
   int run(const Affine<F>* pts, const uint32_t* scalars, uint64_t n, cudaStream_t st, bool want_xyzz = false,
-          int force_c = 0, uint32_t pre_stride = 0, uint32_t pre_offset = 0) {
+          int force_c = 0, uint32_t pre_stride = 0, uint32_t pre_offset = 0, const uint8_t* host_scalars = nullptr,
+          cudaStream_t copy_st = nullptr) {
     int launches = 0;
     result.reserve(sizeof(XYZZ<F>) + sizeof(Affine<F>));
     flag.reserve(sizeof(int));
@@ -801,7 +832,7 @@ struct MsmEngine {
     buckets.reserve((size_t)pl.nbuckets * sizeof(XYZZ<F>));
 
     StageTrace tr(st);
-    launches += sort_entries(scalars, n, pl, wstride, pre_stride, pre_offset, st, tr);
+    launches += sort_entries(scalars, n, pl, wstride, pre_stride, pre_offset, st, tr, host_scalars, copy_st);
     // the task count is data dependent: launch for the upper bound, threads past
     // task_base[nbuckets] exit at once (no host round trip in the middle of the pipeline)
     const uint32_t max_tasks = (uint32_t)(total / MSM_TASK_LEN) + pl.nbuckets + 1;

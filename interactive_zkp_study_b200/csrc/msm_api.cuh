@@ -142,13 +142,16 @@ struct GroupApi {
   }
 
   // plain table: the sub-range is just a pointer offset; precomputed table: stride/offset indexing
+  // host_scalars: the scalars are still in host memory and `dscalars` is where they go (uploaded in chunks on
+  // the second stream, recoded chunk by chunk on the first: slot 0 only)
   static int run_on_table(Context& c, Resource* t, uint64_t offset, const uint32_t* dscalars, uint64_t n, bool partial,
-                          int slot = 0) {
+                          int slot = 0, const uint8_t* host_scalars = nullptr) {
     cudaStream_t st = slot ? c.stream2 : c.stream;
     if (t->pre_c)
       return engine(slot).run(t->buf.as<Affine<F>>(), dscalars, n, st, partial, t->pre_c, (uint32_t)t->n,
-                              (uint32_t)offset);
-    return engine(slot).run(t->buf.as<Affine<F>>() + offset, dscalars, n, st, partial, msm_options().window_bits);
+                              (uint32_t)offset, host_scalars, c.stream2);
+    return engine(slot).run(t->buf.as<Affine<F>>() + offset, dscalars, n, st, partial, msm_options().window_bits, 0, 0,
+                            host_scalars, c.stream2);
   }
 
   // `count` independent MSMs on one table, alternating between two streams (each with its own
@@ -248,11 +251,8 @@ struct GroupApi {
       if (!out_xy || (n && !scalars)) throw InvalidArgument("msm_table: null argument");
       if (!range_ok(offset, n, t->n)) throw InvalidArgument("msm_table: point range exceeds the table");
       DevBuf& ds = scratch_scalars();
-      if (n) {
-        ds.reserve(n * 32);
-        CUDA_CHECK(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
-      }
-      c.launches += run_on_table(c, t, offset, ds.as<uint32_t>(), n, false);
+      if (n) ds.reserve(n * 32);
+      c.launches += run_on_table(c, t, offset, ds.as<uint32_t>(), n, false, 0, scalars);
       fetch_result(c, out_xy, out_is_inf);
     });
   }
@@ -317,11 +317,8 @@ struct GroupApi {
       if (!range_ok(offset, n, t->n)) throw InvalidArgument("msm_multi_table: point range exceeds the table");
       if (!comm_state().ready) throw InvalidArgument("msm_multi_table: zkp_comm_init has not been called on this rank");
       DevBuf& ds = scratch_scalars();
-      if (n) {
-        ds.reserve(n * 32);
-        CUDA_CHECK(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
-      }
-      c.launches += run_on_table(c, t, offset, ds.as<uint32_t>(), n, true);
+      if (n) ds.reserve(n * 32);
+      c.launches += run_on_table(c, t, offset, ds.as<uint32_t>(), n, true, 0, scalars);
       multi_tail(c, out_xy, out_is_inf);
     });
   }
