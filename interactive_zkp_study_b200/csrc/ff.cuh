@@ -582,6 +582,10 @@ template <class P>
 __device__ __noinline__ Mont256<P, false> mont_mul_outlined(Mont256<P, false> a, Mont256<P, false> b) {
   return Mont256<P, false>::mul_inline(a, b);
 }
+template <class P>
+__device__ __noinline__ Mont256<P, false> mont_sqr_outlined(Mont256<P, false> a) {
+  return Mont256<P, false>::sqr_inline(a);
+}
 
 using Fp = Mont256<FpParams>;
 using Fr = Mont256<FrParams>;

@@ -255,8 +255,9 @@ static constexpr uint32_t MSM_DIRECT = 0x80000000u;
 #ifndef MSM_ACC_MIN_BLOCKS_G2
 #define MSM_ACC_MIN_BLOCKS_G2 2
 #endif
-// 32-byte coordinates (G1): 104 registers, 4 blocks/SM (5 or 6 blocks measured no faster: the kernel is bound by the IMAD pipe, not by latency); 64-byte coordinates (G2)
-// need ~230 registers and stay at 2 blocks per SM.
+// 32-byte coordinates (G1): 122 registers, 4 blocks/SM (5 or 6 blocks, 96 / 80 registers with ~100 bytes of spills,
+// measured 1-2 % slower again in round 2: the kernel is bound by the IMAD pipe and its dependent carry chains, not by
+// occupancy); 64-byte coordinates (G2) need ~230 registers and stay at 2 blocks per SM.
 template <class F>
 struct AccMinBlocks {
   static constexpr int value = sizeof(F) == 32 ? MSM_ACC_MIN_BLOCKS : MSM_ACC_MIN_BLOCKS_G2;
@@ -334,7 +335,55 @@ static __global__ void msm_task_emit_kernel(const uint32_t* __restrict__ offsets
   }
 }
 
-template <class F>
+// The mixed addition of the accumulation loop with a chosen subset of its ten field products routed through the
+// shared out-of-line bodies (bit i of OUTLINE: product i; 2 and 5 are the squarings).  Ten inlined products are
+// 68 KB of loop body, more than the instruction cache keeps near the schedulers (ncu: no_instruction 1.1 stalls per
+// issue); a call costs a few register moves.  Same formulas and edge cases as XYZZ::madd (ec.cuh).
+template <int OUTLINE>
+struct AccMul {
+  template <int I>
+  static ZKP_DEVINL Fp mul(const Fp& a, const Fp& b) {
+    if constexpr ((OUTLINE >> I) & 1) return mont_mul_outlined<FpParams>(a, b);
+    else return Fp::mul_inline(a, b);
+  }
+  template <int I>
+  static ZKP_DEVINL Fp sqr(const Fp& a) {
+    if constexpr ((OUTLINE >> I) & 1) return mont_sqr_outlined<FpParams>(a);
+    else return Fp::sqr_inline(a);
+  }
+  static ZKP_DEVINL void madd(XYZZ<Fp>& a, const Affine<Fp>& p) {
+    if (p.is_inf()) return;
+    if (a.is_inf()) {
+      a.x = p.x; a.y = p.y; a.zz = Fp::one(); a.zzz = Fp::one();
+      return;
+    }
+    Fp u2 = mul<0>(p.x, a.zz);
+    Fp s2 = mul<1>(p.y, a.zzz);
+    Fp pp_ = u2 - a.x;
+    Fp r = s2 - a.y;
+    if (pp_.is_zero()) {
+      if (r.is_zero()) a = XYZZ<Fp>::dbl_affine(p);
+      else a = XYZZ<Fp>::inf();
+      return;
+    }
+    Fp pp = sqr<2>(pp_);
+    Fp ppp = mul<3>(pp_, pp);
+    Fp q = mul<4>(a.x, pp);
+    Fp x3 = sqr<5>(r) - ppp - q.dbl();
+    a.y = mul<6>(r, q - x3) - mul<7>(a.y, ppp);
+    a.x = x3;
+    a.zz = mul<8>(a.zz, pp);
+    a.zzz = mul<9>(a.zzz, ppp);
+  }
+};
+static constexpr int MSM_ACC_OUTLINE = 0x3DB;  // products 0, 1, 3, 4, 6-9 out of line; the squarings (2, 5) inlined
+template <class F, int OUTLINE>
+ZKP_DEVINL void acc_madd(XYZZ<F>& a, const Affine<F>& p) {
+  if constexpr (sizeof(F) == 32 && OUTLINE != 0) AccMul<OUTLINE>::madd(a, p);
+  else a.madd(p);
+}
+
+template <class F, int OUTLINE = 0>
 __global__ void __launch_bounds__(128, AccMinBlocks<F>::value) msm_accumulate_kernel(const Affine<F>* __restrict__ pts,
                                                               const uint32_t* __restrict__ sorted,
                                                               const uint4* __restrict__ tasks,
@@ -350,7 +399,7 @@ __global__ void __launch_bounds__(128, AccMinBlocks<F>::value) msm_accumulate_ke
     uint32_t e = sorted[k];
     Affine<F> p = pts[e & 0x7fffffffu];
     if (e >> 31) p.y = p.y.neg();
-    acc.madd(p);
+    acc_madd<F, OUTLINE>(acc, p);
   }
   if (task.w & MSM_DIRECT) buckets[task.w & ~MSM_DIRECT] = acc;
   else partials[task.w] = acc;
@@ -838,10 +887,11 @@ struct MsmEngine {
     const uint32_t max_tasks = (uint32_t)(total / MSM_TASK_LEN) + pl.nbuckets + 1;
     launches += build_tasks(pl.nbuckets, max_tasks, st);
     tr.mark("tasks");
-    // fully inlined field arithmetic here (an out-of-line-product build of this kernel measured 4 % slower)
-    msm_accumulate_kernel<F><<<ceil_div(max_tasks, 128), 128, 0, st>>>(pts, sorted.as<uint32_t>(), tasks.as<uint4>(),
-                                                                      task_base.as<uint32_t>() + pl.nbuckets,
-                                                                      partials.as<XYZZ<F>>(), buckets.as<XYZZ<F>>());
+    // G1: the eight products of the mixed addition through the shared out-of-line body, the two squarings inlined
+    // (measured at 2^20: 2.213 ms; everything inlined 2.248, everything out of line 2.241, other splits between)
+    msm_accumulate_kernel<F, MSM_ACC_OUTLINE><<<ceil_div(max_tasks, 128), 128, 0, st>>>(
+        pts, sorted.as<uint32_t>(), tasks.as<uint4>(), task_base.as<uint32_t>() + pl.nbuckets, partials.as<XYZZ<F>>(),
+        buckets.as<XYZZ<F>>());
     CUDA_CHECK_LAUNCH();
     launches++;
     tr.mark("accumulate");
