@@ -21,7 +21,7 @@ UNITS = ["capi_core.cu", "comm.cu", "diag.cu", "msm_g1.cu", "msm_g2.cu", "ntt.cu
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-diag-suppress", "128",
+    "-Xcompiler", "-fPIC", "-diag-suppress", "128,550",
     "-I", os.path.join(ROOT, "include"),
 ] + os.environ.get("ZKP_B200_NVCC_EXTRA", "").split()
 

@@ -219,6 +219,25 @@ __global__ void dbg_field_op_kernel(int op, const FE* a, const FE* b, uint64_t n
     case 2: r = x * y; break;
     case 3: r = x.inv(); break;
     case 5: r = x.inv_fermat(); break;
+    case 6: {  // the two-step product of the lazily reduced Fp2 arithmetic: 512-bit product, then one reduction
+      uint32_t t[16];
+      FE::mul_wide(x, y, t);
+      r = FE::redc_wide(t);
+      break;
+    }
+    default: r = x.sqr(); break;
+  }
+  out[i] = r.from_mont();
+}
+
+// Fp2 products / squarings / inverses of n pairs (64-byte elements c0 || c1, canonical)
+__global__ void dbg_fp2_op_kernel(int op, const Fp2* a, const Fp2* b, uint64_t n, Fp2* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp2 x = a[i].to_mont(), y = b ? b[i].to_mont() : Fp2::zero(), r;
+  switch (op) {
+    case 2: r = x * y; break;
+    case 3: r = x.inv(); break;
     default: r = x.sqr(); break;
   }
   out[i] = r.from_mont();
@@ -330,17 +349,21 @@ int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effecti
 
 int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out) {
   return guarded([&](Context& c) {
-    if (!a || !out || op < 0 || op > 5) throw InvalidArgument("zkp_dbg_field_op: bad argument");
+    if (!a || !out || op < 0 || op > 6) throw InvalidArgument("zkp_dbg_field_op: bad argument");
     if (n == 0) return;
+    if (field < 0 || field > 2) throw InvalidArgument("zkp_dbg_field_op: field must be 0 (Fp), 1 (Fr) or 2 (Fp2)");
+    const size_t sz = field == 2 ? 64 : 32;
     ScopedDevBuf da, db, dout;
-    da.reserve(n * 32);
-    dout.reserve(n * 32);
-    CUDA_CHECK(cudaMemcpyAsync(da.p, a, n * 32, cudaMemcpyHostToDevice, c.stream));
+    da.reserve(n * sz);
+    dout.reserve(n * sz);
+    CUDA_CHECK(cudaMemcpyAsync(da.p, a, n * sz, cudaMemcpyHostToDevice, c.stream));
     if (b) {
-      db.reserve(n * 32);
-      CUDA_CHECK(cudaMemcpyAsync(db.p, b, n * 32, cudaMemcpyHostToDevice, c.stream));
+      db.reserve(n * sz);
+      CUDA_CHECK(cudaMemcpyAsync(db.p, b, n * sz, cudaMemcpyHostToDevice, c.stream));
     }
-    if (field == 0)
+    if (field == 2)
+      dbg_fp2_op_kernel<<<ceil_div(n, 128), 128, 0, c.stream>>>(op, da.as<Fp2>(), b ? db.as<Fp2>() : nullptr, n, dout.as<Fp2>());
+    else if (field == 0)
       dbg_field_op_kernel<Fp><<<ceil_div(n, 128), 128, 0, c.stream>>>(op, da.as<Fp>(), b ? db.as<Fp>() : nullptr, n,
                                                                      dout.as<Fp>());
     else
@@ -348,7 +371,7 @@ int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint
                                                                      dout.as<Fr>());
     CUDA_CHECK_LAUNCH();
     c.launches++;
-    CUDA_CHECK(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaMemcpyAsync(out, dout.p, n * sz, cudaMemcpyDeviceToHost, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
   });
 }

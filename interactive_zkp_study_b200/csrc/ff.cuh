@@ -66,6 +66,22 @@ ZKP_DEVINL void mad_lanes_cin(uint32_t& x0, uint32_t left, uint32_t (&acc)[8], u
       : "r"(left), "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
 }
 
+// x0 += left; the carry ripples through acc (no product): the row opening of a pure reduction row
+ZKP_DEVINL void add_cin(uint32_t& x0, uint32_t left, uint32_t (&acc)[8]) {
+  asm("add.cc.u32   %8, %8, %9;\n\t"
+      "addc.cc.u32  %0, %0, 0;\n\t"
+      "addc.cc.u32  %1, %1, 0;\n\t"
+      "addc.cc.u32  %2, %2, 0;\n\t"
+      "addc.cc.u32  %3, %3, 0;\n\t"
+      "addc.cc.u32  %4, %4, 0;\n\t"
+      "addc.cc.u32  %5, %5, 0;\n\t"
+      "addc.cc.u32  %6, %6, 0;\n\t"
+      "addc.u32     %7, %7, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+        "+r"(x0)
+      : "r"(left));
+}
+
 // ---- partial chains for the dedicated squaring (sqr_inline): the same lane accumulators, but only lanes
 // K..3 receive a product (the lower multiplicand limbs of a squaring row are absent), generated text.
 template <int K>
@@ -383,6 +399,94 @@ struct __align__(16) Mont256 {
       O[6] = O[7] = 0;
     }
     // T = E + left + (O << 32), O[6] = O[7] = 0, T < 2*MOD
+    Mont256 r;
+    asm("add.cc.u32  %0, %8,  %16;\n\t"
+        "addc.cc.u32 %1, %9,  %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32    %7, %15, %23;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+          "=r"(r.v[7])
+        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(left),
+          "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
+    final_sub(r.v);
+    return r;
+  }
+
+  // ---- lazy reduction (Fp2 products, fp2.cuh): the 512-bit product and the Montgomery reduction as two steps, so
+  // that sums and differences of products are reduced ONCE.  mul_wide is the CIOS loop above without its
+  // reduction half (64 limb-MACs; the low limb of every row is final), for any a, b < 2^256.  redc_wide is the
+  // reduction half alone (72 limb-MACs): T < MOD * 2^256  ->  T / 2^256 mod MOD, fully reduced.  The upper limbs of
+  // T enter the sliding window one per row, in the slot the shift has just vacated.
+  static ZKP_DEVINL void mul_wide(const Mont256& a, const Mont256& b, uint32_t (&T)[16]) {
+    uint32_t E[8], O[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) E[i] = O[i] = 0;
+    uint32_t left = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      detail::mad_lanes_cin(E[0], left, O, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+      O[7] += detail::mad_lanes(E, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+      T[i] = E[0];
+      left = E[1];
+#pragma unroll
+      for (int k = 0; k < 6; k++) E[k] = E[k + 2];
+      E[6] = E[7] = 0;
+      detail::mad_lanes_cin(O[0], left, E, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
+      E[7] += detail::mad_lanes(O, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1]);
+      T[i + 1] = O[0];
+      left = O[1];
+#pragma unroll
+      for (int k = 0; k < 6; k++) O[k] = O[k + 2];
+      O[6] = O[7] = 0;
+    }
+    // upper half = E + left + (O << 32)
+    asm("add.cc.u32  %0, %8,  %16;\n\t"
+        "addc.cc.u32 %1, %9,  %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32    %7, %15, %23;"
+        : "=r"(T[8]), "=r"(T[9]), "=r"(T[10]), "=r"(T[11]), "=r"(T[12]), "=r"(T[13]), "=r"(T[14]), "=r"(T[15])
+        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(left),
+          "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
+  }
+
+  template <int I>
+  static ZKP_DEVINL void redc_row(uint32_t (&X)[8], uint32_t (&Y)[8], uint32_t& left, const uint32_t (&T)[16]) {
+    detail::add_cin(X[0], left, Y);
+    uint32_t q = X[0] * P::N0INV;
+    uint32_t cx = detail::mad_lanes(X, P::MOD_(0), P::MOD_(2), P::MOD_(4), P::MOD_(6), q);
+    uint32_t cy = detail::mad_lanes(Y, P::MOD_(1), P::MOD_(3), P::MOD_(5), P::MOD_(7), q);
+    (void)cy;
+    Y[7] += cx;
+    left = X[1];
+#pragma unroll
+    for (int k = 0; k < 6; k++) X[k] = X[k + 2];
+    X[6] = T[8 + I];  // limb 8 + I of T joins the window in the slot the shift vacated
+    X[7] = 0;
+  }
+  static ZKP_DEVINL Mont256 redc_wide(const uint32_t (&T)[16]) {
+    uint32_t E[8], O[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      E[i] = T[i];
+      O[i] = 0;
+    }
+    uint32_t left = 0;
+    redc_row<0>(E, O, left, T);
+    redc_row<1>(O, E, left, T);
+    redc_row<2>(E, O, left, T);
+    redc_row<3>(O, E, left, T);
+    redc_row<4>(E, O, left, T);
+    redc_row<5>(O, E, left, T);
+    redc_row<6>(E, O, left, T);
+    redc_row<7>(O, E, left, T);
     Mont256 r;
     asm("add.cc.u32  %0, %8,  %16;\n\t"
         "addc.cc.u32 %1, %9,  %17;\n\t"

@@ -485,7 +485,7 @@ def groth16_quotient(a_bytes, b_bytes, c_bytes, length, z_bytes, z_len):
 
 # ------------------------------------------------------------------ diagnostics (tests)
 def dbg_field_op(field, op, a_bytes, b_bytes, n):
-    out = bytearray(32 * n)
+    out = bytearray((64 if field == 2 else 32) * n)
     check(_lib.lib().zkp_dbg_field_op(field, op, buf(a_bytes), buf(b_bytes), n, buf(out)))
     return bytes(out)
 

@@ -44,10 +44,29 @@ def test_field_ops_bit_exact(native, field, mod):
     pa = [x * rinv % mod for x in pats]
     assert _unvec(native.dbg_field_op(field, 4, _vec(pa), None, len(pa))) == [(x * x) % mod for x in pa]
     assert _unvec(native.dbg_field_op(field, 2, _vec(pa), _vec(pa[::-1]), len(pa))) == [(x * y) % mod for x, y in zip(pa, pa[::-1])]
+    # the two-step form (512-bit product, then one Montgomery reduction) behind the lazily reduced Fp2 product
+    assert _unvec(native.dbg_field_op(field, 6, _vec(pa), _vec(pa[::-1]), len(pa))) == [(x * y) % mod for x, y in zip(pa, pa[::-1])]
+    assert _unvec(native.dbg_field_op(field, 6, _vec(a[:500]), _vec(b[:500]), 500)) == [(x * y) % mod for x, y in zip(a[:500], b[:500])]
     m = 300
     got = _unvec(native.dbg_field_op(field, 3, _vec(a[:m]), None, m))
     assert got == [bn254.inv(x, mod) for x in a[:m]]  # inv(0) == 0 as in py_ecc (binary extended Euclid)
     assert _unvec(native.dbg_field_op(field, 5, _vec(a[:m]), None, m)) == got  # Fermat chain agrees
+
+
+def test_fp2_ops_bit_exact(native):
+    """Fp2 product (Karatsuba on unreduced 512-bit products, one reduction per component), squaring, inverse."""
+    rng = random.Random(99)
+    edge = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, (1 << 253), (1 << 32) - 1]
+    xs = [(a, b) for a in edge for b in edge] + [(rng.randrange(P), rng.randrange(P)) for _ in range(3000)]
+    ys = [(b, a) for a, b in reversed(xs[:81])] + [(rng.randrange(P), rng.randrange(P)) for _ in range(3000)]
+    enc = lambda v: b"".join(int(c).to_bytes(32, "little") for pair in v for c in pair)
+    dec = lambda b: [(int.from_bytes(b[64 * i:64 * i + 32], "little"), int.from_bytes(b[64 * i + 32:64 * i + 64], "little"))
+                     for i in range(len(b) // 64)]
+    n = len(xs)
+    assert dec(native.dbg_field_op(2, 2, enc(xs), enc(ys), n)) == [bn254.f2_mul(x, y) for x, y in zip(xs, ys)]
+    assert dec(native.dbg_field_op(2, 4, enc(xs), None, n)) == [bn254.f2_mul(x, x) for x in xs]
+    inv = dec(native.dbg_field_op(2, 3, enc(xs[81:381]), None, 300))
+    assert all(bn254.f2_mul(x, y) == (1, 0) for x, y in zip(xs[81:381], inv))
 
 
 @pytest.mark.parametrize("quad", [0, 2])
