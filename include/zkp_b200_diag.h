@@ -33,6 +33,11 @@ int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint
 /* out[i] = a[i] + b[i] (group: 0 = G1, 1 = G2; 2 / 3 = the same through the quad-lane operations of
  * csrc/ec_quad.cuh) via XYZZ, result affine; exercises all edge cases */
 int zkp_dbg_point_add(int group, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
+/* Guarded allocation (start the process with ZKP_B200_GUARD=1): every device block of the library carries a
+ * 512-byte canary zone on both sides; this checks the zones of all live blocks (blocks are also checked when
+ * freed) and returns the number of live blocks and of blocks found damaged so far.  compute-sanitizer is closed
+ * on the B200 pool; tests/conftest.py turns a damaged canary into a failure of the GPU suite. */
+int zkp_debug_check_guards(uint64_t* live_buffers, uint64_t* violations);
 #ifdef __cplusplus
 }
 #endif

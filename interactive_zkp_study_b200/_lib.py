@@ -118,6 +118,7 @@ PROTOTYPES = {
     "zkp_pinned_free": (c_int, [vp]),
     "zkp_imad_peak": (c_int, [c_int, f64p, f64p]),
     "zkp_latency_probe": (c_int, [c_int, f64p]),
+    "zkp_debug_check_guards": (c_int, [u64p, u64p]),
     "zkp_dbg_field_op": (c_int, [c_int, c_int, vp, vp, u64, vp]),
     "zkp_dbg_point_add": (c_int, [c_int, vp, vp, u64, vp]),
 }

@@ -1,6 +1,7 @@
 // libzkp_b200: lifecycle, handles, timers, diagnostics.  See include/zkp_b200.h.
 #include <cstdlib>
 #include <cstring>
+#include <unordered_map>
 #include "ff.cuh"
 #include "registry.cuh"
 
@@ -21,6 +22,68 @@ static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 static StageProfile g_last_profile;
 int g_msm_profile_enabled = 0;
 StageProfile& last_msm_profile() { return g_last_profile; }
+
+// ------------------------------------------------------------------ guarded allocation (ZKP_B200_GUARD=1)
+static constexpr size_t GUARD_BYTES = 512;
+static constexpr unsigned char GUARD_FILL = 0xA5;
+static std::mutex g_guard_mu;
+static std::unordered_map<void*, size_t> g_guarded;  // user pointer -> user bytes
+static unsigned long long g_guard_violations = 0;
+
+static bool guard_mode() {
+  static const bool on = getenv("ZKP_B200_GUARD") && atoi(getenv("ZKP_B200_GUARD"));
+  return on;
+}
+
+// number of canary bytes around `user` that no longer hold the fill pattern (device synchronised first)
+static size_t guard_damage(void* user, size_t bytes) {
+  unsigned char host[2 * GUARD_BYTES];
+  char* base = static_cast<char*>(user) - GUARD_BYTES;
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(host, base, GUARD_BYTES, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+  if (cudaMemcpy(host + GUARD_BYTES, base + GUARD_BYTES + bytes, GUARD_BYTES, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+  size_t bad = 0;
+  for (size_t i = 0; i < 2 * GUARD_BYTES; i++) bad += host[i] != GUARD_FILL;
+  return bad;
+}
+
+void* dev_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (!guard_mode()) {
+    CUDA_CHECK(cudaMalloc(&p, bytes));
+    return p;
+  }
+  const size_t padded = (bytes + 15) & ~size_t(15);  // the trailing canary starts on a 16-byte boundary
+  CUDA_CHECK(cudaMalloc(&p, padded + 2 * GUARD_BYTES));
+  char* base = static_cast<char*>(p);
+  CUDA_CHECK(cudaMemset(base, GUARD_FILL, GUARD_BYTES));
+  CUDA_CHECK(cudaMemset(base + GUARD_BYTES + padded, GUARD_FILL, GUARD_BYTES));
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  g_guarded[base + GUARD_BYTES] = padded;
+  return base + GUARD_BYTES;
+}
+
+void dev_free(void* p) {
+  if (!p) return;
+  if (!guard_mode()) {
+    cudaFree(p);
+    return;
+  }
+  size_t bytes = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    auto it = g_guarded.find(p);
+    if (it == g_guarded.end()) return;  // not ours (or freed twice): leave it
+    bytes = it->second;
+    g_guarded.erase(it);
+  }
+  size_t bad = guard_damage(p, bytes);
+  if (bad) {
+    g_guard_violations++;
+    fprintf(stderr, "[zkp guard] %zu canary bytes overwritten around a %zu-byte device buffer\n", bad, bytes);
+  }
+  cudaFree(static_cast<char*>(p) - GUARD_BYTES);
+}
 
 // ------------------------------------------------------------------ device buffer pool
 static constexpr size_t POOL_MAX_BYTES = size_t(8) << 30;
@@ -195,6 +258,27 @@ int zkp_device_pci_bus_id(char* out, int cap) {
   return guarded([&](Context& c) {
     if (!out || cap < 16) throw InvalidArgument("zkp_device_pci_bus_id: need a buffer of at least 16 bytes");
     CUDA_CHECK(cudaDeviceGetPCIBusId(out, cap, c.device));
+  });
+}
+
+int zkp_debug_check_guards(uint64_t* live_buffers, uint64_t* violations) {
+  return guarded([&](Context&) {
+    if (!guard_mode()) throw InvalidArgument("zkp_debug_check_guards: start the process with ZKP_B200_GUARD=1");
+    std::vector<std::pair<void*, size_t>> live;
+    {
+      std::lock_guard<std::mutex> lk(g_guard_mu);
+      live.assign(g_guarded.begin(), g_guarded.end());
+    }
+    unsigned long long bad_buffers = 0;
+    for (auto& kv : live) {
+      size_t bad = guard_damage(kv.first, kv.second);
+      if (bad) {
+        bad_buffers++;
+        fprintf(stderr, "[zkp guard] %zu canary bytes overwritten around a live %zu-byte device buffer\n", bad, kv.second);
+      }
+    }
+    if (live_buffers) *live_buffers = live.size();
+    if (violations) *violations = g_guard_violations + bad_buffers;
   });
 }
 

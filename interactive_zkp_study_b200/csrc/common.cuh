@@ -28,22 +28,29 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 #define CUDA_CHECK(x) ::zkp::cuda_check((x), #x, __FILE__, __LINE__)
 #define CUDA_CHECK_LAUNCH() ::zkp::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
 
+// Every device allocation of the library goes through these two.  With ZKP_B200_GUARD=1 in the environment each
+// block gets a 512-byte canary zone on both sides (filled with 0xA5, checked when the block is freed and by
+// zkp_debug_check_guards): compute-sanitizer is closed on the B200 pool, so this is how an out-of-bounds WRITE
+// next to any workspace, table or scalar vector is caught (capi_core.cu).
+void* dev_alloc(size_t bytes);
+void dev_free(void* p);
+
 // A device buffer that only ever grows; reused across calls so steady-state calls allocate nothing.
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   void reserve(size_t bytes) {
     if (bytes <= cap) return;
-    if (p) CUDA_CHECK(cudaFree(p));
+    if (p) dev_free(p);
     p = nullptr;
     cap = 0;
-    CUDA_CHECK(cudaMalloc(&p, bytes));
+    p = dev_alloc(bytes);
     cap = bytes;
   }
   template <class T>
   T* as() const { return reinterpret_cast<T*>(p); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
     p = nullptr;
     cap = 0;
   }

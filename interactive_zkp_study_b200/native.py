@@ -484,6 +484,13 @@ def groth16_quotient(a_bytes, b_bytes, c_bytes, length, z_bytes, z_len):
 
 
 # ------------------------------------------------------------------ diagnostics (tests)
+def debug_check_guards():
+    """(live device blocks, blocks whose canaries were overwritten) -- needs ZKP_B200_GUARD=1 in the environment."""
+    live, bad = ctypes.c_uint64(), ctypes.c_uint64()
+    check(_lib.lib().zkp_debug_check_guards(ctypes.byref(live), ctypes.byref(bad)))
+    return live.value, bad.value
+
+
 def dbg_field_op(field, op, a_bytes, b_bytes, n):
     out = bytearray((64 if field == 2 else 32) * n)
     check(_lib.lib().zkp_dbg_field_op(field, op, buf(a_bytes), buf(b_bytes), n, buf(out)))
