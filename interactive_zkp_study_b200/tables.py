@@ -1,41 +1,69 @@
 """Device-resident copies of the static point tables the reference re-passes on every call
 (``srs.g1_powers``, ``sigma1_2``, ``sigma1_5``, ``sigma2_2``; SURVEY.md 8b "Ownership").
 
-Cached by object identity, guarded by a content fingerprint (length + sampled points) so that a
-recycled ``id()`` or an in-place edit can never serve stale points.
+Cached per list OBJECT.  An entry keeps a reference to the list (so its ``id()`` cannot be recycled by another
+list while the entry lives) and to every element it uploaded.  A hit requires
+  * the same list object with the same length,
+  * every element to be the very object that was uploaded (an in-place ``points[i] = other`` is seen at any
+    index -- tamper tests do exactly that), and
+  * for lists of up to ``_FULL_CHECK_MAX`` points, the full encoded content to be byte-identical with what was
+    uploaded (this also catches a coordinate object mutated in place, e.g. ``points[i][0].n = ...``); longer
+    lists are checked by element identity plus a sample of encoded points.
+Anything else re-uploads the table.
 """
 from collections import OrderedDict
 
 from . import native
 
 _MAX_ENTRIES = 32
+_FULL_CHECK_MAX = 4096
 _cache = OrderedDict()
 
 
-def _fingerprint(points, g2):
+class _Entry:
+    __slots__ = ("points", "elements", "content", "handle")
+
+    def __init__(self, points, elements, content, handle):
+        self.points, self.elements, self.content, self.handle = points, elements, content, handle
+
+
+def _content(points, g2):
+    """What is compared on a hit: every encoded point for short lists, a sample for long ones."""
     n = len(points)
-    idx = sorted(set([0, 1, n // 3, n // 2, (2 * n) // 3, n - 2, n - 1]) & set(range(n)))
     enc = native.g2_bytes if g2 else native.g1_bytes
-    return (n, tuple(enc(points[i]) for i in idx))
+    if n <= _FULL_CHECK_MAX:
+        return b"".join(enc(p) for p in points)
+    idx = sorted(set([0, 1, n // 3, n // 2, (2 * n) // 3, n - 2, n - 1]))
+    return b"".join(enc(points[i]) for i in idx)
+
+
+def _valid(entry, points, g2):
+    if entry.points is not points or len(points) != len(entry.elements):
+        return False
+    for a, b in zip(points, entry.elements):
+        if a is not b:
+            return False
+    return _content(points, g2) == entry.content
 
 
 def _get(points, g2):
     key = (id(points), bool(g2))
-    fp = _fingerprint(points, g2)
     hit = _cache.get(key)
-    if hit is not None and hit[0] == fp:
+    if hit is not None and _valid(hit, points, g2):
         _cache.move_to_end(key)
-        return hit[1]
+        return hit.handle
+    if hit is not None:
+        _cache.pop(key).handle.free()
     n = len(points)
     if g2:
         handle = native.g2_table_load(native.g2_vec_bytes(points), n)
     else:
         handle = native.g1_table_load(native.g1_vec_bytes(points), n)
     _maybe_precompute(handle, n)
-    _cache[key] = (fp, handle)
+    _cache[key] = _Entry(points, tuple(points), _content(points, g2), handle)
     while len(_cache) > _MAX_ENTRIES:
-        _, (_, old) = _cache.popitem(last=False)
-        old.free()
+        _, old = _cache.popitem(last=False)
+        old.handle.free()
     return handle
 
 
@@ -60,11 +88,11 @@ def g2_table(points):
 
 def clear():
     while _cache:
-        _, (_, h) = _cache.popitem()
-        h.free()
+        _, entry = _cache.popitem()
+        entry.handle.free()
 
 
 def adopt_g1(points, handle):
     """Register an already device-resident table (e.g. fresh from SRS.generate) for `points`."""
     _maybe_precompute(handle, len(points))
-    _cache[(id(points), False)] = (_fingerprint(points, False), handle)
+    _cache[(id(points), False)] = _Entry(points, tuple(points), _content(points, False), handle)

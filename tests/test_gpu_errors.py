@@ -68,3 +68,20 @@ def test_table_cache_follows_list_contents(native):
     want2 = bn254.g1_msm([(int(q[0]), int(q[1])) for q in srs.g1_powers], [5, 6, 7, 8])
     got2 = commit(p, srs)
     assert (int(got2[0]), int(got2[1])) == want2 != want
+    # a longer table edited at an index no sampling scheme would look at, then a coordinate mutated in place
+    pts = [g1_from_ints(bn254.g1_add(bn254.g1_mul(bn254.G1, 77), bn254.g1_mul(bn254.G1, k))) for k in range(1, 41)]
+    srs = SRS(pts, [None, None], 39)
+    coeffs = list(range(3, 43))
+    ref = lambda: bn254.g1_msm([(int(q[0]), int(q[1])) for q in srs.g1_powers], coeffs)
+    big = Polynomial(coeffs)
+    first = commit(big, srs)
+    assert (int(first[0]), int(first[1])) == ref()
+    srs.g1_powers[5] = g1_from_ints(bn254.g1_mul(bn254.G1, 123456))
+    second = commit(big, srs)
+    assert (int(second[0]), int(second[1])) == ref() != (int(first[0]), int(first[1]))
+    other = bn254.g1_mul(bn254.G1, 424242)
+    srs.g1_powers[17][0].n, srs.g1_powers[17][1].n = other       # same objects, new coordinates
+    third = commit(big, srs)
+    assert (int(third[0]), int(third[1])) == ref() != (int(second[0]), int(second[1]))
+    # a same-length list that reuses the id() of a dead one cannot hit: entries hold their list alive
+    assert all(e.points is not None for e in tables._cache.values())
