@@ -131,6 +131,14 @@ int zkp_g1_msm_multi_table(uint64_t table, uint64_t offset, const uint8_t* scala
                            int* out_is_inf);
 int zkp_g2_msm_multi(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n,
                      uint8_t out_xy[128], int* out_is_inf);
+/* Split form on the library's second stream: begin enqueues the same local MSM -> all-gather -> fold and returns at
+ * once, end waits for it and fetches the point; whatever is called in between runs beside it.  A Groth16 prover
+ * starts its A and B elements this way before the quotient they do not depend on (proving.py:23-45 need only
+ * R.Ax / R.Bx; hxr, poly_utils.py:116-125, feeds proof_c alone).  One pending call per group; collective. */
+int zkp_g1_msm_multi_begin(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n);
+int zkp_g1_msm_multi_end(uint8_t out_xy[64], int* out_is_inf);
+int zkp_g2_msm_multi_begin(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n);
+int zkp_g2_msm_multi_end(uint8_t out_xy[128], int* out_is_inf);
 
 /* ---- fixed-base batch scalar multiplication (CRS generation) -------------------
  * out[i] = scalars[i] * base.  Replaces SRS.generate (zkp/plonk/srs.py:78-82) and

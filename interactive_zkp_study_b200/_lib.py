@@ -68,6 +68,10 @@ PROTOTYPES = {
     "zkp_g1_msm_multi": (c_int, [u64, u64, u64, u64, u64, vp, intp]),
     "zkp_g1_msm_multi_table": (c_int, [u64, u64, vp, u64, vp, intp]),
     "zkp_g2_msm_multi": (c_int, [u64, u64, u64, u64, u64, vp, intp]),
+    "zkp_g1_msm_multi_begin": (c_int, [u64, u64, u64, u64, u64]),
+    "zkp_g1_msm_multi_end": (c_int, [vp, intp]),
+    "zkp_g2_msm_multi_begin": (c_int, [u64, u64, u64, u64, u64]),
+    "zkp_g2_msm_multi_end": (c_int, [vp, intp]),
     "zkp_fr_dot_dev": (c_int, [u64, u64, u64, u64, u64, vp]),
     "zkp_g1_fixed_base_mul": (c_int, [vp, vp, u64, u64p]),
     "zkp_g2_fixed_base_mul": (c_int, [vp, vp, u64, u64p]),

@@ -23,6 +23,7 @@ struct NcclApi {
 
 NcclApi g_nccl;
 ncclComm_t g_comm = nullptr;
+cudaEvent_t g_ev_last = nullptr;  // completion of the communicator's most recent collective (on whatever stream)
 CommState g_state;
 DevBuf g_barrier_word;
 
@@ -61,7 +62,10 @@ CommState& comm_state() { return g_state; }
 
 void comm_all_gather(const void* send, void* recv, size_t bytes, cudaStream_t st) {
   if (!g_state.ready) throw InvalidArgument("multi-GPU MSM: zkp_comm_init has not been called on this rank");
+  if (!g_ev_last) CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_last, cudaEventDisableTiming));
+  else CUDA_CHECK(cudaStreamWaitEvent(st, g_ev_last, 0));
   nccl_check(g_nccl.AllGather(send, recv, bytes, ncclUint8, g_comm, st), "ncclAllGather");
+  CUDA_CHECK(cudaEventRecord(g_ev_last, st));
 }
 
 }  // namespace zkp
@@ -93,7 +97,7 @@ int zkp_comm_init(int rank, int world, const uint8_t id[ZKP_COMM_ID_BYTES]) {
     nccl_check(g_nccl.CommInitRank(&g_comm, world, uid, rank), "ncclCommInitRank");
     g_state.rank = rank;
     g_state.world = world;
-    g_state.gathered.reserve((size_t)world * 256);
+    for (DevBuf& b : g_state.gathered) b.reserve((size_t)world * 256);
     g_barrier_word.reserve(64);
     CUDA_CHECK(cudaMemsetAsync(g_barrier_word.p, 0, 64, c.stream));
     g_state.ready = true;
@@ -112,6 +116,7 @@ int zkp_comm_info(int* rank, int* world, int* nccl_version) {
 int zkp_comm_barrier(void) {
   return guarded([&](Context& c) {
     if (!g_state.ready) throw InvalidArgument("zkp_comm_barrier: no communicator");
+    if (g_ev_last) CUDA_CHECK(cudaStreamWaitEvent(c.stream, g_ev_last, 0));
     nccl_check(g_nccl.AllReduce(g_barrier_word.p, g_barrier_word.p, 1, ncclUint32, ncclSum, g_comm, c.stream), "ncclAllReduce");
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
   });
@@ -121,6 +126,7 @@ int zkp_comm_destroy(void) {
   return guarded([&](Context& c) {
     if (!g_state.ready) return;
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream2));
     g_state.ready = false;
     nccl_check(g_nccl.CommDestroy(g_comm), "ncclCommDestroy");
     g_comm = nullptr;

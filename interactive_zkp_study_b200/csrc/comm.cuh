@@ -15,13 +15,14 @@ struct CommState {
   bool ready = false;
   int rank = 0, world = 1;
   int nccl_version = 0;
-  DevBuf gathered;  // world x (largest partial) bytes: receive buffer of the all-gather
+  DevBuf gathered[2];  // world x (largest partial) bytes: receive buffer of the all-gather, one per stream lane
 };
 
 CommState& comm_state();
 // Enqueues the all-gather of `bytes` bytes per rank (send -> recv[rank * bytes]) on `st`.  world == 1
 // degenerates to a device-to-device copy through the same NCCL call path.  Throws if zkp_comm_init has
-// not succeeded.
+// not succeeded.  Collectives of the one communicator are chained by an event whatever stream they are
+// enqueued on, so two lanes never have two of them in flight at once (every rank issues them in the same order).
 void comm_all_gather(const void* send, void* recv, size_t bytes, cudaStream_t st);
 
 }  // namespace zkp

@@ -281,18 +281,53 @@ struct GroupApi {
   // Sharded MSM, one rank's call: local Pippenger over this rank's point range -> XYZZ partial
   // -> all-gather of one partial per rank -> fold + affine, all enqueued on the library stream back to
   // back; the host only waits for the final 64 / 128 bytes.  Every rank returns the full result.
-  static void multi_tail(Context& c, uint8_t* out_xy, int* out_is_inf) {
-    MsmEngine<F>& e = engine();
+  static void multi_enqueue_tail(Context& c, int slot) {
+    MsmEngine<F>& e = engine(slot);
+    cudaStream_t st = slot ? c.stream2 : c.stream;
     CommState& cs = comm_state();
     const size_t PB = sizeof(XYZZ<F>);
-    cs.gathered.reserve((size_t)cs.world * PB);
-    comm_all_gather(e.result.template as<char>() + PT, cs.gathered.p, PB, c.stream);
+    DevBuf& gathered = cs.gathered[slot];
+    gathered.reserve((size_t)cs.world * PB);
+    comm_all_gather(e.result.template as<char>() + PT, gathered.p, PB, st);
     using FC = typename CompactOf<F>::type;
-    combine_partials_kernel<FC><<<1, 32, 0, c.stream>>>(cs.gathered.template as<XYZZ<FC>>(), (uint32_t)cs.world,
-                                                      e.result.template as<Affine<FC>>(), e.flag.template as<int>());
+    combine_partials_kernel<FC><<<1, 32, 0, st>>>(gathered.template as<XYZZ<FC>>(), (uint32_t)cs.world,
+                                                 e.result.template as<Affine<FC>>(), e.flag.template as<int>());
     CUDA_CHECK_LAUNCH();
     c.launches++;
+  }
+  static void multi_tail(Context& c, uint8_t* out_xy, int* out_is_inf) {
+    multi_enqueue_tail(c, 0);
     fetch_result(c, out_xy, out_is_inf);
+  }
+
+  // The same collective on the second lane without waiting for it: begin enqueues local MSM -> all-gather -> fold
+  // on the second stream (behind everything already queued on the first) and returns; end fetches the point.
+  // What the caller enqueues on the first stream in between -- the quotient of a Groth16 proof, which the A and
+  // B elements do not depend on -- runs beside it.  One pending call per group.
+  static int msm_multi_begin(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n) {
+    return guarded([&](Context& c) {
+      Resource* t = need(table, KIND, "msm_multi_begin");
+      Resource* s = need(scalars, HandleKind::Scalars, "msm_multi_begin");
+      if (!range_ok(offset, n, t->n) || !range_ok(sc_offset, n, s->n)) throw InvalidArgument("msm_multi_begin: range out of bounds");
+      if (!comm_state().ready) throw InvalidArgument("msm_multi_begin: zkp_comm_init has not been called on this rank");
+      CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
+      CUDA_CHECK(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
+      c.launches += run_on_table(c, t, offset, s->buf.as<uint32_t>() + 8 * sc_offset, n, true, 1);
+      multi_enqueue_tail(c, 1);
+    });
+  }
+  static int msm_multi_end(uint8_t* out_xy, int* out_is_inf) {
+    return guarded([&](Context& c) {
+      if (!out_xy) throw InvalidArgument("msm_multi_end: null output");
+      MsmEngine<F>& e = engine(1);
+      if (!e.result.p) throw InvalidArgument("msm_multi_end: no msm_multi_begin is pending");
+      int flag = 0;
+      CUDA_CHECK(cudaMemcpyAsync(out_xy, e.result.p, PT, cudaMemcpyDeviceToHost, c.stream2));
+      CUDA_CHECK(cudaMemcpyAsync(&flag, e.flag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream2));
+      CUDA_CHECK(cudaStreamSynchronize(c.stream2));
+      if (flag) memset(out_xy, 0, PT);
+      if (out_is_inf) *out_is_inf = flag;
+    });
   }
 
   static int msm_multi(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n, uint8_t* out_xy,

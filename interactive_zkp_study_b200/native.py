@@ -418,6 +418,20 @@ def g2_msm_multi(table, offset, scalars, sc_offset, n):
     return g2_from_bytes(bytes(out), bool(inf.value))
 
 
+def msm_multi_begin(table, offset, scalars, sc_offset, n):
+    """Collective, asynchronous: starts this rank's shard of a sharded MSM (G1 or G2 by the table's kind) on the
+    library's second stream; msm_multi_end(kind) fetches the point."""
+    fn = _lib.lib().zkp_g1_msm_multi_begin if table.kind == "g1" else _lib.lib().zkp_g2_msm_multi_begin
+    check(fn(table.handle, offset, scalars.handle, sc_offset, n))
+
+
+def msm_multi_end(kind):
+    out, inf = _msm_out(1 if kind == "g1" else 2)
+    fn = _lib.lib().zkp_g1_msm_multi_end if kind == "g1" else _lib.lib().zkp_g2_msm_multi_end
+    check(fn(buf(out), ctypes.byref(inf)))
+    return g1_from_bytes(bytes(out), bool(inf.value)) if kind == "g1" else g2_from_bytes(bytes(out), bool(inf.value))
+
+
 def g1_combine_partials(partials_bytes, count):
     out, inf = _msm_out(1)
     check(_lib.lib().zkp_g1_combine_partials(buf(partials_bytes), count, buf(out), ctypes.byref(inf)))

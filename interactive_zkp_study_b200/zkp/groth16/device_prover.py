@@ -49,9 +49,9 @@ def setup_from_toxic(k, alpha, beta, delta, x_val, zx_val, priv_vals, precompute
     return DeviceKey(k, m_priv, TA, TB2, TC)
 
 
-def _proof_scalars(key, uA, uB, hq, rx_priv, r, s):
-    """The three MSM scalar vectors of one proof, assembled on the device (see the table layout above)."""
-    k, mp = key.k, key.m_priv
+def _scalars_ab(key, uA, uB, r, s):
+    """Scalar vectors of the A and B elements (they need only uA, uB): uA | 1 | r and uB | 1 | s."""
+    k = key.k
     one = native.fr_vec_bytes([1])
     scA = native.scalars_alloc(k + 2)
     native.scalars_copy(scA, 0, uA, 0, k)
@@ -59,6 +59,12 @@ def _proof_scalars(key, uA, uB, hq, rx_priv, r, s):
     scB = native.scalars_alloc(k + 2)
     native.scalars_copy(scB, 0, uB, 0, k)
     native.scalars_upload(scB, k, one + native.fe_bytes(s), 2)
+    return scA, scB
+
+
+def _scalars_c(key, uB, hq, rx_priv, r):
+    """Scalar vector of the X part of C: r*uB | r | Rx_priv | H  (see the table layout above)."""
+    k, mp = key.k, key.m_priv
     nC = k + 1 + mp + (k - 1)
     scC = native.scalars_alloc(nC)
     native.scalars_copy(scC, 0, uB, 0, k)
@@ -68,6 +74,13 @@ def _proof_scalars(key, uA, uB, hq, rx_priv, r, s):
         native.scalars_copy(scC, k + 1, rx_priv, 0, mp)
     if k > 1:
         native.scalars_copy(scC, k + 1 + mp, hq, 0, k - 1)
+    return scC, nC
+
+
+def _proof_scalars(key, uA, uB, hq, rx_priv, r, s):
+    """The three MSM scalar vectors of one proof, assembled on the device."""
+    scA, scB = _scalars_ab(key, uA, uB, r, s)
+    scC, nC = _scalars_c(key, uB, hq, rx_priv, r)
     return scA, scB, scC, nC
 
 
@@ -132,14 +145,19 @@ def prove_sharded(comm, key, uA, uB, uC, Z, rx_priv, r, s):
     (zkp_g1_msm_multi / zkp_g2_msm_multi: local Pippenger -> one all-gather of the partial sums -> fold, inside
     the library).  Collective: every rank passes the same coefficient vectors and gets the same proof.  The
     quotient -- NTT work, which stays on one GPU -- is computed by every rank for itself: that
-    costs no wall time and needs no 32 MiB broadcast of H."""
+    costs no wall time and needs no 32 MiB broadcast of H; the A and B collectives run beside it on the second
+    stream (zkp_g1/g2_msm_multi_begin / _end)."""
     k = key.k
     r, s = int(r) % R, int(s) % R
+    # A and B need only uA, uB: their collectives start on the library's second stream and run beside the quotient
+    scA, scB = _scalars_ab(key, uA, uB, r, s)
+    native.msm_multi_begin(key.TA, 0, scA, key.rA[0], key.rA[1])
+    native.msm_multi_begin(key.TB2, 0, scB, key.rB[0], key.rB[1])
     hq, _ = native.groth16_quotient_dev(uA, uB, uC, k, Z, k + 1, want_remainder=False)
-    scA, scB, scC, _ = _proof_scalars(key, uA, uB, hq, rx_priv, r, s)
-    A = native.g1_msm_multi(key.TA, 0, scA, key.rA[0], key.rA[1])
-    B = native.g2_msm_multi(key.TB2, 0, scB, key.rB[0], key.rB[1])
+    scC, _ = _scalars_c(key, uB, hq, rx_priv, r)
     X = native.g1_msm_multi(key.TC, 0, scC, key.rC[0], key.rC[1])
+    A = native.msm_multi_end("g1")
+    B = native.msm_multi_end("g2")
     C = native.g1_msm(native.g1_bytes(A) + native.g1_bytes(X), native.fe_bytes(s) + native.fr_vec_bytes([1]), 2)
     for h in (scA, scB, scC, hq):
         h.free()
