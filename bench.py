@@ -367,7 +367,7 @@ def groth16_record(log_k, peak_tmacs, comm=None):
                        "frac": ach / (peak_tmacs * res["n_gpus"]),
                        "algorithmic_macs": macs,
                        "algorithmic_note": "SURVEY 8d model: 4 G1 MSMs + 1 G2 MSM (x3) of 2^%d points at 23 664 MAC/pt + 1e10 for the quotient; "
-                                           "the prover here folds them into 2 G1 MSMs (k+2 and 3k-2 points) + 1 G2 MSM" % log_k}
+                                           "the prover here folds them into 2 G1 MSMs (k+2 and 3k points) + 1 G2 MSM started before the quotient" % log_k}
     return res
 
 

@@ -88,6 +88,14 @@ int zkp_g1_msm_dev(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t s
                    uint8_t out_xy[64], int* out_is_inf);
 int zkp_g2_msm_dev(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n,
                    uint8_t out_xy[128], int* out_is_inf);
+/* Split form of zkp_g1/g2_msm_dev on the library's second stream: begin enqueues the MSM behind everything already
+ * queued and returns at once, end waits for it and fetches the point; the calls made in between run beside it
+ * (device_prover.prove starts the G2 element B this way before the quotient, which B does not depend on:
+ * proving.py:35-45 needs only R.Bx).  One pending call per group. */
+int zkp_g1_msm_dev_begin(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n);
+int zkp_g1_msm_dev_end(uint8_t out_xy[64], int* out_is_inf);
+int zkp_g2_msm_dev_begin(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n);
+int zkp_g2_msm_dev_end(uint8_t out_xy[128], int* out_is_inf);
 /* `count` independent MSMs on one table in one call: MSM k uses points [offsets[k], +lens[k]) and scalars
  * [sc_offsets[k], +lens[k]) of handle scalars[k]; out_xy holds count x 64 bytes.  The MSMs alternate between
  * two streams so the latency-bound tail of one overlaps the accumulation of the next (a prover issues its

@@ -68,6 +68,10 @@ PROTOTYPES = {
     "zkp_g1_msm_multi": (c_int, [u64, u64, u64, u64, u64, vp, intp]),
     "zkp_g1_msm_multi_table": (c_int, [u64, u64, vp, u64, vp, intp]),
     "zkp_g2_msm_multi": (c_int, [u64, u64, u64, u64, u64, vp, intp]),
+    "zkp_g1_msm_dev_begin": (c_int, [u64, u64, u64, u64, u64]),
+    "zkp_g1_msm_dev_end": (c_int, [vp, intp]),
+    "zkp_g2_msm_dev_begin": (c_int, [u64, u64, u64, u64, u64]),
+    "zkp_g2_msm_dev_end": (c_int, [vp, intp]),
     "zkp_g1_msm_multi_begin": (c_int, [u64, u64, u64, u64, u64]),
     "zkp_g1_msm_multi_end": (c_int, [vp, intp]),
     "zkp_g2_msm_multi_begin": (c_int, [u64, u64, u64, u64, u64]),

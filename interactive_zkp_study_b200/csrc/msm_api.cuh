@@ -304,23 +304,26 @@ struct GroupApi {
   // on the second stream (behind everything already queued on the first) and returns; end fetches the point.
   // What the caller enqueues on the first stream in between -- the quotient of a Groth16 proof, which the A and
   // B elements do not depend on -- runs beside it.  One pending call per group.
-  static int msm_multi_begin(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n) {
+  static int msm_begin(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n, bool multi) {
     return guarded([&](Context& c) {
-      Resource* t = need(table, KIND, "msm_multi_begin");
-      Resource* s = need(scalars, HandleKind::Scalars, "msm_multi_begin");
-      if (!range_ok(offset, n, t->n) || !range_ok(sc_offset, n, s->n)) throw InvalidArgument("msm_multi_begin: range out of bounds");
-      if (!comm_state().ready) throw InvalidArgument("msm_multi_begin: zkp_comm_init has not been called on this rank");
+      Resource* t = need(table, KIND, "msm_begin");
+      Resource* s = need(scalars, HandleKind::Scalars, "msm_begin");
+      if (!range_ok(offset, n, t->n) || !range_ok(sc_offset, n, s->n)) throw InvalidArgument("msm_begin: range out of bounds");
+      if (multi && !comm_state().ready) throw InvalidArgument("msm_multi_begin: zkp_comm_init has not been called on this rank");
       CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
       CUDA_CHECK(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
-      c.launches += run_on_table(c, t, offset, s->buf.as<uint32_t>() + 8 * sc_offset, n, true, 1);
-      multi_enqueue_tail(c, 1);
+      c.launches += run_on_table(c, t, offset, s->buf.as<uint32_t>() + 8 * sc_offset, n, multi, 1);
+      if (multi) multi_enqueue_tail(c, 1);
     });
+  }
+  static int msm_multi_begin(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n) {
+    return msm_begin(table, offset, scalars, sc_offset, n, true);
   }
   static int msm_multi_end(uint8_t* out_xy, int* out_is_inf) {
     return guarded([&](Context& c) {
       if (!out_xy) throw InvalidArgument("msm_multi_end: null output");
       MsmEngine<F>& e = engine(1);
-      if (!e.result.p) throw InvalidArgument("msm_multi_end: no msm_multi_begin is pending");
+      if (!e.result.p) throw InvalidArgument("msm_end: no begin call is pending");
       int flag = 0;
       CUDA_CHECK(cudaMemcpyAsync(out_xy, e.result.p, PT, cudaMemcpyDeviceToHost, c.stream2));
       CUDA_CHECK(cudaMemcpyAsync(&flag, e.flag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream2));

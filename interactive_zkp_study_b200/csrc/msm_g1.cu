@@ -33,6 +33,10 @@ int zkp_g1_msm_multi(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t
                      uint8_t out_xy[64], int* out_is_inf) {
   return Api::msm_multi(table, offset, scalars, sc_offset, n, out_xy, out_is_inf);
 }
+int zkp_g1_msm_dev_begin(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n) {
+  return Api::msm_begin(table, offset, scalars, sc_offset, n, false);
+}
+int zkp_g1_msm_dev_end(uint8_t out_xy[64], int* out_is_inf) { return Api::msm_multi_end(out_xy, out_is_inf); }
 int zkp_g1_msm_multi_begin(uint64_t table, uint64_t offset, uint64_t scalars, uint64_t sc_offset, uint64_t n) {
   return Api::msm_multi_begin(table, offset, scalars, sc_offset, n);
 }

@@ -418,6 +418,20 @@ def g2_msm_multi(table, offset, scalars, sc_offset, n):
     return g2_from_bytes(bytes(out), bool(inf.value))
 
 
+def msm_dev_begin(table, offset, scalars, sc_offset, n):
+    """Asynchronous msm_dev on the library's second stream (G1 or G2 by the table's kind); msm_dev_end(kind)
+    fetches the point.  What is called in between runs beside it."""
+    fn = _lib.lib().zkp_g1_msm_dev_begin if table.kind == "g1" else _lib.lib().zkp_g2_msm_dev_begin
+    check(fn(table.handle, offset, scalars.handle, sc_offset, n))
+
+
+def msm_dev_end(kind):
+    out, inf = _msm_out(1 if kind == "g1" else 2)
+    fn = _lib.lib().zkp_g1_msm_dev_end if kind == "g1" else _lib.lib().zkp_g2_msm_dev_end
+    check(fn(buf(out), ctypes.byref(inf)))
+    return g1_from_bytes(bytes(out), bool(inf.value)) if kind == "g1" else g2_from_bytes(bytes(out), bool(inf.value))
+
+
 def msm_multi_begin(table, offset, scalars, sc_offset, n):
     """Collective, asynchronous: starts this rank's shard of a sharded MSM (G1 or G2 by the table's kind) on the
     library's second stream; msm_multi_end(kind) fetches the point."""

@@ -10,9 +10,13 @@ ONE multi-scalar multiplication:
 
     TA  (G1) = [x^j]_1 (j < k) | alpha_1 | delta_1                  scalars  uA | 1 | r            -> A
     TB2 (G2) = [x^j]_2 (j < k) | beta_2  | delta_2                  scalars  uB | 1 | s            -> B
-    TC  (G1) = [x^j]_1 (j < k) | beta_1 | sigma1_4[private] | sigma1_5 (k-1)
-                                                                     scalars  r*uB | r | Rx_priv | H -> X
-    C = s*A + X        (the s*r*delta terms of proving.py:64 cancel)
+    TC  (G1) = [x^j]_1 (j < k) | beta_1 | sigma1_4[private] | sigma1_5 (k-1) | alpha_1 | delta_1
+                                                       scalars  r*uB + s*uA | r | Rx_priv | H | s | s*r -> C
+
+C = s*A + r*B1 - s*r*delta_1 + (wires) + (H) of proving.py:64-73 with A and B1 expanded over the SAME points [x^j]_1:
+the s*A term becomes s*uA on the first k rows plus s*alpha_1 + s*r*delta_1, the -s*r*delta_1 cancels against
+r*B1's s*r*delta_1, so C needs neither A's value nor a scalar multiplication -- the three elements are three
+independent multi-scalar multiplications, and B (G2, the longest) starts before the quotient it does not need.
 """
 from ... import native
 from ...compat import G1, G2, curve_order, g1_from_ints, g2_from_ints
@@ -23,6 +27,11 @@ R = curve_order
 class DeviceKey:
     def __init__(self, k, m_priv, TA, TB2, TC):
         self.k, self.m_priv, self.TA, self.TB2, self.TC = k, m_priv, TA, TB2, TC
+
+
+def tc_rows(k, m_priv):
+    """Rows of the C table: [x^j]_1 (k) | beta_1 | sigma1_4[private] (m_priv) | sigma1_5 (k-1) | alpha_1 | delta_1."""
+    return k + 1 + m_priv + (k - 1) + 2
 
 
 def _powers(x, count):
@@ -38,10 +47,10 @@ def setup_from_toxic(k, alpha, beta, delta, x_val, zx_val, priv_vals, precompute
     s15 = native.fr_vec_op(3, pw[:32 * (k - 1)], native.fe_bytes(zx_val % R * inv_delta % R), k - 1) if k > 1 else b""
     enc = native.fr_vec_bytes
     scA = pw + enc([alpha % R, delta % R])
-    scC = pw + enc([beta % R]) + enc([v % R for v in priv_vals]) + s15
+    scC = pw + enc([beta % R]) + enc([v % R for v in priv_vals]) + s15 + enc([alpha % R, delta % R])
     TA = native.g1_fixed_base_mul(native.g1_bytes(G1), scA, k + 2)
     TB2 = native.g2_fixed_base_mul(native.g2_bytes(G2), pw + enc([beta % R, delta % R]), k + 2)
-    TC = native.g1_fixed_base_mul(native.g1_bytes(G1), scC, k + 1 + m_priv + (k - 1))
+    TC = native.g1_fixed_base_mul(native.g1_bytes(G1), scC, tc_rows(k, m_priv))
     if precompute:
         for t in (TA, TB2, TC):
             if t.n >= 2:
@@ -62,26 +71,21 @@ def _scalars_ab(key, uA, uB, r, s):
     return scA, scB
 
 
-def _scalars_c(key, uB, hq, rx_priv, r):
-    """Scalar vector of the X part of C: r*uB | r | Rx_priv | H  (see the table layout above)."""
+def _scalars_c(key, uA, uB, hq, rx_priv, r, s):
+    """Scalar vector of C: r*uB + s*uA | r | Rx_priv | H | s | s*r  (see the table layout above)."""
     k, mp = key.k, key.m_priv
-    nC = k + 1 + mp + (k - 1)
+    nC = tc_rows(k, mp)
     scC = native.scalars_alloc(nC)
     native.scalars_copy(scC, 0, uB, 0, k)
     native.scalars_scale(scC, 0, k, r)
+    native.axpy_dev(scC, 0, s, uA, 0, k)
     native.scalars_upload(scC, k, native.fe_bytes(r), 1)
     if mp:
         native.scalars_copy(scC, k + 1, rx_priv, 0, mp)
     if k > 1:
         native.scalars_copy(scC, k + 1 + mp, hq, 0, k - 1)
+    native.scalars_upload(scC, nC - 2, native.fe_bytes(s) + native.fe_bytes(s * r % R), 2)
     return scC, nC
-
-
-def _proof_scalars(key, uA, uB, hq, rx_priv, r, s):
-    """The three MSM scalar vectors of one proof, assembled on the device."""
-    scA, scB = _scalars_ab(key, uA, uB, r, s)
-    scC, nC = _scalars_c(key, uB, hq, rx_priv, r)
-    return scA, scB, scC, nC
 
 
 def prove(key, uA, uB, uC, Z, rx_priv, r, s, keep_quotient=False):
@@ -91,11 +95,15 @@ def prove(key, uA, uB, uC, Z, rx_priv, r, s, keep_quotient=False):
     k = key.k
     r, s = int(r) % R, int(s) % R
     # H: k-1 coefficients; the remainder (k coefficients, zero for a satisfied instance) only on request
+    # B (G2, the longest of the three) needs only uB: it starts on the library's second stream and runs beside the
+    # quotient; A and C follow on the first stream
+    scA, scB = _scalars_ab(key, uA, uB, r, s)
+    native.msm_dev_begin(key.TB2, 0, scB, 0, k + 2)
     hq, hr = native.groth16_quotient_dev(uA, uB, uC, k, Z, k + 1, want_remainder=keep_quotient)
-    scA, scB, scC, nC = _proof_scalars(key, uA, uB, hq, rx_priv, r, s)
-    # A and X in G1 on one stream, B in G2 beside them on a second one
-    A, B, X = native.groth16_msms_dev(key.TA, scA, k + 2, key.TB2, scB, k + 2, key.TC, scC, nC)
-    C = native.g1_msm(native.g1_bytes(A) + native.g1_bytes(X), native.fe_bytes(s) + native.fr_vec_bytes([1]), 2)
+    scC, nC = _scalars_c(key, uA, uB, hq, rx_priv, r, s)
+    A = native.g1_msm_dev(key.TA, 0, scA, 0, k + 2)
+    C = native.g1_msm_dev(key.TC, 0, scC, 0, nC)
+    B = native.msm_dev_end("g2")
     for h in (scA, scB, scC):
         h.free()
     out = (g1_from_ints(A), g2_from_ints(B), g1_from_ints(C))
@@ -126,7 +134,7 @@ def setup_from_toxic_sharded(comm, k, alpha, beta, delta, x_val, zx_val, priv_va
     enc = native.fr_vec_bytes
     scA = pw + enc([alpha % R, delta % R])
     scB = pw + enc([beta % R, delta % R])
-    scC = pw + enc([beta % R]) + enc([v % R for v in priv_vals]) + s15
+    scC = pw + enc([beta % R]) + enc([v % R for v in priv_vals]) + s15 + enc([alpha % R, delta % R])
     out = []
     for sc, g2 in ((scA, False), (scB, True), (scC, False)):
         start, count = sharded.shard_range(len(sc) // 32, comm.rank, comm.world)
@@ -154,11 +162,10 @@ def prove_sharded(comm, key, uA, uB, uC, Z, rx_priv, r, s):
     native.msm_multi_begin(key.TA, 0, scA, key.rA[0], key.rA[1])
     native.msm_multi_begin(key.TB2, 0, scB, key.rB[0], key.rB[1])
     hq, _ = native.groth16_quotient_dev(uA, uB, uC, k, Z, k + 1, want_remainder=False)
-    scC, _ = _scalars_c(key, uB, hq, rx_priv, r)
-    X = native.g1_msm_multi(key.TC, 0, scC, key.rC[0], key.rC[1])
+    scC, _ = _scalars_c(key, uA, uB, hq, rx_priv, r, s)
+    C = native.g1_msm_multi(key.TC, 0, scC, key.rC[0], key.rC[1])
     A = native.msm_multi_end("g1")
     B = native.msm_multi_end("g2")
-    C = native.g1_msm(native.g1_bytes(A) + native.g1_bytes(X), native.fe_bytes(s) + native.fr_vec_bytes([1]), 2)
     for h in (scA, scB, scC, hq):
         h.free()
     return (g1_from_ints(A), g2_from_ints(B), g1_from_ints(C))

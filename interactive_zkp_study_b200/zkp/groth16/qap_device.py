@@ -171,7 +171,8 @@ def setup(dev, alpha, beta, gamma, delta, x_val, pub_r_indexs=None, lcm=True, pr
     inv_delta, inv_gamma = pow(delta, -1, R), pow(gamma, -1, R)
     enc = native.fr_vec_bytes
     g1b, g2b = native.g1_bytes(G1), native.g2_bytes(G2)
-    # TA = [x^j]_1 | alpha | delta ;  TB2 = [x^j]_2 | beta | delta ;  TC = [x^j]_1 | beta | sigma1_4[priv] | sigma1_5
+    # TA = [x^j]_1 | alpha | delta ;  TB2 = [x^j]_2 | beta | delta ;
+    # TC = [x^j]_1 | beta | sigma1_4[priv] | sigma1_5 | alpha | delta   (device_prover.tc_rows)
     mp = len(priv)
     scA = native.scalars_alloc(k + 2)
     native.scalars_fill_powers(scA, 0, k, 1, x_val)
@@ -179,7 +180,7 @@ def setup(dev, alpha, beta, gamma, delta, x_val, pub_r_indexs=None, lcm=True, pr
     scB = native.scalars_alloc(k + 2)
     native.scalars_copy(scB, 0, scA, 0, k)
     native.scalars_upload(scB, k, enc([beta, delta]), 2)
-    nC = k + 1 + mp + (k - 1)
+    nC = device_prover.tc_rows(k, mp)
     scC = native.scalars_alloc(nC)
     native.scalars_copy(scC, 0, scA, 0, k)
     native.scalars_upload(scC, k, enc([beta]), 1)
@@ -190,6 +191,7 @@ def setup(dev, alpha, beta, gamma, delta, x_val, pub_r_indexs=None, lcm=True, pr
         pv.free()
     if k > 1:
         native.scalars_fill_powers(scC, k + 1 + mp, k - 1, zx * inv_delta % R, x_val)
+    native.scalars_upload(scC, nC - 2, enc([alpha, delta]), 2)
     TA = native.g1_fixed_base_mul_dev(g1b, scA, k + 2)
     TB2 = native.g2_fixed_base_mul_dev(g2b, scB, k + 2)
     TC = native.g1_fixed_base_mul_dev(g1b, scC, nC)

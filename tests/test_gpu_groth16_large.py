@@ -64,3 +64,17 @@ def test_device_prover_2_16(native):
     lhs = (ev(uA, k) * ev(uB, k) - ev(uC, k)) % R
     rhs = (ev(hq, k - 1) * ref_path.poly_eval(z_host, t) + ev(hr, k)) % R
     assert lhs == rhs
+
+
+def test_device_prover_2_20_config3(native):
+    """BASELINE config 3 inside the GPU suite: Groth16 prove at 2^20 constraints, every proof element equal to its
+    closed-form discrete log times the generator and the quotient identity at a random point (the same
+    checks bench.py's groth16_prove sub-record makes)."""
+    k = 1 << 20
+    uA, uB, uC, z_host, hq, hr = _case(native, k, k - 2, 2026, True)
+    t = 0xfeedface12345
+    ev = lambda h, n: native.fr_poly_eval_dev(h, 0, n, t)
+    zh = native.scalars_load(native.fr_vec_bytes(z_host), k + 1)
+    lhs = (ev(uA, k) * ev(uB, k) - ev(uC, k)) % R
+    rhs = (ev(hq, k - 1) * ev(zh, k + 1) + ev(hr, k)) % R
+    assert lhs == rhs

@@ -183,7 +183,7 @@ def test_groth16_prove_sharded_equals_single_gpu(native, comm):
     r, s = rng.randrange(R), rng.randrange(R)
     key = dp.setup_from_toxic(k, alpha, beta, delta, x, zx, priv)
     skey = dp.setup_from_toxic_sharded(comm, k, alpha, beta, delta, x, zx, priv)
-    assert (skey.rA, skey.rB, skey.rC) == ((0, k + 2), (0, k + 2), (0, 3 * k - 2))
+    assert (skey.rA, skey.rB, skey.rC) == ((0, k + 2), (0, k + 2), (0, 3 * k))
     want = dp.prove(key, uA, uB, uC, Z, rx, r, s)
     got = dp.prove_sharded(comm, skey, uA, uB, uC, Z, rx, r, s)
     enc = lambda P: (native.g1_bytes(P[0]), native.g2_bytes(P[1]), native.g1_bytes(P[2]))

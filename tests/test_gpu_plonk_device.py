@@ -83,6 +83,22 @@ def test_device_prover_synthetic_verifies(native, log_n):
     assert _pt(proof2.a_comm) != _pt(proof.a_comm)
 
 
+def test_device_prover_2_20_config4(native):
+    """BASELINE config 4 inside the GPU suite: PLONK prove at 2^20 gates, accepted by the oracle's restatement of
+    the reference verifier; a tampered evaluation is rejected."""
+    from interactive_zkp_study_b200.zkp.plonk import device_prover as dp
+    import plonk_synth
+    n = 1 << 20
+    key, wit, tau = plonk_synth.device_setup(plonk_synth.chain_circuit(n, seed=20))
+    pd = _proof_dict(dp.prove(key, *wit))
+    pre = {k: key.comm[k] for k in dp.CIRCUIT_POLYS}
+    g2p = [bn254.G2, bn254.g2_mul(bn254.G2, tau)]
+    assert plonk_verifier.verify(pd, pre, n, key.omega, g2p) is True
+    bad = dict(pd)
+    bad["z_omega_eval"] = (bad["z_omega_eval"] + 1) % R
+    assert plonk_verifier.verify(bad, pre, n, key.omega, g2p) is False
+
+
 def test_device_prover_rejects_bad_witness(native):
     from interactive_zkp_study_b200.zkp.plonk import device_prover as dp
     import plonk_synth

@@ -65,8 +65,8 @@ def run(log_k=20, reps=3, verify=True, quiet=False, comm=None):
     res = {"constraints": k, "private_wires": mp, "prove_ms": best, "first_call_ms": times[0], "setup_s": setup_s,
            "verified_against_discrete_logs": ok,
            "n_gpus": 1 if comm is None else comm.world,
-           "work": "quotient h = (uA*uB - uC) div Z (NTT products + cached Newton inverse), 2 G1 MSMs (k+2, 3k-2 points), "
-                   "1 G2 MSM (k+2 points), one scalar multiplication s*A" +
+           "work": "quotient h = (uA*uB - uC) div Z (NTT products + cached Newton inverse), 2 G1 MSMs (k+2, 3k points), "
+                   "1 G2 MSM (k+2 points), no scalar multiplication (C is an independent MSM)" +
                    ("" if comm is None else "; each MSM sharded by point range over the ranks (zkp_g1/g2_msm_multi), the quotient "
                                             "computed by every rank (single-GPU NTT work)")}
     if not quiet:
