@@ -77,6 +77,7 @@ struct NttPassArgs {
   Fr n_inv;             // Montgomery
 };
 
+
 // Shared-memory tile: element `slot` is kept as two 16-byte halves, half h at uint4 index (h << log_tile) +
 // swz(slot): every access is a 128-bit LDS / STS (two per element instead of eight 32-bit ones).  swz XORs
 // the low three slot bits with parities of the higher ones so that the eight lanes of a quarter-warp fall
@@ -132,6 +133,9 @@ __global__ void __launch_bounds__(128, 4) ntt_pass_kernel(NttPassArgs a) {
   };
 
   // ---- load
+  // (A load through the bulk-copy engine -- two 16-byte cp.async.bulk per element into the swizzled slots, one
+  // mbarrier per tile -- was measured in round 2: UBLKCP takes uniform-register addresses, so the 2048 copies of a
+  // tile are issued lane by lane: 0.294 ms against 0.248 at 2^20.  profiles/r2_ntt_bulk_experiment.txt)
   for (uint32_t l = tid; l < tile; l += nthreads) {
     uint64_t gi = global_of(l);
     Fr x;

@@ -6,7 +6,8 @@ round 3 is O(n^2); at 2^20 gates the rounds have to stay in HBM.  Same protocol,
 proof elements (bit-identical to the reference-minted golden proofs for equal blinding scalars):
 
   round 1  3 iNTT, blinding, 3 MSMs                          (round1.py:38-108)
-  round 2  grand product = fused num/den kernel + batch inversion + product scan, iNTT, MSM   (round2.py, permutation.py:89-137)
+  round 2  grand product = fused num/den kernel + batch inversion + product scan, iNTT, MSM (on the second stream,
+           beside the coset transforms of round 3, which do not need alpha)                  (round2.py, permutation.py:89-137)
   round 3  quotient on the coset {g w_N^i}, N = 4n (the smallest power of two >= 3n+6): 4 coset NTTs of the witness polynomials (the 8 circuit
            polynomials' coset evaluations are part of the device key), one pointwise kernel
            t = [gate + alpha perm]/Z_H + alpha^2 (z-1)/(n(x-1)), one inverse coset NTT, divisibility =
@@ -52,6 +53,21 @@ def _commit(key, h, off, length):
     start, count = key.srs_range
     m = max(0, min(count, length - start))
     return native.g1_msm_multi(key.srs_table, 0, h, off + start if m else 0, m)
+
+
+def _commit_begin(key, h, off, length):
+    """_commit in split form: the MSM (or this rank's share and the collective) is enqueued on the library's second
+    stream; _commit_end fetches the point.  What is called in between runs beside it."""
+    if key.ranks is None:
+        native.msm_dev_begin(key.srs_table, 0, h, off, length)
+    else:
+        start, count = key.srs_range
+        m = max(0, min(count, length - start))
+        native.msm_multi_begin(key.srs_table, 0, h, off + start if m else 0, m)
+
+
+def _commit_end(key):
+    return native.msm_dev_end("g1") if key.ranks is None else native.msm_multi_end("g1")
 
 
 def _commit_many(key, items):
@@ -143,16 +159,19 @@ def prove(key, a_vals, b_vals, c_vals, blinds=None, keep=False):
         native.scalars_upload(z, 0, native.fe_bytes(1), 1)
     native.ntt_dev(z, 0, log_n, w, inverse=True)
     _blind(z, n, blinds[6:9])
-    proof.z_comm = g1_from_ints(_commit(key, z, 0, n + 3))
-    tr.append_point(b"z_comm", proof.z_comm)
-    # ---- round 3
-    alpha = int(tr.challenge_scalar(b"alpha"))
+    # the z commitment starts on the library's second stream; the four coset transforms of round 3 need a, b, c, z
+    # but not alpha, so they run beside it and the challenge is drawn once the commitment is back
+    _commit_begin(key, z, 0, n + 3)
     ext = []
     for h, length in ((wires["a"], n + 2), (wires["b"], n + 2), (wires["c"], n + 2), (z, n + 3)):
         e = _alloc_from(h, length, N8)
         native.scalars_convert(e, 0, length, True)
         native.ntt_dev(e, 0, log_n + key.log_ext, key.omega8, coset_shift=COSET_SHIFT)
         ext.append(e)
+    proof.z_comm = g1_from_ints(_commit_end(key))
+    tr.append_point(b"z_comm", proof.z_comm)
+    # ---- round 3
+    alpha = int(tr.challenge_scalar(b"alpha"))
     t = native.scalars_alloc(N8)
     native.plonk_quotient_dev(ext + [key.coset[k] for k in CIRCUIT_POLYS], n, key.ext, key.x, key.l1f, key.zh8, beta,
                               gamma, alpha, t)
