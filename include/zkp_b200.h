@@ -113,7 +113,10 @@ int zkp_g1_msm_dev_partial(uint64_t table, uint64_t offset, uint64_t scalars, ui
 int zkp_g1_combine_partials(const uint8_t* partials, uint32_t count, uint8_t out_xy[64], int* out_is_inf);
 /* Window-width override for experiments (0 = automatic). */
 int zkp_msm_set_window_bits(int c);
-/* Engine tunables for measurements by name (0 = automatic); today: "window_bits" as above. */
+/* Engine tunables for measurements by name (0 = automatic): "window_bits" as above; "accumulate" 1 = XYZZ chains
+ * (the default), 2 = affine pairwise tree with shared inversions for buckets of up to 511 entries (csrc/msm_tree.cuh;
+ * same results, measured slower on B200 and therefore opt-in); "tree_rounds" 1..9 affine rounds before the XYZZ
+ * chains take over, "tree_items" most additions per thread under one shared inversion. */
 int zkp_msm_set_option(const char* name, int value);
 
 /* ---- multi-GPU: points sharded by contiguous range, one process per GPU -----------------

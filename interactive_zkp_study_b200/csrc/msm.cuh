@@ -263,23 +263,26 @@ struct AccMinBlocks {
   static constexpr int value = sizeof(F) == 32 ? MSM_ACC_MIN_BLOCKS : MSM_ACC_MIN_BLOCKS_G2;
 };
 
+// light_max != 0: buckets of up to light_max entries belong to the affine tree (msm_tree.cuh) and get no task
 static __global__ void msm_task_count_kernel(const uint32_t* __restrict__ offsets, uint32_t nbuckets,
-                                             uint32_t* __restrict__ ntasks) {
+                                             uint32_t* __restrict__ ntasks, uint32_t light_max) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbuckets) return;
   uint32_t cnt = offsets[b + 1] - offsets[b];
+  if (cnt <= light_max) cnt = 0;
   ntasks[b] = (cnt + MSM_TASK_LEN - 1) / MSM_TASK_LEN;
 }
 
 // len_hist[MSM_TASK_LEN - len] counts tasks of each length (descending order of length)
 static __global__ void msm_task_hist_kernel(const uint32_t* __restrict__ offsets, uint32_t nbuckets,
-                                            uint32_t* __restrict__ len_hist) {
+                                            uint32_t* __restrict__ len_hist, uint32_t light_max) {
   __shared__ uint32_t h[MSM_TASK_LEN + 1];
   for (uint32_t k = threadIdx.x; k <= MSM_TASK_LEN; k += blockDim.x) h[k] = 0;
   __syncthreads();
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < nbuckets) {
     uint32_t cnt = offsets[b + 1] - offsets[b];
+    if (cnt <= light_max) cnt = 0;
     uint32_t full = cnt / MSM_TASK_LEN, rem = cnt % MSM_TASK_LEN;
     if (full) atomicAdd(&h[0], full);
     if (rem) atomicAdd(&h[MSM_TASK_LEN - rem], 1u);
@@ -306,7 +309,7 @@ static __global__ void msm_task_bins_kernel(uint32_t* __restrict__ len_hist) {
 // accumulate kernel stores it there (no copy through the partial array, nothing left for the fold)
 static __global__ void msm_task_emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_base,
                                             uint32_t nbuckets, uint32_t* __restrict__ len_cursor,
-                                            uint4* __restrict__ tasks) {
+                                            uint4* __restrict__ tasks, uint32_t light_max) {
   __shared__ uint32_t h[MSM_TASK_LEN + 1];     // block-local count per bin
   __shared__ uint32_t base[MSM_TASK_LEN + 1];  // block's reserved start per bin
   for (uint32_t k = threadIdx.x; k <= MSM_TASK_LEN; k += blockDim.x) h[k] = 0;
@@ -316,6 +319,7 @@ static __global__ void msm_task_emit_kernel(const uint32_t* __restrict__ offsets
   if (b < nbuckets) {
     beg = offsets[b];
     cnt = offsets[b + 1] - beg;
+    if (cnt <= light_max) cnt = 0;
     full = cnt / MSM_TASK_LEN;
     rem = cnt % MSM_TASK_LEN;
     if (full) r_full = atomicAdd(&h[0], full);
@@ -414,11 +418,13 @@ template <class F>
 __global__ void __launch_bounds__(128) msm_bucket_fold_kernel(const XYZZ<F>* __restrict__ partials,
                                                                const uint32_t* __restrict__ task_base, uint32_t nbuckets,
                                                                XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ heavy_count,
-                                                               uint32_t* __restrict__ heavy_list, uint32_t serial_limit) {
+                                                               uint32_t* __restrict__ heavy_list, uint32_t serial_limit,
+                                                               bool tree) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbuckets) return;
   uint32_t t0 = task_base[b], t1 = task_base[b + 1];
   if (t1 - t0 == 1) return;  // a single task: the accumulate kernel wrote the bucket itself
+  if (tree && t1 == t0) return;  // no task at all: the affine tree wrote the bucket (or its infinity)
   if (t1 - t0 > serial_limit) {
     heavy_list[atomicAdd(heavy_count, 1u)] = b;
     return;
@@ -455,6 +461,10 @@ __global__ void __launch_bounds__(128) msm_bucket_fold_heavy_kernel(const XYZZ<F
     __syncthreads();
   }
 }
+
+}  // namespace zkp
+#include "msm_tree.cuh"
+namespace zkp {
 
 // Window-precomputed tables: T[w][i] = 2^(c*w) * P_i, so every window's digits weigh the same and all
 // windows share ONE bucket set (no per-window sums, no final doubling chain).
@@ -664,6 +674,9 @@ __global__ void fe_from_mont_kernel(FE* __restrict__ v, uint64_t n) {
 // Tunables (zkp_msm_set_option; 0 = automatic).
 struct MsmOptions {
   int window_bits = 0;  // plain tables: window width override
+  int accumulate = 0;   // bucket accumulation: 0 = automatic (XYZZ chains), 1 = XYZZ chains, 2 = affine tree where it applies
+  int tree_items = 0;   // affine tree: most additions per thread and shared inversion (0 = default)
+  int tree_rounds = 0;  // affine tree: rounds before the XYZZ chains take over (0 = default)
 };
 MsmOptions& msm_options();  // defined in msm_g1.cu
 
@@ -672,6 +685,7 @@ struct MsmEngine {
   using FC = typename CompactOf<F>::type;  // same layout, out-of-line products (small code)
   DevBuf codes, sorted, hist, offsets, cursor, tile_sums, buckets, lvlA[2], lvlE[2], result, flag;
   DevBuf ntask, task_base, len_bins, tasks, partials, heavy;
+  DevBuf thist, tplan, torder, tbuf[2], tpre;  // affine tree (msm_tree.cuh)
   static constexpr int UPLOAD_CHUNKS = 4;
   cudaEvent_t ev_chunk[UPLOAD_CHUNKS] = {};
   int reduce_L = 8;
@@ -766,31 +780,115 @@ struct MsmEngine {
   }
 
   // ---- stage 3a: tasks: count per bucket -> scan -> length histogram -> emit sorted by length
-  int build_tasks(uint32_t nbuckets, uint32_t max_tasks, cudaStream_t st) {
+  int build_tasks(uint32_t nbuckets, uint32_t max_tasks, cudaStream_t st, uint32_t light_max = 0) {
     const uint32_t* off = offsets.as<uint32_t>();
     ntask.reserve(((size_t)nbuckets + 1) * 4);
     task_base.reserve(((size_t)nbuckets + 1) * 4);
     len_bins.reserve((MSM_TASK_LEN + 1) * 4);
     tasks.reserve((size_t)max_tasks * sizeof(uint4));
     partials.reserve((size_t)max_tasks * sizeof(XYZZ<F>));
-    msm_task_count_kernel<<<ceil_div(nbuckets, 256), 256, 0, st>>>(off, nbuckets, ntask.as<uint32_t>());
+    msm_task_count_kernel<<<ceil_div(nbuckets, 256), 256, 0, st>>>(off, nbuckets, ntask.as<uint32_t>(), light_max);
     CUDA_CHECK_LAUNCH();
     int launches = 1 + scan_u32(ntask.as<uint32_t>(), nbuckets, task_base.as<uint32_t>(), st);
     CUDA_CHECK(cudaMemsetAsync(len_bins.p, 0, (MSM_TASK_LEN + 1) * 4, st));
-    msm_task_hist_kernel<<<ceil_div(nbuckets, 256), 256, 0, st>>>(off, nbuckets, len_bins.as<uint32_t>());
+    msm_task_hist_kernel<<<ceil_div(nbuckets, 256), 256, 0, st>>>(off, nbuckets, len_bins.as<uint32_t>(), light_max);
     CUDA_CHECK_LAUNCH();
     msm_task_bins_kernel<<<1, 32, 0, st>>>(len_bins.as<uint32_t>());
     CUDA_CHECK_LAUNCH();
     msm_task_emit_kernel<<<ceil_div(nbuckets, 256), 256, 0, st>>>(off, task_base.as<uint32_t>(), nbuckets,
-                                                                 len_bins.as<uint32_t>(), tasks.as<uint4>());
+                                                                 len_bins.as<uint32_t>(), tasks.as<uint4>(), light_max);
     CUDA_CHECK_LAUNCH();
     return launches + 3;
+  }
+
+  // ---- stage 3, affine form: buckets of up to TREE_MAX entries summed as pairwise trees with shared inversions
+  // (msm_tree.cuh).
+  static bool use_tree(uint64_t total, uint32_t nbuckets) {
+    static const char* env = getenv("ZKP_B200_MSM_ACC");  // "xyzz" / "tree": overrides the option (tests, A/B runs)
+    int mode = msm_options().accumulate;
+    if (env && !strcmp(env, "xyzz")) mode = 1;
+    if (env && !strcmp(env, "tree")) mode = 2;
+    if (mode == 1) return false;
+    if (total >= (1ull << 32) - nbuckets || nbuckets > (1u << TREE_BUCKET_BITS)) return false;
+    // Opt-in only (zkp_msm_set_option("accumulate", 2) / ZKP_B200_MSM_ACC=tree).  Measured on B200 at 2^20 points,
+    // c = 20 (profiles/r2_affine_tree_experiment.txt): 788 instead of 1304 limb-MACs per addition did not pay -- a
+    // round runs the integer pipe at 40-45 % (every operand is gathered twice, 32 more bytes per addition travel
+    // through the prefix array, and each block idles through a ~60 us single-thread inversion), against 88 % for the
+    // XYZZ chains: 2 rounds + chains 3.70 ms, 1 round + chains 2.98 ms, XYZZ chains alone 2.21 ms.
+    return mode == 2;
+  }
+  int run_tree(const Affine<F>* pts, uint32_t nbuckets, uint64_t total, cudaStream_t st, StageTrace& tr) {
+    constexpr int TB = TreeCfg<FC>::TB;
+    int full = 1;
+    while (full < TREE_ROUNDS && (1ull << full) < total) full++;  // a bucket holds at most `total` entries
+    // rounds in affine form before the XYZZ chains take over (every round costs an inversion latency per block)
+    static const int env_rounds = getenv("ZKP_B200_TREE_ROUNDS") ? atoi(getenv("ZKP_B200_TREE_ROUNDS")) : 0;
+    int K = env_rounds > 0 ? env_rounds : msm_options().tree_rounds > 0 ? msm_options().tree_rounds : 2;
+    if (K > full) K = full;
+    thist.reserve(2 * (TREE_MAX + 1) * 4);
+    tplan.reserve((size_t)TREE_ROUNDS * TREE_REC * 4);
+    torder.reserve((size_t)nbuckets * sizeof(uint2));
+    tbuf[0].reserve((size_t)(total / 2 + nbuckets + 2) * sizeof(Affine<F>));
+    if (K > 1) tbuf[1].reserve((size_t)(total / 4 + nbuckets + 2) * sizeof(Affine<F>));
+    uint32_t* hist_p = thist.as<uint32_t>();
+    uint32_t* cursor_p = hist_p + (TREE_MAX + 1);
+    CUDA_CHECK(cudaMemsetAsync(hist_p, 0, (TREE_MAX + 1) * 4, st));
+    msm_tree_hist_kernel<FC><<<ceil_div(nbuckets, 256), 256, 0, st>>>(offsets.as<uint32_t>(), nbuckets, hist_p,
+                                                                     buckets.as<XYZZ<FC>>());
+    CUDA_CHECK_LAUNCH();
+    msm_tree_plan_kernel<<<1, TREE_JMAX, 0, st>>>(hist_p, cursor_p, tplan.as<uint32_t>(), K);
+    CUDA_CHECK_LAUNCH();
+    msm_tree_emit_kernel<<<ceil_div(nbuckets, 256), 256, 0, st>>>(offsets.as<uint32_t>(), nbuckets, cursor_p,
+                                                                 torder.as<uint2>());
+    CUDA_CHECK_LAUNCH();
+    tr.mark("tree plan");
+    // items per thread of the largest blocks (= additions per shared inversion / TB): a multiple of 8, as many as
+    // still leave every SM several waves of blocks
+    static const int env_items = getenv("ZKP_B200_TREE_B") ? atoi(getenv("ZKP_B200_TREE_B")) : 0;
+    const uint32_t max_items = env_items > 0 ? (uint32_t)env_items : msm_options().tree_items > 0 ? (uint32_t)msm_options().tree_items : 32u;
+    const uint64_t nonempty = total < nbuckets ? total : nbuckets;
+    const uint64_t slots = (uint64_t)TreeCfg<FC>::MIN_BLOCKS * (uint64_t)(ctx().sm_count > 0 ? ctx().sm_count : 148);
+    uint32_t B[TREE_ROUNDS], blocks[TREE_ROUNDS];
+    uint64_t pre_items = 0;
+    for (int r = 0; r < K; r++) {
+      const uint64_t expect = total >> (r + 1), upper = expect + nonempty + 1;
+      uint64_t b = expect / ((uint64_t)TB * slots * 2);  // the average block is about half the largest
+      if (b > max_items) b = max_items;
+      if (b >= 8) b &= ~7ull;
+      if (b < 2) b = 2;
+      B[r] = (uint32_t)b;
+      TreeSched sc;
+      blocks[r] = tree_sched(upper, B[r], TB, sc) + 16;  // the split of the true item count never needs more
+      if (upper > pre_items) pre_items = upper;
+    }
+    tpre.reserve((size_t)pre_items * sizeof(F));
+    const Affine<FC>* p = reinterpret_cast<const Affine<FC>*>(pts);
+    for (int r = 0; r < K; r++) {
+      Affine<FC>* out = tbuf[r & 1].template as<Affine<FC>>();
+      const uint32_t* rec = tplan.as<uint32_t>() + (size_t)r * TREE_REC;
+      if (r == 0)
+        msm_tree_round_kernel<FC, true><<<blocks[r], TB, 0, st>>>(p, sorted.as<uint32_t>(), nullptr, out, torder.as<uint2>(), rec,
+                                                                 r, B[r], tpre.as<FC>(), buckets.as<XYZZ<FC>>());
+      else
+        msm_tree_round_kernel<FC, false><<<blocks[r], TB, 0, st>>>(nullptr, nullptr, tbuf[(r - 1) & 1].template as<Affine<FC>>(), out,
+                                                                  torder.as<uint2>(), rec, r, B[r], tpre.as<FC>(),
+                                                                  buckets.as<XYZZ<FC>>());
+      CUDA_CHECK_LAUNCH();
+      if (tr.print) tr.mark("tree round");
+    }
+    if (K < full) {
+      msm_tree_finish_kernel<F, MSM_ACC_OUTLINE><<<ceil_div(nonempty, 128), 128, 0, st>>>(
+          tbuf[(K - 1) & 1].template as<Affine<F>>(), torder.as<uint2>(), tplan.as<uint32_t>(), K, buckets.as<XYZZ<F>>());
+      CUDA_CHECK_LAUNCH();
+      if (tr.print) tr.mark("tree finish");
+    }
+    return 4 + K;
   }
 
   // ---- stage 3b + 4: fold the buckets that were cut into several tasks, then the weighted-sum recursion
   // down to one item per window.  Returns the window sums through `wsum`.
   int reduce_buckets(uint32_t nbuckets, int n_windows, uint64_t avg_entries, cudaStream_t st, StageTrace& tr,
-                     const XYZZ<FC>** wsum) {
+                     const XYZZ<FC>** wsum, bool tree = false) {
     int launches = 0;
     XYZZ<FC>* bk = buckets.as<XYZZ<FC>>();
     heavy.reserve(((size_t)nbuckets + 1) * 4);
@@ -799,7 +897,7 @@ struct MsmEngine {
         partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(), nbuckets, bk, heavy.as<uint32_t>(), heavy.as<uint32_t>() + 1,
         // "heavy" is relative to the average bucket: every bucket of a dense MSM (many entries per
         // bucket) folds serially in parallel with the others; only outliers get a whole block
-        MSM_FOLD_SERIAL + 3 * (uint32_t)(avg_entries / MSM_TASK_LEN));
+        MSM_FOLD_SERIAL + 3 * (uint32_t)(avg_entries / MSM_TASK_LEN), tree);
     CUDA_CHECK_LAUNCH();
     msm_bucket_fold_heavy_kernel<FC><<<296, 128, 0, st>>>(partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(),
                                                           heavy.as<uint32_t>(), heavy.as<uint32_t>() + 1, bk);
@@ -886,9 +984,12 @@ struct MsmEngine {
     launches += sort_entries(scalars, n, pl, wstride, pre_stride, pre_offset, st, tr, host_scalars, copy_st);
     // the task count is data dependent: launch for the upper bound, threads past
     // task_base[nbuckets] exit at once (no host round trip in the middle of the pipeline)
-    const uint32_t max_tasks = (uint32_t)(total / MSM_TASK_LEN) + pl.nbuckets + 1;
-    launches += build_tasks(pl.nbuckets, max_tasks, st);
+    const bool tree = use_tree(total, pl.nbuckets);
+    const uint32_t max_tasks = tree ? (uint32_t)(total / MSM_TASK_LEN) + (uint32_t)(total / (TREE_MAX + 1)) + 1
+                                    : (uint32_t)(total / MSM_TASK_LEN) + pl.nbuckets + 1;
+    launches += build_tasks(pl.nbuckets, max_tasks, st, tree ? TREE_MAX : 0u);
     tr.mark("tasks");
+    if (tree) launches += run_tree(pts, pl.nbuckets, total, st, tr);
     // G1: the eight products of the mixed addition through the shared out-of-line body, the two squarings inlined
     // (measured at 2^20: 2.213 ms; everything inlined 2.248, everything out of line 2.241, other splits between)
     msm_accumulate_kernel<F, MSM_ACC_OUTLINE><<<ceil_div(max_tasks, 128), 128, 0, st>>>(
@@ -898,7 +999,7 @@ struct MsmEngine {
     launches++;
     tr.mark("accumulate");
     const XYZZ<FC>* wsum = nullptr;
-    launches += reduce_buckets(pl.nbuckets, n_windows, total / pl.nbuckets, st, tr, &wsum);
+    launches += reduce_buckets(pl.nbuckets, n_windows, total / pl.nbuckets, st, tr, &wsum, tree);
     msm_final_kernel<FC><<<1, 32, 0, st>>>(wsum, n_windows, pl.c, nullptr, 0,
                                           want_xyzz ? nullptr : reinterpret_cast<Affine<FC>*>(out_aff), flag.as<int>(),
                                           want_xyzz ? reinterpret_cast<XYZZ<FC>*>(out_xyzz) : nullptr);

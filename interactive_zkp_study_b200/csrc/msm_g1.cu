@@ -25,7 +25,19 @@ int zkp_msm_set_window_bits(int c) {
 int zkp_msm_set_option(const char* name, int value) {
   std::string n = name ? name : "";
   if (n == "window_bits") return zkp_msm_set_window_bits(value);
-  set_last_error("zkp_msm_set_option: unknown option (window_bits)");
+  if (n == "accumulate" && value >= 0 && value <= 2) {  // 0 automatic, 1 XYZZ chains, 2 affine tree
+    msm_options().accumulate = value;
+    return ZKP_OK;
+  }
+  if (n == "tree_items" && value >= 0 && value <= 256) {  // additions per thread under one shared inversion
+    msm_options().tree_items = value;
+    return ZKP_OK;
+  }
+  if (n == "tree_rounds" && value >= 0 && value <= 9) {  // affine rounds before the XYZZ chains take over
+    msm_options().tree_rounds = value;
+    return ZKP_OK;
+  }
+  set_last_error("zkp_msm_set_option: unknown option or value (window_bits, accumulate 0..2, tree_items 0..256, tree_rounds 0..9)");
   return ZKP_ERR_INVALID_ARGUMENT;
 }
 
