@@ -211,6 +211,11 @@ int zkp_init(int device) {
     g_ctx.sm_count = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.stream2, cudaStreamNonBlocking));
+    {
+      int lo = 0, hi = 0;  // numerically lower = higher priority
+      CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CUDA_CHECK(cudaStreamCreateWithPriority(&g_ctx.stream_hi, cudaStreamNonBlocking, hi));
+    }
     CUDA_CHECK(cudaEventCreateWithFlags(&g_ctx.ev_fork, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&g_ctx.ev_join, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreate(&g_ev0));

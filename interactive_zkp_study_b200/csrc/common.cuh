@@ -95,6 +95,7 @@ struct Context {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;                 // second lane of the batched-MSM pipeline
+  cudaStream_t stream_hi = nullptr;               // high-priority side lane of the part-streamed MSM (upload + sort)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::mutex mu;  // serialises entry points (Flask's dev server is threaded, ctypes drops the GIL)
   unsigned long long launches = 0;  // kernels launched by this library (bench.py "gpu_launches")
@@ -119,10 +120,10 @@ struct StageTrace {
     static std::vector<cudaEvent_t> p;
     return p;
   }
-  explicit StageTrace(cudaStream_t s) : st(s) {
+  explicit StageTrace(cudaStream_t s, bool enabled = true) : st(s) {
     static const bool env = getenv("ZKP_B200_TRACE") && atoi(getenv("ZKP_B200_TRACE"));
-    print = env;
-    on = env || g_msm_profile_enabled;
+    print = env && enabled;
+    on = (env || g_msm_profile_enabled) && enabled;
     mark("start");
   }
   void mark(const char* name) {

@@ -169,12 +169,12 @@ static __global__ void scan_apply_kernel(const uint32_t* __restrict__ in, uint32
 // is the index of 2^(c*w) * P_i inside the [w][i] table, w * pre_stride + pre_offset + i.
 static __global__ void msm_scatter_kernel(const uint32_t* __restrict__ codes, uint64_t total, uint64_t n,
                                    uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted,
-                                   uint32_t pre_stride, uint32_t pre_offset) {
+                                   uint32_t pre_stride, uint32_t pre_offset, uint32_t idx_base) {
   uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   uint32_t code = codes[idx];
   if (code == MSM_INVALID) return;
-  uint32_t i = (uint32_t)(idx % n);
+  uint32_t i = (uint32_t)(idx % n) + idx_base;  // idx_base: first point of this part of a part-streamed MSM
   if (pre_stride) i += (uint32_t)(idx / n) * pre_stride + pre_offset;
   uint32_t pos = atomicAdd(&cursor[code >> 1], 1u);
   sorted[pos] = i | ((code & 1u) << 31);
@@ -393,12 +393,15 @@ __global__ void __launch_bounds__(128, AccMinBlocks<F>::value) msm_accumulate_ke
                                                               const uint4* __restrict__ tasks,
                                                               const uint32_t* __restrict__ ntasks_ptr,
                                                               XYZZ<F>* __restrict__ partials,
-                                                              XYZZ<F>* __restrict__ buckets) {
+                                                              XYZZ<F>* __restrict__ buckets, bool cont) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= *ntasks_ptr) return;  // the task count is data dependent and stays on the device
   uint4 task = tasks[t];
   uint32_t beg = task.y, end = task.y + task.z;
+  // cont: a later part of a part-streamed MSM (MsmEngine::run): the bucket already holds the earlier parts' sum
+  // and a bucket that is one task continues from it
   XYZZ<F> acc = XYZZ<F>::inf();
+  if (cont && (task.w & MSM_DIRECT)) acc = buckets[task.w & ~MSM_DIRECT];
   for (uint32_t k = beg; k < end; k++) {
     uint32_t e = sorted[k];
     Affine<F> p = pts[e & 0x7fffffffu];
@@ -419,12 +422,13 @@ __global__ void __launch_bounds__(128) msm_bucket_fold_kernel(const XYZZ<F>* __r
                                                                const uint32_t* __restrict__ task_base, uint32_t nbuckets,
                                                                XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ heavy_count,
                                                                uint32_t* __restrict__ heavy_list, uint32_t serial_limit,
-                                                               bool tree) {
+                                                               bool tree, bool cont) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbuckets) return;
   uint32_t t0 = task_base[b], t1 = task_base[b + 1];
   if (t1 - t0 == 1) return;  // a single task: the accumulate kernel wrote the bucket itself
-  if (tree && t1 == t0) return;  // no task at all: the affine tree wrote the bucket (or its infinity)
+  if ((tree || cont) && t1 == t0) return;  // no task at all: the affine tree wrote the bucket (or its infinity) /
+                                           // a later part of a part-streamed MSM adds nothing to it
   if (t1 - t0 > serial_limit) {
     heavy_list[atomicAdd(heavy_count, 1u)] = b;
     return;
@@ -432,6 +436,7 @@ __global__ void __launch_bounds__(128) msm_bucket_fold_kernel(const XYZZ<F>* __r
   XYZZ<F> acc = XYZZ<F>::inf();
   if (t1 > t0) acc = partials[t0];
   for (uint32_t t = t0 + 1; t < t1; t++) acc.add(partials[t]);
+  if (cont) acc.add(buckets[b]);
   buckets[b] = acc;
 }
 
@@ -440,7 +445,7 @@ __global__ void __launch_bounds__(128) msm_bucket_fold_heavy_kernel(const XYZZ<F
                                                                      const uint32_t* __restrict__ task_base,
                                                                      const uint32_t* __restrict__ heavy_count,
                                                                      const uint32_t* __restrict__ heavy_list,
-                                                                     XYZZ<F>* __restrict__ buckets) {
+                                                                     XYZZ<F>* __restrict__ buckets, bool cont) {
   __shared__ XYZZ<F> sm[128];
   uint32_t count = *heavy_count;
   for (uint32_t h = blockIdx.x; h < count; h += gridDim.x) {
@@ -457,7 +462,10 @@ __global__ void __launch_bounds__(128) msm_bucket_fold_heavy_kernel(const XYZZ<F
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) buckets[b] = acc;
+    if (threadIdx.x == 0) {
+      if (cont) acc.add(buckets[b]);
+      buckets[b] = acc;
+    }
     __syncthreads();
   }
 }
@@ -677,6 +685,7 @@ struct MsmOptions {
   int accumulate = 0;   // bucket accumulation: 0 = automatic (XYZZ chains), 1 = XYZZ chains, 2 = affine tree where it applies
   int tree_items = 0;   // affine tree: most additions per thread and shared inversion (0 = default)
   int tree_rounds = 0;  // affine tree: rounds before the XYZZ chains take over (0 = default)
+  int parts = 0;        // part-streamed MSM: point ranges per MSM (0 = 4 for host scalars, 1 for resident ones)
 };
 MsmOptions& msm_options();  // defined in msm_g1.cu
 
@@ -686,6 +695,19 @@ struct MsmEngine {
   DevBuf codes, sorted, hist, offsets, cursor, tile_sums, buckets, lvlA[2], lvlE[2], result, flag;
   DevBuf ntask, task_base, len_bins, tasks, partials, heavy;
   DevBuf thist, tplan, torder, tbuf[2], tpre;  // affine tree (msm_tree.cuh)
+  // part-streamed form (run): the second set of the buffers one lane fills while the other reads
+  static constexpr int MAX_PARTS = 8;
+  DevBuf alt_sorted, alt_offsets, alt_ntask, alt_task_base, alt_len_bins, alt_tasks, alt_partials;
+  cudaEvent_t ev_ready[MAX_PARTS] = {}, ev_done[MAX_PARTS] = {}, ev_lane = nullptr;
+  void swap_part_sets() {
+    std::swap(sorted, alt_sorted);
+    std::swap(offsets, alt_offsets);
+    std::swap(ntask, alt_ntask);
+    std::swap(task_base, alt_task_base);
+    std::swap(len_bins, alt_len_bins);
+    std::swap(tasks, alt_tasks);
+    std::swap(partials, alt_partials);
+  }
   static constexpr int UPLOAD_CHUNKS = 4;
   cudaEvent_t ev_chunk[UPLOAD_CHUNKS] = {};
   int reduce_L = 8;
@@ -737,7 +759,7 @@ struct MsmEngine {
   // atomics, the slow part of it) runs under the rest of the upload instead of after it.
   int sort_entries(const uint32_t* scalars, uint64_t n, const MsmPlan& pl, uint32_t wstride, uint32_t pre_stride,
                    uint32_t pre_offset, cudaStream_t st, StageTrace& tr, const uint8_t* host_scalars = nullptr,
-                   cudaStream_t copy_st = nullptr) {
+                   cudaStream_t copy_st = nullptr, uint32_t idx_base = 0) {
     const uint64_t total = (uint64_t)pl.W * n;
     codes.reserve(total * 4);
     sorted.reserve(total * 4);
@@ -773,7 +795,7 @@ struct MsmEngine {
     tr.mark("digits+scan");
     CUDA_CHECK(cudaMemcpyAsync(cursor.p, offsets.p, ((size_t)pl.nbuckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
     msm_scatter_kernel<<<ceil_div(total, 256), 256, 0, st>>>(codes.as<uint32_t>(), total, n, cursor.as<uint32_t>(),
-                                                            sorted.as<uint32_t>(), pre_stride, pre_offset);
+                                                            sorted.as<uint32_t>(), pre_stride, pre_offset, idx_base);
     CUDA_CHECK_LAUNCH();
     tr.mark("scatter");
     return launches + 1;
@@ -885,11 +907,8 @@ struct MsmEngine {
     return 4 + K;
   }
 
-  // ---- stage 3b + 4: fold the buckets that were cut into several tasks, then the weighted-sum recursion
-  // down to one item per window.  Returns the window sums through `wsum`.
-  int reduce_buckets(uint32_t nbuckets, int n_windows, uint64_t avg_entries, cudaStream_t st, StageTrace& tr,
-                     const XYZZ<FC>** wsum, bool tree = false) {
-    int launches = 0;
+  // ---- stage 3b: fold the buckets that were cut into several tasks (cont: onto what the bucket already holds)
+  int fold_buckets(uint32_t nbuckets, uint64_t avg_entries, cudaStream_t st, bool tree, bool cont) {
     XYZZ<FC>* bk = buckets.as<XYZZ<FC>>();
     heavy.reserve(((size_t)nbuckets + 1) * 4);
     CUDA_CHECK(cudaMemsetAsync(heavy.p, 0, 4, st));
@@ -897,13 +916,18 @@ struct MsmEngine {
         partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(), nbuckets, bk, heavy.as<uint32_t>(), heavy.as<uint32_t>() + 1,
         // "heavy" is relative to the average bucket: every bucket of a dense MSM (many entries per
         // bucket) folds serially in parallel with the others; only outliers get a whole block
-        MSM_FOLD_SERIAL + 3 * (uint32_t)(avg_entries / MSM_TASK_LEN), tree);
+        MSM_FOLD_SERIAL + 3 * (uint32_t)(avg_entries / MSM_TASK_LEN), tree, cont);
     CUDA_CHECK_LAUNCH();
     msm_bucket_fold_heavy_kernel<FC><<<296, 128, 0, st>>>(partials.as<XYZZ<FC>>(), task_base.as<uint32_t>(),
-                                                          heavy.as<uint32_t>(), heavy.as<uint32_t>() + 1, bk);
+                                                          heavy.as<uint32_t>(), heavy.as<uint32_t>() + 1, bk, cont);
     CUDA_CHECK_LAUNCH();
-    launches += 2;
-    tr.mark("fold");
+    return 2;
+  }
+
+  // ---- stage 4: the weighted-sum recursion down to one item per window.  Returns the window sums through `wsum`.
+  int reduce_buckets(uint32_t nbuckets, int n_windows, cudaStream_t st, StageTrace& tr, const XYZZ<FC>** wsum) {
+    int launches = 0;
+    XYZZ<FC>* bk = buckets.as<XYZZ<FC>>();
     uint32_t n_in = nbuckets / n_windows;  // buckets per window
     const XYZZ<FC>* A = bk;
     const XYZZ<FC>* E = nullptr;
@@ -956,7 +980,7 @@ struct MsmEngine {
   // reduction of the last part is still log2(buckets) dependent levels long.
   int run(const Affine<F>* pts, const uint32_t* scalars, uint64_t n, cudaStream_t st, bool want_xyzz = false,
           int force_c = 0, uint32_t pre_stride = 0, uint32_t pre_offset = 0, const uint8_t* host_scalars = nullptr,
-          cudaStream_t copy_st = nullptr) {
+          cudaStream_t copy_st = nullptr, cudaStream_t lane = nullptr) {
     int launches = 0;
     result.reserve(sizeof(XYZZ<F>) + sizeof(Affine<F>));
     flag.reserve(sizeof(int));
@@ -981,25 +1005,93 @@ struct MsmEngine {
     buckets.reserve((size_t)pl.nbuckets * sizeof(XYZZ<F>));
 
     StageTrace tr(st);
-    launches += sort_entries(scalars, n, pl, wstride, pre_stride, pre_offset, st, tr, host_scalars, copy_st);
-    // the task count is data dependent: launch for the upper bound, threads past
-    // task_base[nbuckets] exit at once (no host round trip in the middle of the pipeline)
     const bool tree = use_tree(total, pl.nbuckets);
-    const uint32_t max_tasks = tree ? (uint32_t)(total / MSM_TASK_LEN) + (uint32_t)(total / (TREE_MAX + 1)) + 1
-                                    : (uint32_t)(total / MSM_TASK_LEN) + pl.nbuckets + 1;
-    launches += build_tasks(pl.nbuckets, max_tasks, st, tree ? TREE_MAX : 0u);
-    tr.mark("tasks");
-    if (tree) launches += run_tree(pts, pl.nbuckets, total, st, tr);
-    // G1: the eight products of the mixed addition through the shared out-of-line body, the two squarings inlined
-    // (measured at 2^20: 2.213 ms; everything inlined 2.248, everything out of line 2.241, other splits between)
-    msm_accumulate_kernel<F, MSM_ACC_OUTLINE><<<ceil_div(max_tasks, 128), 128, 0, st>>>(
-        pts, sorted.as<uint32_t>(), tasks.as<uint4>(), task_base.as<uint32_t>() + pl.nbuckets, partials.as<XYZZ<F>>(),
-        buckets.as<XYZZ<F>>());
-    CUDA_CHECK_LAUNCH();
-    launches++;
-    tr.mark("accumulate");
+    // Part-streamed form (host scalars, large n): the points are cut into `parts` contiguous ranges that all add
+    // into ONE bucket set.  A side lane (high-priority stream) uploads range p+1 and sorts its digits while the
+    // main stream accumulates range p, so only the first range's upload and sort stay exposed; the bucket
+    // reduction runs once.  Two workspace sets alternate between the lanes.
+    static const int env_parts = getenv("ZKP_B200_MSM_PARTS") ? atoi(getenv("ZKP_B200_MSM_PARTS")) : 0;
+    int parts = 1;
+    if (lane && !tree) {
+      const int asked = env_parts > 0 ? env_parts : msm_options().parts;  // explicit: any size (tests, A/B runs)
+      if (asked > 0) parts = (uint64_t)asked < n ? asked : (int)n;
+      else if (host_scalars && n >= (1u << 18)) parts = 4;
+      if (parts > MAX_PARTS) parts = MAX_PARTS;
+    }
+    if (parts == 1) {
+      launches += sort_entries(scalars, n, pl, wstride, pre_stride, pre_offset, st, tr, host_scalars, copy_st);
+      // the task count is data dependent: launch for the upper bound, threads past
+      // task_base[nbuckets] exit at once (no host round trip in the middle of the pipeline)
+      const uint32_t max_tasks = tree ? (uint32_t)(total / MSM_TASK_LEN) + (uint32_t)(total / (TREE_MAX + 1)) + 1
+                                      : (uint32_t)(total / MSM_TASK_LEN) + pl.nbuckets + 1;
+      launches += build_tasks(pl.nbuckets, max_tasks, st, tree ? TREE_MAX : 0u);
+      tr.mark("tasks");
+      if (tree) launches += run_tree(pts, pl.nbuckets, total, st, tr);
+      // G1: the eight products of the mixed addition through the shared out-of-line body, the two squarings inlined
+      // (measured at 2^20: 2.213 ms; everything inlined 2.248, everything out of line 2.241, other splits between)
+      msm_accumulate_kernel<F, MSM_ACC_OUTLINE><<<ceil_div(max_tasks, 128), 128, 0, st>>>(
+          pts, sorted.as<uint32_t>(), tasks.as<uint4>(), task_base.as<uint32_t>() + pl.nbuckets, partials.as<XYZZ<F>>(),
+          buckets.as<XYZZ<F>>(), false);
+      CUDA_CHECK_LAUNCH();
+      launches++;
+      tr.mark("accumulate");
+      launches += fold_buckets(pl.nbuckets, total / pl.nbuckets, st, tree, false);
+      tr.mark("fold");
+    } else {
+      if (!ev_ready[0]) {
+        for (auto& e : ev_ready) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ev_done) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_lane, cudaEventDisableTiming));
+      }
+      CUDA_CHECK(cudaEventRecord(ev_lane, st));  // the lane starts behind everything already queued on the main stream
+      CUDA_CHECK(cudaStreamWaitEvent(lane, ev_lane, 0));
+      StageTrace lane_tr(lane, false);
+      // Ranges grow by 1.35x: the first one (whose upload and sort nothing hides) is small, and each later upload +
+      // sort (0.9 ms per 2^20 points alone, 1.7 ms when eight ranks pull from host memory at once) still fits under
+      // the accumulation of the range before it (2.2 ms per 2^20 points).
+      uint64_t cut[MAX_PARTS + 1];
+      {
+        double w = 1.0, sum = 0.0, acc = 0.0;
+        for (int p = 0; p < parts; p++, w *= 1.35) sum += w;
+        w = 1.0;
+        cut[0] = 0;
+        for (int p = 0; p < parts; p++, w *= 1.35) {
+          acc += w;
+          cut[p + 1] = p + 1 == parts ? n : (uint64_t)((double)n * (acc / sum));
+          if (cut[p + 1] <= cut[p]) cut[p + 1] = cut[p] + 1;  // tiny MSMs under an explicit part count: no empty range
+          if (cut[p + 1] > n) cut[p + 1] = n;
+        }
+      }
+      for (int p = 0; p < parts; p++) {
+        const uint64_t i0 = cut[p], i1 = cut[p + 1], np = i1 - i0;
+        if (np == 0) continue;
+        if (p > 0) swap_part_sets();
+        if (p >= 2) CUDA_CHECK(cudaStreamWaitEvent(lane, ev_done[p - 2], 0));  // this workspace set is free again
+        if (host_scalars)
+          CUDA_CHECK(cudaMemcpyAsync(const_cast<uint32_t*>(scalars) + 8 * i0, host_scalars + 32 * i0, np * 32,
+                                     cudaMemcpyHostToDevice, lane));
+        MsmPlan plp = pl;  // same window width and bucket set, fewer points
+        launches += sort_entries(scalars + 8 * i0, np, plp, wstride, pre_stride, pre_offset + (uint32_t)i0, lane, lane_tr,
+                                 nullptr, nullptr, pre_stride ? 0u : (uint32_t)i0);
+        const uint64_t total_p = (uint64_t)pl.W * np;
+        const uint32_t max_tasks = (uint32_t)(total_p / MSM_TASK_LEN) + pl.nbuckets + 1;
+        launches += build_tasks(pl.nbuckets, max_tasks, lane);
+        CUDA_CHECK(cudaEventRecord(ev_ready[p], lane));
+        CUDA_CHECK(cudaStreamWaitEvent(st, ev_ready[p], 0));
+        if (p == 0) tr.mark("tasks");
+        msm_accumulate_kernel<F, MSM_ACC_OUTLINE><<<ceil_div(max_tasks, 128), 128, 0, st>>>(
+            pts, sorted.as<uint32_t>(), tasks.as<uint4>(), task_base.as<uint32_t>() + pl.nbuckets, partials.as<XYZZ<F>>(),
+            buckets.as<XYZZ<F>>(), p > 0);
+        CUDA_CHECK_LAUNCH();
+        launches++;
+        launches += fold_buckets(pl.nbuckets, total_p / pl.nbuckets, st, false, p > 0);
+        CUDA_CHECK(cudaEventRecord(ev_done[p], st));
+      }
+      tr.mark("accumulate");
+      tr.mark("fold");
+    }
     const XYZZ<FC>* wsum = nullptr;
-    launches += reduce_buckets(pl.nbuckets, n_windows, total / pl.nbuckets, st, tr, &wsum, tree);
+    launches += reduce_buckets(pl.nbuckets, n_windows, st, tr, &wsum);
     msm_final_kernel<FC><<<1, 32, 0, st>>>(wsum, n_windows, pl.c, nullptr, 0,
                                           want_xyzz ? nullptr : reinterpret_cast<Affine<FC>*>(out_aff), flag.as<int>(),
                                           want_xyzz ? reinterpret_cast<XYZZ<FC>*>(out_xyzz) : nullptr);

@@ -147,11 +147,12 @@ struct GroupApi {
   static int run_on_table(Context& c, Resource* t, uint64_t offset, const uint32_t* dscalars, uint64_t n, bool partial,
                           int slot = 0, const uint8_t* host_scalars = nullptr) {
     cudaStream_t st = slot ? c.stream2 : c.stream;
+    cudaStream_t lane = slot ? nullptr : c.stream_hi;  // the part-streamed form belongs to the first lane
     if (t->pre_c)
       return engine(slot).run(t->buf.as<Affine<F>>(), dscalars, n, st, partial, t->pre_c, (uint32_t)t->n,
-                              (uint32_t)offset, host_scalars, c.stream2);
+                              (uint32_t)offset, host_scalars, c.stream2, lane);
     return engine(slot).run(t->buf.as<Affine<F>>() + offset, dscalars, n, st, partial, msm_options().window_bits, 0, 0,
-                            host_scalars, c.stream2);
+                            host_scalars, c.stream2, lane);
   }
 
   // `count` independent MSMs on one table, alternating between two streams (each with its own

@@ -33,11 +33,15 @@ int zkp_msm_set_option(const char* name, int value) {
     msm_options().tree_items = value;
     return ZKP_OK;
   }
+  if (n == "parts" && value >= 0 && value <= 8) {  // point ranges of a part-streamed MSM (0 = automatic)
+    msm_options().parts = value;
+    return ZKP_OK;
+  }
   if (n == "tree_rounds" && value >= 0 && value <= 9) {  // affine rounds before the XYZZ chains take over
     msm_options().tree_rounds = value;
     return ZKP_OK;
   }
-  set_last_error("zkp_msm_set_option: unknown option or value (window_bits, accumulate 0..2, tree_items 0..256, tree_rounds 0..9)");
+  set_last_error("zkp_msm_set_option: unknown option or value (window_bits, accumulate 0..2, tree_items 0..256, tree_rounds 0..9, parts 0..8)");
   return ZKP_ERR_INVALID_ARGUMENT;
 }
 
