@@ -697,7 +697,9 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / steps,
                 "h2d_bytes_per_step": 32 * n * world, "d2h_bytes_per_step": 64 * world,
                 "path": ("zkp_g1_msm_table" if world == 1 else "zkp_g1_msm_multi_table") +
-                        ": device-resident point table (static SRS), scalars from pinned host memory",
+                        ": device-resident point table (static SRS), scalars from pinned host memory; part-streamed "
+                        "(4 point ranges growing 1.35x: range p+1 is uploaded and sorted on a side lane while range p "
+                        "accumulates into the one bucket set)",
                 "numa_node_of_rank0": numa_node},
         "gpu_launches": launches,
         "clocks": clocks,

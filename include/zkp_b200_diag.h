@@ -23,12 +23,13 @@ extern "C" {
 int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effective);
 /* Single-thread latency of one operation (ns): mode 0/1/2 = 1/2/4 independent Fp products per step,
  * 3 = XYZZ add (inlined products), 4 = XYZZ add (out-of-line products), 5 = mixed add, 6 = double;
- * 7 / 8 = XYZZ add on a quad of lanes (inlined / out-of-line products), 9 = double on a quad.
+ * 7 / 8 = XYZZ add on a quad of lanes (inlined / out-of-line products), 9 = double on a quad,
+ * 10 = Fp inversion (batched division steps, Mont256::inv), 11 = Fp inversion by binary extended Euclid.
  * The MSM's reduction tail is bounded by these, not by throughput. */
 int zkp_latency_probe(int mode, double* ns_per_op);
 /* Field-op self-test hooks used by tests/ (field: 0 = Fp, 1 = Fr, 2 = Fp2 with 64-byte elements c0 || c1 and
  * ops 2 / 3 / 4 only; op: 0 add, 1 sub, 2 mul, 3 inv, 4 sqr,
- * 5 Fermat inverse, 6 mul as 512-bit product + separate Montgomery reduction) */
+ * 5 Fermat inverse, 6 mul as 512-bit product + separate Montgomery reduction, 7 inverse by binary extended Euclid) */
 int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out);
 /* out[i] = a[i] + b[i] (group: 0 = G1, 1 = G2; 2 / 3 = the same through the quad-lane operations of
  * csrc/ec_quad.cuh) via XYZZ, result affine; exercises all edge cases */

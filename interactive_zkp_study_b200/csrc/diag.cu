@@ -45,7 +45,7 @@ __device__ __noinline__ uint32_t quad_probe(int mode, int iters) {
 }
 
 __global__ void latency_probe_kernel(int mode, int iters, uint32_t* out) {
-  if (mode >= 7) {  // one warp, quad operations: 7 add (inlined products), 8 add (out-of-line), 9 double (out-of-line)
+  if (mode >= 7 && mode <= 9) {  // one warp, quad operations: 7 add (inlined products), 8 add (out-of-line), 9 double (out-of-line)
     uint32_t s = mode == 7 ? quad_probe<Fp>(0, iters) : quad_probe<FpC>(mode == 8 ? 0 : 1, iters);
     if (threadIdx.x == 0) out[0] = s;
     return;
@@ -58,6 +58,11 @@ __global__ void latency_probe_kernel(int mode, int iters, uint32_t* out) {
 #pragma unroll
   for (int k = 0; k < 8; k++) y.v[k] = (0x85ebca6bu * (k + 3)) & (k == 7 ? 0x0fffffffu : 0xffffffffu);
   uint32_t s = 0;
+  if (mode >= 10) {  // 10: inversion by batched division steps (Mont256::inv), 11: binary extended Euclid
+    for (int it = 0; it < iters; it++) x[0] = mode == 10 ? (x[0] + y).inv() : (x[0] + y).inv_euclid();
+    out[0] = x[0].v[0];
+    return;
+  }
   if (mode <= 2) {
     for (int it = 0; it < iters; it++) {
       x[0] = x[0] * y;
@@ -219,6 +224,7 @@ __global__ void dbg_field_op_kernel(int op, const FE* a, const FE* b, uint64_t n
     case 2: r = x * y; break;
     case 3: r = x.inv(); break;
     case 5: r = x.inv_fermat(); break;
+    case 7: r = x.inv_euclid(); break;
     case 6: {  // the two-step product of the lazily reduced Fp2 arithmetic: 512-bit product, then one reduction
       uint32_t t[16];
       FE::mul_wide(x, y, t);
@@ -287,10 +293,10 @@ extern "C" {
 int zkp_latency_probe(int mode, double* ns_per_op) {
   return guarded([&](Context& c) {
     diag_events();
-    if (mode < 0 || mode > 9 || !ns_per_op) throw InvalidArgument("zkp_latency_probe: bad mode");
+    if (mode < 0 || mode > 11 || !ns_per_op) throw InvalidArgument("zkp_latency_probe: bad mode");
     ScopedDevBuf out;
     out.reserve(64);
-    const int iters = 2000;
+    const int iters = mode >= 10 ? 100 : 2000;
     latency_probe_kernel<<<1, 32, 0, c.stream>>>(mode, iters / 10, out.as<uint32_t>());
     CUDA_CHECK_LAUNCH();
     float best = 1e30f;
@@ -349,7 +355,7 @@ int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effecti
 
 int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out) {
   return guarded([&](Context& c) {
-    if (!a || !out || op < 0 || op > 6) throw InvalidArgument("zkp_dbg_field_op: bad argument");
+    if (!a || !out || op < 0 || op > 7) throw InvalidArgument("zkp_dbg_field_op: bad argument");
     if (n == 0) return;
     if (field < 0 || field > 2) throw InvalidArgument("zkp_dbg_field_op: field must be 0 (Fp), 1 (Fr) or 2 (Fp2)");
     const size_t sz = field == 2 ? 64 : 32;

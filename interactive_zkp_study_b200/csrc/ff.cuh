@@ -21,6 +21,7 @@
 #pragma once
 #include <cstdint>
 #include "bn254_params.cuh"
+#include "modinv30.cuh"
 
 namespace zkp {
 
@@ -579,11 +580,21 @@ struct __align__(16) Mont256 {
     return acc;
   }
 
-  // Inverse, inv(0) = 0 as in py_ecc's prime_field_inv.  Binary extended Euclid on the integer held in
-  // the limbs (shifts, adds and subtractions only: ~4x shorter than the 254-squaring Fermat chain for
-  // a lone thread), then one Montgomery product by R^3 to land back in Montgomery form:
-  // (aR)^-1 * R^3 * R^-1 = a^-1 R.
+  // Inverse, inv(0) = 0 as in py_ecc's prime_field_inv.  Batched division steps on the integer held in the
+  // limbs (modinv30.cuh: 30 steps on 32-bit registers per 2x2 matrix applied to the 270-bit values), then one
+  // Montgomery product by R^3 to land back in Montgomery form: (aR)^-1 * R^3 * R^-1 = a^-1 R.
   __device__ __noinline__ Mont256 inv() const {
+    if (is_zero()) return *this;
+    Mont256 r, r3;
+    modinv30::inverse<P>(v, r.v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r3.v[i] = P::R3_(i);
+    return r * r3;
+  }
+
+  // The inversion of rounds 1-2: binary extended Euclid (shifts, adds and subtractions only: ~4x shorter than the
+  // 254-squaring Fermat chain for a lone thread, ~2.5x longer than inv()).  Kept as an independent cross-check.
+  __device__ __noinline__ Mont256 inv_euclid() const {
     if (is_zero()) return *this;
     uint32_t u[8], w[8], x1[8], x2[8];
 #pragma unroll

@@ -49,8 +49,16 @@ def test_field_ops_bit_exact(native, field, mod):
     assert _unvec(native.dbg_field_op(field, 6, _vec(a[:500]), _vec(b[:500]), 500)) == [(x * y) % mod for x, y in zip(a[:500], b[:500])]
     m = 300
     got = _unvec(native.dbg_field_op(field, 3, _vec(a[:m]), None, m))
-    assert got == [bn254.inv(x, mod) for x in a[:m]]  # inv(0) == 0 as in py_ecc (binary extended Euclid)
+    assert got == [bn254.inv(x, mod) for x in a[:m]]  # inv(0) == 0 as in py_ecc (batched division steps, modinv30.cuh)
     assert _unvec(native.dbg_field_op(field, 5, _vec(a[:m]), None, m)) == got  # Fermat chain agrees
+    assert _unvec(native.dbg_field_op(field, 7, _vec(a[:m]), None, m)) == got  # binary extended Euclid agrees
+    # values whose Montgomery form a R mod p is small / has long runs of zeros or ones (the division steps look at
+    # the low bits of that integer), and small plain values
+    mont_small = [x * rinv % mod for x in (1, 2, 3, 1 << 30, (1 << 30) - 1, 1 << 60, (1 << 255) % mod, mod - 1, mod - 2,
+                                            (1 << 200) - 1, int("aaaaaaaa" * 7, 16))]
+    more = mont_small + [1, 2, 3, 5, 1 << 30, 1 << 31, 1 << 32, mod - 1, mod - 2, (mod + 1) // 2] + [rng.randrange(1 << k) for k in range(1, 254, 3)]
+    got = _unvec(native.dbg_field_op(field, 3, _vec(more), None, len(more)))
+    assert got == [bn254.inv(x, mod) for x in more]
 
 
 def test_fp2_ops_bit_exact(native):
