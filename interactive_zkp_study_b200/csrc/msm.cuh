@@ -613,7 +613,10 @@ __global__ void __launch_bounds__(WsFused<F>::SEG * 4) msm_ws2_fused_kernel(cons
     se[i] = E[base + i];
   }
   __syncthreads();
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index as a broadcast: the compiler then knows that `role` and `warp_live` are the same for the whole
+  // warp, the branches on them are uniform and the shuffles of the quad operations inside need no reconvergence
+  // guard (with threadIdx.x >> 5 every pair of SHFL sat between a WARPSYNC and an ENDCOLLECTIVE: 580 of them)
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const uint32_t role = warp & 1;
   const int ql = lane & 3;
   for (uint32_t m = seg; m > 1; m >>= 1) {
