@@ -24,7 +24,9 @@ int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effecti
 /* Single-thread latency of one operation (ns): mode 0/1/2 = 1/2/4 independent Fp products per step,
  * 3 = XYZZ add (inlined products), 4 = XYZZ add (out-of-line products), 5 = mixed add, 6 = double;
  * 7 / 8 = XYZZ add on a quad of lanes (inlined / out-of-line products), 9 = double on a quad,
- * 10 = Fp inversion (batched division steps, Mont256::inv), 11 = Fp inversion by binary extended Euclid.
+ * 10 = Fp inversion (batched division steps, Mont256::inv), 11 = Fp inversion by binary extended Euclid,
+ * 12-15 = pieces of the quad addition (without its edge-case tail / product levels only / four dependent products
+ * on a lone thread / the same with a broadcast after each).
  * The MSM's reduction tail is bounded by these, not by throughput. */
 int zkp_latency_probe(int mode, double* ns_per_op);
 /* Field-op self-test hooks used by tests/ (field: 0 = Fp, 1 = Fr, 2 = Fp2 with 64-byte elements c0 || c1 and

@@ -44,7 +44,70 @@ __device__ __noinline__ uint32_t quad_probe(int mode, int iters) {
   return acc.x.v[0] ^ acc.zzz.v[0];
 }
 
+// Where the time of a quad addition goes (modes 12-15, one warp): 12 = the addition without its edge-case tail,
+// 13 = only its four dependent select / product / broadcast levels, 14 = four dependent products on a lone
+// thread, 15 = four dependent products each followed by one broadcast.
+template <class F>
+__device__ __noinline__ uint32_t quad_bisect(int mode, int iters) {
+  using Q = Quad<F>;
+  const int ql = threadIdx.x & 3;
+  XYZZ<F> a, b;
+  for (int k = 0; k < 8; k++) {
+    uint32_t m = k == 7 ? 0x0fffffffu : 0xffffffffu;
+    a.x.v[k] = (0x9e3779b9u * (k + 1)) & m; a.y.v[k] = (0x9e3779b9u * (k + 9)) & m;
+    a.zz.v[k] = (0x9e3779b9u * (k + 17)) & m; a.zzz.v[k] = (0x9e3779b9u * (k + 25)) & m;
+    b.x.v[k] = (0x85ebca6bu * (k + 3)) & m; b.y.v[k] = (0x85ebca6bu * (k + 11)) & m;
+    b.zz.v[k] = (0x85ebca6bu * (k + 19)) & m; b.zzz.v[k] = (0x85ebca6bu * (k + 27)) & m;
+  }
+  for (int it = 0; it < iters; it++) {
+    if (mode == 12) {
+      F m1 = Q::sel(ql, a.x, b.x, a.y, b.y) * Q::sel(ql, b.zz, a.zz, b.zzz, a.zzz);
+      F u1 = Q::from(m1, 0), u2 = Q::from(m1, 1), s1 = Q::from(m1, 2), s2 = Q::from(m1, 3);
+      F p = u2 - u1, rr = s2 - s1;
+      F m2 = Q::sel(ql, p, a.zz, rr, a.zzz) * Q::sel(ql, p, b.zz, rr, b.zzz);
+      F pp = Q::from(m2, 0), r2 = Q::from(m2, 2);
+      F m3 = Q::sel(ql, p, m2, u1, p) * pp;
+      F ppp = Q::from(m3, 0), q = Q::from(m3, 2);
+      XYZZ<F> r;
+      r.x = r2 - ppp - q.dbl();
+      r.zz = Q::from(m3, 1);
+      F m4 = Q::sel(ql, s1, s1, rr, m2) * Q::sel(ql, ppp, ppp, q - r.x, ppp);
+      r.y = Q::from(m4, 2) - Q::from(m4, 0);
+      r.zzz = Q::from(m4, 3);
+      a = r;
+    } else if (mode == 13) {
+      F m1 = Q::sel(ql, a.x, b.x, a.y, b.y) * Q::sel(ql, b.zz, a.zz, b.zzz, a.zzz);
+      F u1 = Q::from(m1, 0), u2 = Q::from(m1, 1), s1 = Q::from(m1, 2), s2 = Q::from(m1, 3);
+      F m2 = Q::sel(ql, u1, a.zz, s1, a.zzz) * Q::sel(ql, u2, b.zz, s2, b.zzz);
+      F pp = Q::from(m2, 0), r2 = Q::from(m2, 2);
+      F m3 = Q::sel(ql, u1, m2, r2, s2) * pp;
+      F ppp = Q::from(m3, 0), q = Q::from(m3, 2);
+      a.zz = Q::from(m3, 1);
+      F m4 = Q::sel(ql, s1, s1, r2, m2) * Q::sel(ql, ppp, ppp, q, ppp);
+      a.x = Q::from(m4, 2);
+      a.y = Q::from(m4, 0);
+      a.zzz = Q::from(m4, 3);
+    } else if (mode == 14) {
+      a.x = a.x * b.x;
+      a.x = a.x * b.y;
+      a.x = a.x * b.zz;
+      a.x = a.x * b.zzz;
+    } else {
+      a.x = Q::from(a.x * b.x, 0);
+      a.x = Q::from(a.x * b.y, 1);
+      a.x = Q::from(a.x * b.zz, 2);
+      a.x = Q::from(a.x * b.zzz, 3);
+    }
+  }
+  return a.x.v[0] ^ a.zzz.v[0] ^ a.y.v[1] ^ a.zz.v[2];
+}
+
 __global__ void latency_probe_kernel(int mode, int iters, uint32_t* out) {
+  if (mode >= 12) {
+    uint32_t s = quad_bisect<FpC>(mode, iters);
+    if (threadIdx.x == 0) out[0] = s;
+    return;
+  }
   if (mode >= 7 && mode <= 9) {  // one warp, quad operations: 7 add (inlined products), 8 add (out-of-line), 9 double (out-of-line)
     uint32_t s = mode == 7 ? quad_probe<Fp>(0, iters) : quad_probe<FpC>(mode == 8 ? 0 : 1, iters);
     if (threadIdx.x == 0) out[0] = s;
@@ -58,7 +121,7 @@ __global__ void latency_probe_kernel(int mode, int iters, uint32_t* out) {
 #pragma unroll
   for (int k = 0; k < 8; k++) y.v[k] = (0x85ebca6bu * (k + 3)) & (k == 7 ? 0x0fffffffu : 0xffffffffu);
   uint32_t s = 0;
-  if (mode >= 10) {  // 10: inversion by batched division steps (Mont256::inv), 11: binary extended Euclid
+  if (mode >= 10 && mode <= 11) {  // 10: inversion by batched division steps (Mont256::inv), 11: binary extended Euclid
     for (int it = 0; it < iters; it++) x[0] = mode == 10 ? (x[0] + y).inv() : (x[0] + y).inv_euclid();
     out[0] = x[0].v[0];
     return;
@@ -293,10 +356,10 @@ extern "C" {
 int zkp_latency_probe(int mode, double* ns_per_op) {
   return guarded([&](Context& c) {
     diag_events();
-    if (mode < 0 || mode > 11 || !ns_per_op) throw InvalidArgument("zkp_latency_probe: bad mode");
+    if (mode < 0 || mode > 15 || !ns_per_op) throw InvalidArgument("zkp_latency_probe: bad mode");
     ScopedDevBuf out;
     out.reserve(64);
-    const int iters = mode >= 10 ? 100 : 2000;
+    const int iters = (mode == 10 || mode == 11) ? 100 : 2000;
     latency_probe_kernel<<<1, 32, 0, c.stream>>>(mode, iters / 10, out.as<uint32_t>());
     CUDA_CHECK_LAUNCH();
     float best = 1e30f;

@@ -29,6 +29,9 @@ struct Quad {
     for (int i = 0; i < WORDS; i++) out[i] = __shfl_sync(FULL, in[i], lane);
     return r;
   }
+  // lane ql of the quad takes a / b / c / d.  Written with masks: as nested conditionals ptxas turned the choice
+  // into four divergent paths per call (16 BSSY / BRA / BSYNC per addition, the lanes of a quad executing their
+  // copies one after the other) and the glue between the products cost 3.3 us of a 5.2 us addition.
   static ZKP_DEVINL F sel(int ql, const F& a, const F& b, const F& c, const F& d) {
     F r;
     const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
@@ -36,8 +39,12 @@ struct Quad {
     const uint32_t* pc = reinterpret_cast<const uint32_t*>(&c);
     const uint32_t* pd = reinterpret_cast<const uint32_t*>(&d);
     uint32_t* out = reinterpret_cast<uint32_t*>(&r);
+    const uint32_t m1 = 0u - ((uint32_t)ql & 1u), m2 = 0u - (((uint32_t)ql >> 1) & 1u);
 #pragma unroll
-    for (int i = 0; i < WORDS; i++) out[i] = ql == 0 ? pa[i] : ql == 1 ? pb[i] : ql == 2 ? pc[i] : pd[i];
+    for (int i = 0; i < WORDS; i++) {
+      const uint32_t lo = (pa[i] & ~m1) | (pb[i] & m1), hi = (pc[i] & ~m1) | (pd[i] & m1);
+      out[i] = (lo & ~m2) | (hi & m2);
+    }
     return r;
   }
 
