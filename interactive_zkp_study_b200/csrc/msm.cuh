@@ -374,13 +374,14 @@ struct AccMul {
     Fp ppp = mul<3>(pp_, pp);
     Fp q = mul<4>(a.x, pp);
     Fp x3 = sqr<5>(r) - ppp - q.dbl();
-    a.y = mul<6>(r, q - x3) - mul<7>(a.y, ppp);
+    if constexpr ((OUTLINE >> 10) & 1) a.y = fp_mulsub_outlined(r, q - x3, a.y, ppp);  // one reduction for both products
+    else a.y = mul<6>(r, q - x3) - mul<7>(a.y, ppp);
     a.x = x3;
     a.zz = mul<8>(a.zz, pp);
     a.zzz = mul<9>(a.zzz, ppp);
   }
 };
-static constexpr int MSM_ACC_OUTLINE = 0x3DB;  // products 0, 1, 3, 4, 6-9 out of line; the squarings (2, 5) inlined
+static constexpr int MSM_ACC_OUTLINE = 0x71B;  // products 0, 1, 3, 4, 8, 9 out of line; the squarings (2, 5) inlined; bit 10: Y3 = R (Q - X3) - Y1 PPP as one lazily reduced pair
 template <class F, int OUTLINE>
 ZKP_DEVINL void acc_madd(XYZZ<F>& a, const Affine<F>& p) {
   if constexpr (sizeof(F) == 32 && OUTLINE != 0) AccMul<OUTLINE>::madd(a, p);
@@ -645,27 +646,33 @@ __global__ void __launch_bounds__(WsFused<F>::SEG * 4) msm_ws2_fused_kernel(cons
   if (threadIdx.x == 32) E_out[blockIdx.x] = se[0];
 }
 
-// Horner over the window sums (one thread), to affine, out of Montgomery form.
+// Horner over the window sums, to affine, out of Montgomery form: one warp, every doubling / addition of the
+// chain on quads of lanes (all eight quads run the same operands: the chain is 254 doublings deep on a plain
+// table and nothing else is left to do, so what counts is the latency of one operation -- 1.9 us on a quad
+// against 3.3 us on a lone thread).  The inversion stays a lone-thread computation (every lane runs it).
 // out: canonical little-endian coordinates; flag = 1 when the result is the point at infinity.
 template <class F>
-__global__ void msm_final_kernel(const XYZZ<F>* __restrict__ window_sums, int W, int c, const XYZZ<F>* extra,
-                                 int n_extra, Affine<F>* __restrict__ out, int* __restrict__ inf_flag,
-                                 XYZZ<F>* __restrict__ out_xyzz) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  XYZZ<F> r = XYZZ<F>::inf();
-  for (int w = W - 1; w >= 0; w--) {
-    if (!r.is_inf())
-      for (int k = 0; k < c; k++) r = r.dbl();
-    r.add(window_sums[w]);
+__global__ void __launch_bounds__(32) msm_final_kernel(const XYZZ<F>* __restrict__ window_sums, int W, int c,
+                                                       const XYZZ<F>* extra, int n_extra, Affine<F>* __restrict__ out,
+                                                       int* __restrict__ inf_flag, XYZZ<F>* __restrict__ out_xyzz) {
+  if (blockIdx.x != 0) return;
+  const int ql = threadIdx.x & 3;
+  XYZZ<F> r = window_sums[W - 1];
+  for (int w = W - 2; w >= 0; w--) {
+    if (!r.is_inf())  // the same value on every lane: uniform
+      for (int k = 0; k < c; k++) r = Quad<F>::dbl(r, ql);
+    r = Quad<F>::add(r, window_sums[w], ql);
   }
-  for (int k = 0; k < n_extra; k++) r.add(extra[k]);
-  if (out_xyzz) *out_xyzz = r;
+  for (int k = 0; k < n_extra; k++) r = Quad<F>::add(r, extra[k], ql);
+  if (out_xyzz && threadIdx.x == 0) *out_xyzz = r;
   if (out) {
     Affine<F> a = r.to_affine();
-    *inf_flag = r.is_inf() ? 1 : 0;
     a.x = a.x.from_mont();
     a.y = a.y.from_mont();
-    *out = a;
+    if (threadIdx.x == 0) {
+      *inf_flag = r.is_inf() ? 1 : 0;
+      *out = a;
+    }
   }
 }
 
@@ -689,6 +696,9 @@ struct MsmOptions {
   int tree_items = 0;   // affine tree: most additions per thread and shared inversion (0 = default)
   int tree_rounds = 0;  // affine tree: rounds before the XYZZ chains take over (0 = default)
   int parts = 0;        // part-streamed MSM: point ranges per MSM (0 = 4 for host scalars, 1 for resident ones)
+  int reduce_radix = 0;     // weighted-sum recursion: items per thread of a wide level (0 = 8)
+  int wide_log2 = 0;        // log2 of the item count from which a level is a wide one (0 = 17)
+  int quad_log2 = 0;        // log2 of the radix-2 output count up to which the levels are fused on quads (0 = 12)
 };
 MsmOptions& msm_options();  // defined in msm_g1.cu
 
@@ -713,7 +723,7 @@ struct MsmEngine {
   }
   static constexpr int UPLOAD_CHUNKS = 4;
   cudaEvent_t ev_chunk[UPLOAD_CHUNKS] = {};
-  int reduce_L = 8;
+  int reduce_L = 16;  // measured at 2^20 (tools/reduce_sweep.py): radix 16 one wide level 3.20 ms, radix 8 3.25, radix 4 3.30
   uint32_t wide_threshold = 1u << 17;  // items (all windows) above which a level is throughput bound
   uint32_t quad_threshold = 1u << 12;  // radix-2 outputs (all windows) below which a level is latency bound
 
@@ -935,6 +945,10 @@ struct MsmEngine {
     const XYZZ<FC>* A = bk;
     const XYZZ<FC>* E = nullptr;
     int pp = 0;
+    const MsmOptions& mo = msm_options();
+    const int reduce_L = mo.reduce_radix ? mo.reduce_radix : this->reduce_L;
+    const uint32_t wide_threshold = mo.wide_log2 ? 1u << mo.wide_log2 : this->wide_threshold;
+    const uint32_t quad_threshold = mo.quad_log2 ? 1u << mo.quad_log2 : this->quad_threshold;
     while (n_in > 1) {
       // wide levels (many items): radix reduce_L running sums, fewest group operations per bucket;
       // middle levels: radix 2, one thread per output (still throughput bound);

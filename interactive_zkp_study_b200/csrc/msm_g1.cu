@@ -41,7 +41,19 @@ int zkp_msm_set_option(const char* name, int value) {
     msm_options().tree_rounds = value;
     return ZKP_OK;
   }
-  set_last_error("zkp_msm_set_option: unknown option or value (window_bits, accumulate 0..2, tree_items 0..256, tree_rounds 0..9, parts 0..8)");
+  if (n == "reduce_radix" && (value == 0 || value == 2 || value == 4 || value == 8 || value == 16 || value == 32)) {
+    msm_options().reduce_radix = value;  // items per thread of a wide level of the weighted-sum recursion
+    return ZKP_OK;
+  }
+  if (n == "wide_log2" && value >= 0 && value <= 31) {  // item count from which a level is a wide one
+    msm_options().wide_log2 = value;
+    return ZKP_OK;
+  }
+  if (n == "quad_log2" && value >= 0 && value <= 31) {  // radix-2 output count up to which levels are fused on quads
+    msm_options().quad_log2 = value;
+    return ZKP_OK;
+  }
+  set_last_error("zkp_msm_set_option: unknown option or value (window_bits, accumulate 0..2, tree_items 0..256, tree_rounds 0..9, parts 0..8, reduce_radix 0/2/4/8/16/32, wide_log2, quad_log2)");
   return ZKP_ERR_INVALID_ARGUMENT;
 }
 
