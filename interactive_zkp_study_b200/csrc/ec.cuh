@@ -23,6 +23,29 @@ struct __align__(16) Affine {
   ZKP_DEVINL Affine neg() const { return {x, y.neg()}; }
 };
 
+// a b - c d: the Y coordinate of every XYZZ formula.  The compact Fp flavour (reduction tail of the MSM, tables)
+// takes both products through ONE Montgomery reduction (fp2.cuh fp_mulsub_outlined: 200 instead of 272 limb-MACs).
+template <class F>
+ZKP_DEVINL F field_mulsub(const F& a, const F& b, const F& c, const F& d) {
+  return a * b - c * d;
+}
+template <>
+ZKP_DEVINL FpC field_mulsub<FpC>(const FpC& a, const FpC& b, const FpC& c, const FpC& d) {
+  Fp pa, pb, pc, pd;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    pa.v[i] = a.v[i];
+    pb.v[i] = b.v[i];
+    pc.v[i] = c.v[i];
+    pd.v[i] = d.v[i];
+  }
+  Fp pr = fp_mulsub_outlined(pa, pb, pc, pd);
+  FpC r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = pr.v[i];
+  return r;
+}
+
 template <class F>
 struct __align__(16) XYZZ {
   F x, y, zz, zzz;
@@ -45,7 +68,7 @@ struct __align__(16) XYZZ {
     F m = xx.dbl() + xx;
     XYZZ r;
     r.x = m.sqr() - s.dbl();
-    r.y = m * (s - r.x) - w * p.y;
+    r.y = field_mulsub(m, s - r.x, w, p.y);
     r.zz = v;
     r.zzz = w;
     return r;
@@ -62,7 +85,7 @@ struct __align__(16) XYZZ {
     F m = xx.dbl() + xx;
     XYZZ r;
     r.x = m.sqr() - s.dbl();
-    r.y = m * (s - r.x) - w * y;
+    r.y = field_mulsub(m, s - r.x, w, y);
     r.zz = v * zz;
     r.zzz = w * zzz;
     return r;
@@ -88,7 +111,7 @@ struct __align__(16) XYZZ {
     F ppp = pp_ * pp;
     F q = x * pp;
     F x3 = r.sqr() - ppp - q.dbl();
-    y = r * (q - x3) - y * ppp;
+    y = field_mulsub(r, q - x3, y, ppp);
     x = x3;
     zz = zz * pp;
     zzz = zzz * ppp;
@@ -113,7 +136,7 @@ struct __align__(16) XYZZ {
     F ppp = pp_ * pp;
     F q = u1 * pp;
     F x3 = r.sqr() - ppp - q.dbl();
-    y = r * (q - x3) - s1 * ppp;
+    y = field_mulsub(r, q - x3, s1, ppp);
     x = x3;
     zz = zz * o.zz * pp;
     zzz = zzz * o.zzz * ppp;
