@@ -294,6 +294,12 @@ __global__ void dbg_field_op_kernel(int op, const FE* a, const FE* b, uint64_t n
       r = FE::redc_wide(t);
       break;
     }
+    case 8:  // x y - (x + y)(x - y) through the lazily reduced product pair (Fp; any other field: two products)
+      if constexpr (FE::Params::MOD_(0) == FpParams::MOD_(0))
+        r = fp_mulsub_outlined(x, y, x + y, x - y);
+      else
+        r = x * y - (x + y) * (x - y);
+      break;
     default: r = x.sqr(); break;
   }
   out[i] = r.from_mont();
@@ -418,7 +424,7 @@ int zkp_imad_peak(int variant, double* gmacs_per_s, double* sm_clock_mhz_effecti
 
 int zkp_dbg_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out) {
   return guarded([&](Context& c) {
-    if (!a || !out || op < 0 || op > 7) throw InvalidArgument("zkp_dbg_field_op: bad argument");
+    if (!a || !out || op < 0 || op > 8) throw InvalidArgument("zkp_dbg_field_op: bad argument");
     if (n == 0) return;
     if (field < 0 || field > 2) throw InvalidArgument("zkp_dbg_field_op: field must be 0 (Fp), 1 (Fr) or 2 (Fp2)");
     const size_t sz = field == 2 ? 64 : 32;

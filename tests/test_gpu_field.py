@@ -47,6 +47,11 @@ def test_field_ops_bit_exact(native, field, mod):
     # the two-step form (512-bit product, then one Montgomery reduction) behind the lazily reduced Fp2 product
     assert _unvec(native.dbg_field_op(field, 6, _vec(pa), _vec(pa[::-1]), len(pa))) == [(x * y) % mod for x, y in zip(pa, pa[::-1])]
     assert _unvec(native.dbg_field_op(field, 6, _vec(a[:500]), _vec(b[:500]), 500)) == [(x * y) % mod for x, y in zip(a[:500], b[:500])]
+    # a b - c d with one reduction (the Y coordinate of every XYZZ formula): c = a + b, d = a - b, random and limb patterns
+    want = lambda xs, ys: [(x * y - (x + y) * (x - y)) % mod for x, y in zip(xs, ys)]
+    assert _unvec(native.dbg_field_op(field, 8, ab, bb, n)) == want(a, b)
+    assert _unvec(native.dbg_field_op(field, 8, _vec(pa), _vec(pa[::-1]), len(pa))) == want(pa, pa[::-1])
+    assert _unvec(native.dbg_field_op(field, 8, _vec(pats), _vec(pats[::-1]), len(pats))) == want(pats, pats[::-1])
     m = 300
     got = _unvec(native.dbg_field_op(field, 3, _vec(a[:m]), None, m))
     assert got == [bn254.inv(x, mod) for x in a[:m]]  # inv(0) == 0 as in py_ecc (batched division steps, modinv30.cuh)
