@@ -116,7 +116,10 @@ int zkp_msm_set_window_bits(int c);
 /* Engine tunables for measurements by name (0 = automatic): "window_bits" as above; "accumulate" 1 = XYZZ chains
  * (the default), 2 = affine pairwise tree with shared inversions for buckets of up to 511 entries (csrc/msm_tree.cuh;
  * same results, measured slower on B200 and therefore opt-in); "tree_rounds" 1..9 affine rounds before the XYZZ
- * chains take over, "tree_items" most additions per thread under one shared inversion. */
+ * chains take over, "tree_items" most additions per thread under one shared inversion; "parts" 1..8 point ranges of
+ * the part-streamed form (host scalars: upload + sort of range p+1 under the accumulation of range p; 0 = 4 ranges
+ * from 2^18 points); "reduce_radix" 2/4/8/16/32 items per thread of a wide level of the bucket reduction (0 = 16),
+ * "wide_log2" / "quad_log2" the item counts at which the wide and the quad-fused levels take over (0 = 17 / 12). */
 int zkp_msm_set_option(const char* name, int value);
 
 /* ---- multi-GPU: points sharded by contiguous range, one process per GPU -----------------
