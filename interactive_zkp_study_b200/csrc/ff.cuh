@@ -48,6 +48,25 @@ ZKP_DEVINL uint32_t mad_lanes(uint32_t (&acc)[8], uint32_t m0, uint32_t m1, uint
   return c;
 }
 
+// The same with the carry out added straight into `top` (the limb above the lanes, held by the other accumulator):
+// one IADD3.X.  Returned as a value and added by the caller (`Y[7] += c`) ptxas made it VIADD + predicated IMAD.MOV +
+// IMAD.MOV.U32 -- two of them on the multiplier pipe, 32 per product.
+ZKP_DEVINL void mad_lanes_top(uint32_t (&acc)[8], uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3,
+                                  uint32_t b, uint32_t& top) {
+  asm("mad.lo.cc.u32   %0, %9,  %13, %0;\n\t"
+      "madc.hi.cc.u32  %1, %9,  %13, %1;\n\t"
+      "madc.lo.cc.u32  %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32  %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32  %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
+      "addc.u32        %8, %8, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+        "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+      : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
+}
+
 // x0 += left (one limb below the first lane of acc); the carry of that add enters acc's
 // first lane, then acc += {m0..m3} * b.  The top lane cannot carry out (see ff.cuh header:
 // Y * 2^32 <= T < 2^288).
@@ -139,6 +158,61 @@ ZKP_DEVINL uint32_t mad_lanes_from(uint32_t (&acc)[8], uint32_t m0, uint32_t m1,
   return c;  // K == 4: no lane takes a product
 }
 
+template <int K>
+ZKP_DEVINL void mad_lanes_from_top(uint32_t (&acc)[8], uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t b,
+                                   uint32_t& top) {
+  if constexpr (K == 0) {
+    asm(
+        "mad.lo.cc.u32   %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32  %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32  %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32  %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32  %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
+        "addc.u32        %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+          "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+        : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
+  }
+  else if constexpr (K == 1) {
+    asm(
+        "mad.lo.cc.u32   %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32  %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32  %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
+        "addc.u32        %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+          "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+        : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
+  }
+  else if constexpr (K == 2) {
+    asm(
+        "mad.lo.cc.u32   %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
+        "addc.u32        %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+          "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+        : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
+  }
+  else if constexpr (K == 3) {
+    asm(
+        "mad.lo.cc.u32   %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
+        "addc.u32        %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+          "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+        : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(b));
+  }
+  // K == 4: no lane takes a product
+}
+
+
 // x0 += left, the carry ripples through the lanes below K and enters the product chain of lanes K..3
 template <int K>
 ZKP_DEVINL void mad_lanes_cin_from(uint32_t& x0, uint32_t left, uint32_t (&acc)[8], uint32_t m0, uint32_t m1, uint32_t m2,
@@ -210,13 +284,11 @@ template <class P>
 ZKP_DEVINL void mont_row(uint32_t (&X)[8], uint32_t (&Y)[8], uint32_t left, const uint32_t (&a)[8],
                          uint32_t bi) {
   mad_lanes_cin(X[0], left, Y, a[1], a[3], a[5], a[7], bi);
-  uint32_t cx = mad_lanes(X, a[0], a[2], a[4], a[6], bi);
-  Y[7] += cx;
+  mad_lanes_top(X, a[0], a[2], a[4], a[6], bi, Y[7]);
   uint32_t q = X[0] * P::N0INV;
-  cx = mad_lanes(X, P::MOD_(0), P::MOD_(2), P::MOD_(4), P::MOD_(6), q);
+  mad_lanes_top(X, P::MOD_(0), P::MOD_(2), P::MOD_(4), P::MOD_(6), q, Y[7]);  // Y[7] + carry <= its final value: no overflow
   uint32_t cy = mad_lanes(Y, P::MOD_(1), P::MOD_(3), P::MOD_(5), P::MOD_(7), q);
   (void)cy;  // provably 0
-  Y[7] += cx;
 }
 
 // One row of the dedicated squaring: row I multiplies a_I by the limbs {a_I, 2 a_{I+1}, ...} of
@@ -226,13 +298,11 @@ template <class P, int I>
 ZKP_DEVINL void mont_row_sq(uint32_t (&X)[8], uint32_t (&Y)[8], uint32_t left, const uint32_t (&m)[8], uint32_t bi) {
   constexpr int KX = (I + 1) / 2, KY = I / 2;  // first lane of X (even limbs) / Y (odd limbs) that takes a product
   mad_lanes_cin_from<KY>(X[0], left, Y, m[1], m[3], m[5], m[7], bi);
-  uint32_t cx = mad_lanes_from<KX>(X, m[0], m[2], m[4], m[6], bi);
-  Y[7] += cx;
+  mad_lanes_from_top<KX>(X, m[0], m[2], m[4], m[6], bi, Y[7]);
   uint32_t q = X[0] * P::N0INV;
-  cx = mad_lanes(X, P::MOD_(0), P::MOD_(2), P::MOD_(4), P::MOD_(6), q);
+  mad_lanes_top(X, P::MOD_(0), P::MOD_(2), P::MOD_(4), P::MOD_(6), q, Y[7]);
   uint32_t cy = mad_lanes(Y, P::MOD_(1), P::MOD_(3), P::MOD_(5), P::MOD_(7), q);
   (void)cy;
-  Y[7] += cx;
 }
 
 }  // namespace detail
@@ -430,14 +500,14 @@ struct __align__(16) Mont256 {
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
       detail::mad_lanes_cin(E[0], left, O, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
-      O[7] += detail::mad_lanes(E, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+      detail::mad_lanes_top(E, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i], O[7]);
       T[i] = E[0];
       left = E[1];
 #pragma unroll
       for (int k = 0; k < 6; k++) E[k] = E[k + 2];
       E[6] = E[7] = 0;
       detail::mad_lanes_cin(O[0], left, E, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
-      E[7] += detail::mad_lanes(O, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1]);
+      detail::mad_lanes_top(O, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1], E[7]);
       T[i + 1] = O[0];
       left = O[1];
 #pragma unroll
@@ -462,10 +532,9 @@ struct __align__(16) Mont256 {
   static ZKP_DEVINL void redc_row(uint32_t (&X)[8], uint32_t (&Y)[8], uint32_t& left, const uint32_t (&T)[16]) {
     detail::add_cin(X[0], left, Y);
     uint32_t q = X[0] * P::N0INV;
-    uint32_t cx = detail::mad_lanes(X, P::MOD_(0), P::MOD_(2), P::MOD_(4), P::MOD_(6), q);
+    detail::mad_lanes_top(X, P::MOD_(0), P::MOD_(2), P::MOD_(4), P::MOD_(6), q, Y[7]);
     uint32_t cy = detail::mad_lanes(Y, P::MOD_(1), P::MOD_(3), P::MOD_(5), P::MOD_(7), q);
     (void)cy;
-    Y[7] += cx;
     left = X[1];
 #pragma unroll
     for (int k = 0; k < 6; k++) X[k] = X[k + 2];
