@@ -13,7 +13,11 @@
 // round in registers, first / last round straight from / to global memory) was built and measured in round 2:
 // 0.27 - 0.32 ms at 2^20 against 0.24 ms for the radix-4 rounds below (its 8 scattered loads + 7 twiddle
 // loads per thread stall on the load queue, ncu: lg_throttle 0.9, long_scoreboard 2.1, no_instruction 1.1 per
-// issue) and was not kept.  Twiddles omega^i, i < n/2, are
+// issue) and was not kept.  Also measured and not kept (round 2, after the field product had been brought to the
+// pipe's floor): smaller tiles (2^8 elements = one warp per block, no inter-warp barrier, 8 + 8 + 6 stages at
+// 2^22: 0.868 ms against 0.909; 2^20 0.236 against 0.232; 2^24 3.65 against 3.69 -- a wash) and stage counts
+// spread evenly over the passes (2^22 as 8 + 7 + 7: 0.924 ms; 2^24 as 8 + 8 + 8: 3.65): a stage costs the same
+// wherever it runs, the pass overhead is small.  Twiddles omega^i, i < n/2, are
 // precomputed on the device in Montgomery form and cached per (omega, n); because they are
 // Montgomery constants, the data keeps whatever form it came in (canonical host data needs no
 // conversion).  The n^-1 factor of the inverse and the coset scalings are fused into the
