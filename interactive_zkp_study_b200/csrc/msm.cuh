@@ -382,9 +382,54 @@ struct AccMul {
   }
 };
 static constexpr int MSM_ACC_OUTLINE = 0x71B;  // products 0, 1, 3, 4, 8, 9 out of line; the squarings (2, 5) inlined; bit 10: Y3 = R (Q - X3) - Y1 PPP as one lazily reduced pair
+// The G2 flavour of the same loop body: XYZZ::madd with the two squarings through inlined Fp products
+// (Fp2::sqr_inline_products); the eight Fp2 products stay calls of the shared lazily reduced body.
+struct AccMul2 {
+  // XYZZ::dbl_affine with the same squarings (the rare P + P case; kept in the same style so that the whole loop
+  // body is compiled under one pipe balance)
+  static ZKP_DEVINL XYZZ<Fp2> dbl_affine(const Affine<Fp2>& p) {
+    Fp2 u = p.y.dbl();
+    Fp2 v = u.sqr_inline_products();
+    Fp2 w = fp2_mul_inline(u, v);
+    Fp2 s = fp2_mul_inline(p.x, v);
+    Fp2 xx = p.x.sqr_inline_products();
+    Fp2 m = xx.dbl() + xx;
+    XYZZ<Fp2> r;
+    r.x = m.sqr_inline_products() - s.dbl();
+    r.y = fp2_mul_inline(m, s - r.x) - fp2_mul_inline(w, p.y);
+    r.zz = v;
+    r.zzz = w;
+    return r;
+  }
+  static ZKP_DEVINL void madd(XYZZ<Fp2>& a, const Affine<Fp2>& p) {
+    if (p.is_inf()) return;
+    if (a.is_inf()) {
+      a.x = p.x; a.y = p.y; a.zz = Fp2::one(); a.zzz = Fp2::one();
+      return;
+    }
+    Fp2 u2 = p.x * a.zz;
+    Fp2 s2 = p.y * a.zzz;
+    Fp2 pp_ = u2 - a.x;
+    Fp2 r = s2 - a.y;
+    if (pp_.is_zero()) {
+      if (r.is_zero()) a = dbl_affine(p);
+      else a = XYZZ<Fp2>::inf();
+      return;
+    }
+    Fp2 pp = pp_.sqr_inline_products();
+    Fp2 ppp = pp_ * pp;
+    Fp2 q = a.x * pp;
+    Fp2 x3 = r.sqr_inline_products() - ppp - q.dbl();
+    a.y = r * (q - x3) - a.y * ppp;
+    a.x = x3;
+    a.zz = a.zz * pp;
+    a.zzz = a.zzz * ppp;
+  }
+};
 template <class F, int OUTLINE>
 ZKP_DEVINL void acc_madd(XYZZ<F>& a, const Affine<F>& p) {
   if constexpr (sizeof(F) == 32 && OUTLINE != 0) AccMul<OUTLINE>::madd(a, p);
+  else if constexpr (sizeof(F) == 64 && OUTLINE != 0) AccMul2::madd(a, p);
   else a.madd(p);
 }
 
