@@ -642,21 +642,31 @@ __global__ void __launch_bounds__(64) msm_ws2_kernel(const XYZZ<F>* __restrict__
 // instead of sixteen launches each two additions deep on a lone thread.
 template <class F>
 struct WsFused {
-  static constexpr int SEG = sizeof(F) == 32 ? 128 : 64;  // items per block: 2 * SEG * sizeof(XYZZ) = 32 KB
+  static constexpr int SEG = sizeof(F) == 32 ? 128 : 64;  // items per block
+  // G1: 256 threads, so that the kernel may use 168 registers -- under the 128-register cap of 512 threads it
+  // spilled 800 bytes into a latency-bound loop; the first level (64 chunks x 2 roles x 4 lanes) then takes two
+  // sweeps, every later level one.  G2 needs the 255-register limit either way and keeps 4 threads per item.
+  static constexpr int THREADS = sizeof(F) == 32 ? SEG * 2 : SEG * 4;
+  static constexpr int SMEM = 3 * SEG * (int)sizeof(XYZZ<F>);  // current level (A, E: 2 SEG items) + next level (SEG items)
 };
 template <class F>
-__global__ void __launch_bounds__(WsFused<F>::SEG * 4) msm_ws2_fused_kernel(const XYZZ<F>* __restrict__ A,
+__global__ void __launch_bounds__(WsFused<F>::THREADS) msm_ws2_fused_kernel(const XYZZ<F>* __restrict__ A,
                                                                             const XYZZ<F>* __restrict__ E, uint32_t seg,
                                                                             XYZZ<F>* __restrict__ A_out,
                                                                             XYZZ<F>* __restrict__ E_out) {
   extern __shared__ uint4 ws_smem[];
-  XYZZ<F>* sa = reinterpret_cast<XYZZ<F>*>(ws_smem);
-  XYZZ<F>* se = sa + WsFused<F>::SEG;
+  constexpr int SEG = WsFused<F>::SEG;
+  // a level reads (ca, ce) and writes (na, ne), half as many items: no operand is overwritten inside a level and
+  // one barrier per level is enough; then the two pairs swap (SEG + SEG items in the first, SEG/2 + SEG/2 in the second)
+  XYZZ<F>* ca = reinterpret_cast<XYZZ<F>*>(ws_smem);
+  XYZZ<F>* ce = ca + SEG;
+  XYZZ<F>* na = ce + SEG;
+  XYZZ<F>* ne = na + SEG / 2;
   const uint64_t base = (uint64_t)blockIdx.x * seg;
   if (!E) E = A;  // first level of the recursion: E_i = A_i (bucket b weighs b + 1)
   for (uint32_t i = threadIdx.x; i < seg; i += blockDim.x) {
-    sa[i] = A[base + i];
-    se[i] = E[base + i];
+    ca[i] = A[base + i];
+    ce[i] = E[base + i];
   }
   __syncthreads();
   // the warp index as a broadcast: the compiler then knows that `role` and `warp_live` are the same for the whole
@@ -665,30 +675,30 @@ __global__ void __launch_bounds__(WsFused<F>::SEG * 4) msm_ws2_fused_kernel(cons
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const uint32_t role = warp & 1;
   const int ql = lane & 3;
+  const uint32_t per_sweep = (blockDim.x >> 6) * 8;  // chunks served at once: a role-0 and a role-1 warp per 8 chunks
   for (uint32_t m = seg; m > 1; m >>= 1) {
     const uint32_t chunks = m >> 1;
-    uint32_t chunk = (warp >> 1) * 8 + (lane >> 2);
-    const bool warp_live = (warp >> 1) * 8 < chunks;  // warp-uniform: whole warps drop out as the level narrows
-    const bool live = chunk < chunks;
-    if (!live) chunk = chunks - 1;                    // partial warp: keep all lanes in the shuffles
-    XYZZ<F> r;
-    if (warp_live) {
+    for (uint32_t first = (warp >> 1) * 8; first < chunks; first += per_sweep) {  // warp-uniform bounds
+      uint32_t chunk = first + (lane >> 2);
+      const bool live = chunk < chunks;
+      if (!live) chunk = chunks - 1;  // partial warp: keep all lanes in the shuffles
+      XYZZ<F> r;
       if (role == 0) {
-        r = Quad<F>::dbl(Quad<F>::add(sa[2 * chunk], sa[2 * chunk + 1], ql), ql);
+        r = Quad<F>::dbl(Quad<F>::add(ca[2 * chunk], ca[2 * chunk + 1], ql), ql);
+        if (live && ql == 0) na[chunk] = r;
       } else {
-        r = Quad<F>::add(se[2 * chunk], se[2 * chunk + 1], ql);
-        r = Quad<F>::add(r, sa[2 * chunk + 1], ql);
+        r = Quad<F>::add(ce[2 * chunk], ce[2 * chunk + 1], ql);
+        r = Quad<F>::add(r, ca[2 * chunk + 1], ql);
+        if (live && ql == 0) ne[chunk] = r;
       }
     }
-    __syncthreads();  // every operand of this level has been read
-    if (warp_live && live && ql == 0) {
-      if (role == 0) sa[chunk] = r;
-      else se[chunk] = r;
-    }
     __syncthreads();
+    // swap: the level after reads what was just written and writes a quarter as many items into the old inputs' space
+    XYZZ<F>* t = ca; ca = na; na = t;
+    t = ce; ce = ne; ne = t;
   }
-  if (threadIdx.x == 0) A_out[blockIdx.x] = sa[0];
-  if (threadIdx.x == 32) E_out[blockIdx.x] = se[0];
+  if (threadIdx.x == 0) A_out[blockIdx.x] = ca[0];
+  if (threadIdx.x == 32) E_out[blockIdx.x] = ce[0];
 }
 
 // Horner over the window sums, to affine, out of Montgomery form: one warp, every doubling / addition of the
@@ -1013,7 +1023,7 @@ struct MsmEngine {
       if (wide)
         msm_ws_level_kernel<FC><<<ceil_div((uint64_t)T * n_windows, 64), 64, 0, st>>>(A, E, n_in, L, logL, n_windows, Ao, Eo);
       else if (fused)
-        msm_ws2_fused_kernel<FC><<<T * n_windows, WsFused<FC>::SEG * 4, 2 * WsFused<FC>::SEG * sizeof(XYZZ<FC>), st>>>(A, E, L, Ao, Eo);
+        msm_ws2_fused_kernel<FC><<<T * n_windows, WsFused<FC>::THREADS, WsFused<FC>::SMEM, st>>>(A, E, L, Ao, Eo);
       else
         msm_ws2_kernel<FC><<<ceil_div((uint64_t)ceil_div((uint64_t)T * n_windows, 32) * 64, 64), 64, 0, st>>>(A, E, n_in, n_windows, Ao, Eo);
       CUDA_CHECK_LAUNCH();
