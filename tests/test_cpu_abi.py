@@ -73,3 +73,23 @@ def test_oracle_shim_never_masquerades_as_py_ecc():
             importlib.import_module("py_ecc")
     from interactive_zkp_study_b200 import compat
     assert compat.HAVE_PY_ECC is False or "site-packages" in sys.modules["py_ecc"].__file__
+
+
+def test_engine_options_are_validated_by_name_and_range():
+    """zkp_msm_set_option is host-only state: every documented name is accepted with 0 (= automatic) and with a
+    value in range, anything else is refused with ZKP_ERR_INVALID_ARGUMENT and an error text (no GPU needed)."""
+    from interactive_zkp_study_b200 import _lib
+    lib = _lib.load_library()
+    good = {"window_bits": 16, "accumulate": 2, "tree_items": 64, "tree_rounds": 3, "parts": 4,
+            "reduce_radix": 8, "wide_log2": 15, "quad_log2": 14}
+    try:
+        for name, value in good.items():
+            assert lib.zkp_msm_set_option(name.encode(), value) == 0, name
+        for name, value in (("reduce_radix", 3), ("reduce_radix", 64), ("accumulate", 3), ("parts", 9),
+                            ("window_bits", 21), ("wide_log2", 32), ("no_such_option", 1)):
+            assert lib.zkp_msm_set_option(name.encode(), value) == -3, (name, value)   # ZKP_ERR_INVALID_ARGUMENT
+            assert lib.zkp_last_error()
+        assert lib.zkp_msm_set_option(None, 0) == -3
+    finally:
+        for name in good:
+            assert lib.zkp_msm_set_option(name.encode(), 0) == 0
