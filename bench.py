@@ -44,6 +44,12 @@ MACS_PER_MULSUB = 2 * 64 + 72              # a b - c d with one reduction (fp2.c
 # R (Q - X3) - Y1 PPP as one lazily reduced pair = 1232 limb-MACs (1304 with every product reduced on its own)
 MADD_MACS = 6 * MACS_PER_FP_MUL + 2 * MACS_PER_FP_SQR + MACS_PER_MULSUB
 MADD_MACS_PLAIN = 8 * MACS_PER_FP_MUL + 2 * MACS_PER_FP_SQR
+XYZZ_ADD_MACS = 12 * MACS_PER_FP_MUL + MACS_PER_MULSUB     # full addition in the compact flavour (squarings as products)
+
+
+def BUCKETS_TOTAL(pre_c):
+    """Buckets the reduction walks: one set of 2^(c-1) on a window-precomputed table, 16 sets of 2^15 on a plain one."""
+    return (1 << (pre_c - 1)) if pre_c else 16 * (1 << 15)
 MODEL_ACC_MACS_PER_POINT = 160 * MACS_PER_FP_MUL  # SURVEY model: 16 windows x 10 Fp-mul (XYZZ mixed add) = 21 760
 M64 = (1 << 64) - 1
 
@@ -658,6 +664,11 @@ def run_ours(args):
         "peaks_gmacs": peak,
         "whole_msm": {"macs_per_point_model": msm_macs_per_point(n),
                       "frac": (n * msm_macs_per_point(n) / (msm_us / steps * 1e-6) / 1e12) / peak_t,
+                      # the limb-MACs the whole MSM really executes: the mixed additions above + two full XYZZ additions
+                      # (12 products + the lazily reduced pair = 1832) per bucket of the reduction
+                      "macs_per_point_executed": W_actual * MADD_MACS + 2.0 * XYZZ_ADD_MACS * BUCKETS_TOTAL(pre_c) / n,
+                      "frac_executed": ((n * W_actual * MADD_MACS + 2.0 * XYZZ_ADD_MACS * BUCKETS_TOTAL(pre_c))
+                                        / (msm_us / steps * 1e-6) / 1e12) / peak_t,
                       "note": "SURVEY 8d model (16 windows + amortised bucket reduction, squarings as products) over the whole MSM time"},
         "hbm_view": {"algorithmic_bytes_per_launch": n * W_actual * 68,
                      "achieved_gbs": n * W_actual * 68 / acc_s / 1e9,
